@@ -351,9 +351,18 @@ def _polish(out, P, q, E, e, G, h, s, max_rounds=40):
         Nn = Vt[rk:].T
         if Nn.shape[1]:
             Hr = Nn.T @ P @ Nn
-            w = np.linalg.solve(Hr, -Nn.T @ (P @ z_p + q))
+
+            def _rsolve(b):
+                # the G2 variant has cost-free variables -> reduced Hessian only PSD there
+                try:
+                    if np.linalg.cond(Hr) < 1e13:
+                        return np.linalg.solve(Hr, b)
+                except np.linalg.LinAlgError:
+                    pass
+                return np.linalg.lstsq(Hr, b, rcond=1e-12)[0]
+            w = _rsolve(-Nn.T @ (P @ z_p + q))
             z = z_p + Nn @ w
-            z = z + Nn @ np.linalg.solve(Hr, -Nn.T @ (P @ z + q))      # one refinement
+            z = z + Nn @ _rsolve(-Nn.T @ (P @ z + q))      # one refinement
         else:
             z = z_p
         lam_a = np.linalg.lstsq(C.T, -(P @ z + q), rcond=None)[0][p:] if na else np.zeros(0)

@@ -1,0 +1,429 @@
+// C ABI of librtmpc_b200.so (see include/rtmpc.h).  Host-side glue only: uploads the
+// once-per-problem data, picks the kernel instantiation, launches on the caller's stream.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rtmpc_ipm.cuh"
+#include "rtmpc_loop.cuh"
+
+using namespace rtmpc;
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(const char* what, cudaError_t e = cudaSuccess) {
+    g_err = what;
+    if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+    return -1;
+}
+#define CU(call)                                                    \
+    do {                                                            \
+        cudaError_t _e = (call);                                    \
+        if (_e != cudaSuccess) return fail(#call, _e);              \
+    } while (0)
+
+struct rtmpc_qp {
+    QPDev dev;
+    std::vector<void*> allocs;
+    int bs = 0, r = 0, wpb = 8;
+    size_t smem = 0;
+    int device = 0, num_sms = 0;
+    // staging for the host-buffer entry point (grow-only)
+    int cap = 0;
+    double *s_x = nullptr, *s_ref = nullptr, *s_z = nullptr, *s_U = nullptr;
+    int *s_sel = nullptr, *s_status = nullptr, *s_iters = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+template <typename T>
+static int upload(rtmpc_qp* q, const T* src, size_t count, const T** dst) {
+    *dst = nullptr;
+    if (!src || count == 0) return 0;
+    void* p = nullptr;
+    CU(cudaMalloc(&p, count * sizeof(T)));
+    q->allocs.push_back(p);
+    CU(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = static_cast<const T*>(p);
+    return 0;
+}
+
+typedef void (*ipm_fn)(QPDev, int, const double*, const double*, const int*, int, double*, double*, int*, int*);
+struct KernelChoice { int bs, r; ipm_fn fn; };
+static const KernelChoice kChoices[] = {
+    {2, 4, ipm_solve_kernel<2, 4>},   {3, 9, ipm_solve_kernel<3, 9>},   {3, 16, ipm_solve_kernel<3, 16>},
+    {4, 24, ipm_solve_kernel<4, 24>}, {5, 32, ipm_solve_kernel<5, 32>},
+};
+
+static const KernelChoice* pick_kernel(int n, int mpad) {
+    const int bs_need = (n + 6) / 7, r_need = mpad / 32;
+    for (const auto& c : kChoices)
+        if (c.bs >= bs_need && c.r >= r_need) return &c;
+    return nullptr;
+}
+
+extern "C" {
+
+int rtmpc_abi_version(void) { return RTMPC_ABI_VERSION; }
+const char* rtmpc_last_error(void) { return g_err.c_str(); }
+int64_t rtmpc_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int rtmpc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { g_err = "cudaGetDeviceCount failed: no CUDA device"; return -1; }
+    return n;
+}
+int rtmpc_set_device(int device) {
+    CU(cudaSetDevice(device));
+    return 0;
+}
+
+int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
+    if (!d || !out) return fail("rtmpc_qp_create: null argument");
+    *out = nullptr;
+    if (d->n < 1 || d->n > 32 || d->npad < d->n || d->npad > 32 || (d->npad & 3))
+        return fail("rtmpc_qp_create: need 1 <= n <= npad <= 32 and npad % 4 == 0");
+    if (d->nx < 1 || d->nx > 8 || d->nu < 1 || d->nu > 4) return fail("rtmpc_qp_create: need nx <= 8, nu <= 4");
+    if (d->mpad < 32 || (d->mpad & 31) || d->m > d->mpad) return fail("rtmpc_qp_create: mpad must be a multiple of 32 >= m");
+    const KernelChoice* kc = pick_kernel(d->n, d->mpad);
+    if (!kc) return fail("rtmpc_qp_create: problem too large for the compiled kernel set (mpad <= 1024)");
+    rtmpc_qp* q = new rtmpc_qp();
+    CU(cudaGetDevice(&q->device));
+    CU(cudaDeviceGetAttribute(&q->num_sms, cudaDevAttrMultiProcessorCount, q->device));
+    QPDev& P = q->dev;
+    std::memset(&P, 0, sizeof(P));
+    P.nx = d->nx; P.nu = d->nu; P.N = d->N; P.n = d->n; P.npad = d->npad; P.m = d->m; P.mpad = d->mpad;
+    P.np = d->np; P.nz = d->nz; P.nss = d->nss;
+    P.gs = d->npad + 2;
+    P.ss = d->npad + 1;
+    P.va_len = ((d->mpad > d->nz ? d->mpad : d->nz) + 1) & ~1;
+    P.s_floor = d->s_floor; P.sc_b = d->sc_b; P.max_iter = d->max_iter > 0 ? d->max_iter : 60;
+    int mtot = 0;
+    for (int i = 0; i < d->mpad; ++i) mtot += (d->has_lo[i] ? 1 : 0) + (d->has_up[i] ? 1 : 0);
+    P.mtot = mtot > 0 ? mtot : 1;
+    const size_t nn = (size_t)d->npad * d->npad, mn = (size_t)d->mpad * d->npad;
+    int rc = 0;
+    rc |= upload(q, d->Hs, nn, &P.Hs);
+    rc |= upload(q, d->Hinv, nn, &P.Hinv);
+    rc |= upload(q, d->G, mn, &P.G);
+    rc |= upload(q, d->Y, mn, &P.Y);
+    rc |= upload(q, d->Fx, (size_t)d->npad * d->nx, &P.Fx);
+    rc |= upload(q, d->Fr, (size_t)d->npad * d->nx, &P.Fr);
+    rc |= upload(q, d->lo0, (size_t)d->mpad, &P.lo0);
+    rc |= upload(q, d->up0, (size_t)d->mpad, &P.up0);
+    rc |= upload(q, d->Lx, (size_t)d->mpad * d->nx, &P.Lx);
+    rc |= upload(q, d->Ux, (size_t)d->mpad * d->nx, &P.Ux);
+    rc |= upload(q, d->has_lo, (size_t)d->mpad, &P.has_lo);
+    rc |= upload(q, d->has_up, (size_t)d->mpad, &P.has_up);
+    rc |= upload(q, d->parC, (size_t)d->np * d->nx, &P.parC);
+    rc |= upload(q, d->parh, (size_t)d->np, &P.parh);
+    rc |= upload(q, d->Dscale, (size_t)d->npad, &P.D);
+    rc |= upload(q, d->Phi, (size_t)d->nz * d->npad, &P.Phi);
+    rc |= upload(q, d->Psi, (size_t)d->nz * d->nx, &P.Psi);
+    rc |= upload(q, d->Kss, (size_t)d->nu * d->nx, &P.Kss);
+    if (rc) { rtmpc_qp_destroy(q); return -1; }
+    if (P.nss > 0 && !P.Kss) { rtmpc_qp_destroy(q); return fail("rtmpc_qp_create: Kss required when nss > 0"); }
+
+    q->bs = kc->bs; q->r = kc->r;
+    int max_smem = 0;
+    CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, q->device));
+    int wpb = 8;
+    size_t smem = 0;
+    for (; wpb >= 1; wpb >>= 1) {
+        smem = ((size_t)ipm_block_doubles(P) + 2 + (size_t)wpb * (ipm_warp_doubles(P) + 2)) * sizeof(double);
+        if (smem <= (size_t)max_smem) break;
+    }
+    if (wpb < 1) { rtmpc_qp_destroy(q); return fail("rtmpc_qp_create: problem does not fit in shared memory"); }
+    q->wpb = wpb; q->smem = smem;
+    cudaError_t e = cudaFuncSetAttribute((const void*)kc->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { rtmpc_qp_destroy(q); return fail("cudaFuncSetAttribute", e); }
+    *out = q;
+    return 0;
+}
+
+void rtmpc_qp_destroy(rtmpc_qp* q) {
+    if (!q) return;
+    for (void* p : q->allocs) cudaFree(p);
+    cudaFree(q->s_x); cudaFree(q->s_ref); cudaFree(q->s_z); cudaFree(q->s_U);
+    cudaFree(q->s_sel); cudaFree(q->s_status); cudaFree(q->s_iters);
+    if (q->stream) cudaStreamDestroy(q->stream);
+    delete q;
+}
+
+int rtmpc_qp_solve(rtmpc_qp* q, int32_t B, const double* d_x_init, const double* d_ref, const int32_t* d_sel,
+                   int32_t sel_value, double* d_z, double* d_U_t, int32_t* d_status, int32_t* d_iters,
+                   void* stream) {
+    if (!q) return fail("rtmpc_qp_solve: null handle");
+    if (B <= 0) return 0;
+    if (!d_x_init) return fail("rtmpc_qp_solve: d_x_init is null");
+    const KernelChoice* kc = pick_kernel(q->dev.n, q->dev.mpad);
+    const int wpb = q->wpb;
+    int blocks = (B + wpb - 1) / wpb;
+    if (blocks > q->num_sms) blocks = q->num_sms;   // one resident CTA per SM, warps loop over instances
+    kc->fn<<<blocks, wpb * 32, q->smem, (cudaStream_t)stream>>>(q->dev, B, d_x_init, d_ref, d_sel, sel_value, d_z,
+                                                               d_U_t, d_status, d_iters);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int ensure_staging(rtmpc_qp* q, int B) {
+    if (!q->stream) CU(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+    if (B <= q->cap) return 0;
+    cudaFree(q->s_x); cudaFree(q->s_ref); cudaFree(q->s_z); cudaFree(q->s_U);
+    cudaFree(q->s_sel); cudaFree(q->s_status); cudaFree(q->s_iters);
+    q->cap = 0;
+    const QPDev& P = q->dev;
+    CU(cudaMalloc(&q->s_x, (size_t)B * P.nx * sizeof(double)));
+    CU(cudaMalloc(&q->s_ref, (size_t)B * P.nx * sizeof(double)));
+    CU(cudaMalloc(&q->s_z, (size_t)B * P.nz * sizeof(double)));
+    CU(cudaMalloc(&q->s_U, (size_t)B * (P.N + 1) * P.nu * sizeof(double)));
+    CU(cudaMalloc(&q->s_sel, (size_t)B * sizeof(int)));
+    CU(cudaMalloc(&q->s_status, (size_t)B * sizeof(int)));
+    CU(cudaMalloc(&q->s_iters, (size_t)B * sizeof(int)));
+    q->cap = B;
+    return 0;
+}
+
+int rtmpc_qp_solve_host(rtmpc_qp* q, int32_t B, const double* h_x_init, const double* h_ref, const int32_t* h_sel,
+                        int32_t sel_value, double* h_z, double* h_U_t, int32_t* h_status, int32_t* h_iters) {
+    if (!q) return fail("rtmpc_qp_solve_host: null handle");
+    if (B <= 0) return 0;
+    if (ensure_staging(q, B)) return -1;
+    const QPDev& P = q->dev;
+    cudaStream_t s = q->stream;
+    CU(cudaMemcpyAsync(q->s_x, h_x_init, (size_t)B * P.nx * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (h_ref) CU(cudaMemcpyAsync(q->s_ref, h_ref, (size_t)B * P.nx * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (h_sel) CU(cudaMemcpyAsync(q->s_sel, h_sel, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (rtmpc_qp_solve(q, B, q->s_x, h_ref ? q->s_ref : nullptr, h_sel ? q->s_sel : nullptr, sel_value,
+                       h_z ? q->s_z : nullptr, h_U_t ? q->s_U : nullptr, q->s_status, q->s_iters, s))
+        return -1;
+    if (h_z) CU(cudaMemcpyAsync(h_z, q->s_z, (size_t)B * P.nz * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (h_U_t) CU(cudaMemcpyAsync(h_U_t, q->s_U, (size_t)B * (P.N + 1) * P.nu * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (h_status) CU(cudaMemcpyAsync(h_status, q->s_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (h_iters) CU(cudaMemcpyAsync(h_iters, q->s_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- closed loop ---------------------------------------------------------------------------
+
+struct rtmpc_loop {
+    LoopDev dev;
+    std::vector<void*> allocs;
+    int B = 0, t = 0;
+};
+
+template <typename T>
+static int lalloc(rtmpc_loop* l, size_t count, T** dst, const T* src = nullptr) {
+    *dst = nullptr;
+    if (count == 0) return 0;
+    void* p = nullptr;
+    CU(cudaMalloc(&p, count * sizeof(T)));
+    l->allocs.push_back(p);
+    if (src) CU(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    else CU(cudaMemset(p, 0, count * sizeof(T)));
+    *dst = static_cast<T*>(p);
+    return 0;
+}
+
+extern "C" {
+
+int rtmpc_loop_create(const rtmpc_loop_desc* d, int32_t B, rtmpc_loop** out) {
+    if (!d || !out || B <= 0) return fail("rtmpc_loop_create: bad argument");
+    *out = nullptr;
+    if (d->nx < 1 || d->nx > LOOP_MAX_NX || d->nu < 1 || d->nu > LOOP_MAX_NU) return fail("rtmpc_loop_create: need nx <= 8, nu <= 4");
+    if (d->plant == RTMPC_PLANT_CARTPOLE && (d->nx != 4 || d->nu != 1)) return fail("rtmpc_loop_create: cartpole plant needs nx=4, nu=1");
+    if (!d->A || !d->B || !d->K) return fail("rtmpc_loop_create: A, B, K required");
+    rtmpc_loop* l = new rtmpc_loop();
+    l->B = B;
+    LoopDev& L = l->dev;
+    std::memset(&L, 0, sizeof(L));
+    L.nx = d->nx; L.nu = d->nu; L.N = d->N; L.actuator = d->actuator; L.plant = d->plant; L.nz_rows = d->nz_rows;
+    std::memcpy(L.cart, d->cart_params, sizeof(L.cart));
+    const int nx = d->nx, nu = d->nu;
+    double *A, *Bm, *K, *Kp, *Hz = nullptr, *hz = nullptr, *wh;
+    std::vector<double> zeros(nx, 0.0);
+    int rc = 0;
+    rc |= lalloc(l, (size_t)nx * nx, &A, d->A);
+    rc |= lalloc(l, (size_t)nx * nu, &Bm, d->B);
+    rc |= lalloc(l, (size_t)nu * nx, &K, d->K);
+    rc |= lalloc(l, (size_t)nu * nx, &Kp, d->K_plant ? d->K_plant : d->K);
+    if (d->nz_rows > 0) {
+        rc |= lalloc(l, (size_t)d->nz_rows * nx, &Hz, d->Hz);
+        rc |= lalloc(l, (size_t)d->nz_rows, &hz, d->hz);
+    }
+    rc |= lalloc(l, (size_t)nx, &wh, d->w_half ? d->w_half : zeros.data());
+    L.A = A; L.Bm = Bm; L.K = K; L.Kp = Kp; L.Hz = Hz; L.hz = hz; L.w_half = wh;
+    rc |= lalloc(l, (size_t)B * nx, &L.x);
+    rc |= lalloc(l, (size_t)B * nx, &L.x_nom);
+    rc |= lalloc(l, (size_t)B * nx, &L.x_hat);
+    rc |= lalloc(l, (size_t)B * (d->N + 1) * nu, &L.buf);
+    rc |= lalloc(l, (size_t)B * nu, &L.u_last);
+    rc |= lalloc(l, (size_t)B, &L.err_acc);
+    rc |= lalloc(l, (size_t)B, &L.tube_max);
+    rc |= lalloc(l, (size_t)B, &L.q_t);
+    rc |= lalloc(l, (size_t)B, &L.s_t);
+    rc |= lalloc(l, (size_t)B, &L.Theta);
+    rc |= lalloc(l, (size_t)B, &L.alive);
+    rc |= lalloc(l, (size_t)B, &L.last_loss);
+    rc |= lalloc(l, (size_t)B, &L.gamma_last);
+    if (rc) { rtmpc_loop_destroy(l); return -1; }
+    *out = l;
+    std::vector<double> x0((size_t)B * nx, 0.0);
+    return rtmpc_loop_reset(l, x0.data());
+}
+
+void rtmpc_loop_destroy(rtmpc_loop* l) {
+    if (!l) return;
+    for (void* p : l->allocs) cudaFree(p);
+    delete l;
+}
+
+int rtmpc_loop_reset(rtmpc_loop* l, const double* h_x0) {
+    if (!l || !h_x0) return fail("rtmpc_loop_reset: null argument");
+    LoopDev& L = l->dev;
+    const size_t B = l->B, nx = L.nx, nu = L.nu;
+    CU(cudaMemcpy(L.x, h_x0, B * nx * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(L.x_nom, h_x0, B * nx * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(L.x_hat, h_x0, B * nx * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemset(L.buf, 0, B * (L.N + 1) * nu * sizeof(double)));
+    CU(cudaMemset(L.u_last, 0, B * nu * sizeof(double)));
+    CU(cudaMemset(L.err_acc, 0, B * sizeof(double)));
+    std::vector<double> neg(B, -1e300);
+    CU(cudaMemcpy(L.tube_max, neg.data(), B * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemset(L.q_t, 0, B * sizeof(int)));
+    CU(cudaMemset(L.s_t, 0, B * sizeof(int)));
+    CU(cudaMemset(L.Theta, 0, B * sizeof(int)));
+    std::vector<int> ones(B, 1), minus(B, -1);
+    CU(cudaMemcpy(L.alive, ones.data(), B * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(L.last_loss, minus.data(), B * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(L.gamma_last, ones.data(), B * sizeof(int), cudaMemcpyHostToDevice));
+    l->t = 0;
+    return 0;
+}
+
+double* rtmpc_loop_x(rtmpc_loop* l) { return l ? l->dev.x : nullptr; }
+double* rtmpc_loop_x_nom(rtmpc_loop* l) { return l ? l->dev.x_nom : nullptr; }
+double* rtmpc_loop_x_hat(rtmpc_loop* l) { return l ? l->dev.x_hat : nullptr; }
+int32_t* rtmpc_loop_q_t(rtmpc_loop* l) { return l ? l->dev.q_t : nullptr; }
+int32_t* rtmpc_loop_s_t(rtmpc_loop* l) { return l ? l->dev.s_t : nullptr; }
+int32_t* rtmpc_loop_Theta(rtmpc_loop* l) { return l ? l->dev.Theta : nullptr; }
+int32_t* rtmpc_loop_alive(rtmpc_loop* l) { return l ? l->dev.alive : nullptr; }
+double* rtmpc_loop_err_acc(rtmpc_loop* l) { return l ? l->dev.err_acc : nullptr; }
+double* rtmpc_loop_tube_max(rtmpc_loop* l) { return l ? l->dev.tube_max : nullptr; }
+double* rtmpc_loop_u(rtmpc_loop* l) { return l ? l->dev.u_last : nullptr; }
+int32_t* rtmpc_loop_gamma(rtmpc_loop* l) { return l ? l->dev.gamma_last : nullptr; }
+int32_t rtmpc_loop_time(rtmpc_loop* l) { return l ? l->t : -1; }
+
+int rtmpc_loop_step(rtmpc_loop* l, const double* d_U_t, const int32_t* d_status, const double* d_x_nom0,
+                    int64_t x_nom0_stride, const double* d_ref, const int32_t* d_theta, const int32_t* d_gamma,
+                    const double* d_w, const double* d_p_loss, uint64_t seed, int64_t id_offset, double* d_traj_x,
+                    int64_t traj_stride, void* stream) {
+    if (!l || !d_U_t) return fail("rtmpc_loop_step: null argument");
+    if ((d_theta == nullptr) != (d_gamma == nullptr)) return fail("rtmpc_loop_step: theta and gamma must be given together");
+    const int threads = 128;
+    const int blocks = (l->B + threads - 1) / threads;
+    loop_step_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+        l->dev, l->B, l->t, d_U_t, d_status, d_x_nom0, (long long)x_nom0_stride, d_ref, d_theta, d_gamma, d_w,
+        d_p_loss, (unsigned long long)seed, (long long)id_offset, d_traj_x, (long long)traj_stride);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    l->t += 1;
+    return 0;
+}
+
+// ---- split actuator / estimator calls ---------------------------------------------------------
+
+int rtmpc_actuator_process(int32_t B, int32_t nx, int32_t nu, int32_t N, int32_t kind, int32_t t,
+                           const double* d_A, const double* d_B, const double* d_K, const double* d_K_plant,
+                           const double* d_x_t, const double* d_U_t, const double* d_x_nom0, const int32_t* d_q_pkt,
+                           const int32_t* d_theta, double* d_buf, double* d_x_nom, int32_t* d_s_t, int32_t* d_Theta,
+                           int32_t* d_last_loss, double* d_u_out, double* d_pkt_x, double* d_pkt_xnom, void* stream) {
+    if (B <= 0) return 0;
+    if (nx < 1 || nx > LOOP_MAX_NX || nu < 1 || nu > LOOP_MAX_NU) return fail("rtmpc_actuator_process: need nx <= 8, nu <= 4");
+    if (!d_K || !d_x_t || !d_U_t || !d_q_pkt || !d_theta || !d_buf || !d_s_t || !d_Theta || !d_last_loss || !d_u_out || !d_pkt_x)
+        return fail("rtmpc_actuator_process: null argument");
+    if (kind != RTMPC_ACT_SMART && (!d_A || !d_B || !d_K_plant || !d_x_nom)) return fail("rtmpc_actuator_process: consistent actuator needs A, B, K_plant, x_nom");
+    ActArgs a;
+    a.nx = nx; a.nu = nu; a.N = N; a.kind = kind; a.t = t; a.has_xnom0 = d_x_nom0 != nullptr;
+    a.A = d_A; a.Bm = d_B; a.K = d_K; a.Kp = d_K_plant; a.x_t = d_x_t; a.U_t = d_U_t; a.x_nom0 = d_x_nom0;
+    a.q_pkt = d_q_pkt; a.theta = d_theta; a.buf = d_buf; a.x_nom = d_x_nom; a.u_out = d_u_out; a.pkt_x = d_pkt_x;
+    a.pkt_xnom = d_pkt_xnom; a.s_t = d_s_t; a.Theta = d_Theta; a.last_loss = d_last_loss;
+    actuator_process_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, B);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int rtmpc_estimator_update(int32_t B, int32_t nx, int32_t nu, int32_t N, int32_t robust, int32_t t, int32_t n_hist,
+                           const double* d_A, const double* d_B, const double* d_K, const double* d_K_plant,
+                           const double* d_pkt_x, const double* d_pkt_xnom, const int32_t* d_pkt_s,
+                           const int32_t* d_gamma, const double* d_hist, const double* d_x_nom0_mpc, double* d_x_hat,
+                           int32_t* d_q_t, void* stream) {
+    if (B <= 0) return 0;
+    if (nx < 1 || nx > LOOP_MAX_NX || nu < 1 || nu > LOOP_MAX_NU) return fail("rtmpc_estimator_update: need nx <= 8, nu <= 4");
+    if (!d_A || !d_B || !d_K || !d_gamma || !d_hist || !d_x_hat || !d_q_t || n_hist < 1) return fail("rtmpc_estimator_update: null argument / empty history");
+    if (robust && (!d_K_plant || !d_x_nom0_mpc)) return fail("rtmpc_estimator_update: robust estimator needs K_plant and x_nom0");
+    EstArgs e;
+    e.nx = nx; e.nu = nu; e.N = N; e.robust = robust; e.t = t; e.n_hist = n_hist;
+    e.A = d_A; e.Bm = d_B; e.K = d_K; e.Kp = d_K_plant; e.pkt_x = d_pkt_x; e.pkt_xnom = d_pkt_xnom;
+    e.x_nom0_mpc = d_x_nom0_mpc; e.hist = d_hist; e.pkt_s = d_pkt_s; e.gamma = d_gamma; e.x_hat = d_x_hat; e.q_t = d_q_t;
+    estimator_update_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e, B);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---- support sweep -------------------------------------------------------------------------
+
+int rtmpc_support_sweep(const double* d_V, int32_t nv, int32_t dim, const double* d_dirs, int64_t M, double* d_out,
+                        void* stream) {
+    if (!d_V || !d_dirs || !d_out) return fail("rtmpc_support_sweep: null argument");
+    if (dim < 1 || dim > 16) return fail("rtmpc_support_sweep: need 1 <= dim <= 16");
+    if (M <= 0) return 0;
+    const size_t smem = (size_t)nv * dim * sizeof(double);
+    if (smem > 200 * 1024) return fail("rtmpc_support_sweep: vertex set does not fit in shared memory");
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute((const void*)support_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int threads = 256;
+    long long blocks = (M + threads - 1) / threads;
+    const long long cap = (long long)sms * 8;
+    if (blocks > cap) blocks = cap;
+    support_sweep_kernel<<<(int)blocks, threads, smem, (cudaStream_t)stream>>>(d_V, nv, dim, d_dirs, (long long)M, d_out);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int rtmpc_support_sweep_host(const double* h_V, int32_t nv, int32_t dim, const double* h_dirs, int64_t M,
+                             double* h_out) {
+    if (!h_V || !h_dirs || !h_out) return fail("rtmpc_support_sweep_host: null argument");
+    if (M <= 0) return 0;
+    double *dV = nullptr, *dD = nullptr, *dO = nullptr;
+    int rc = 0;
+    do {
+        if (cudaMalloc(&dV, (size_t)nv * dim * sizeof(double)) != cudaSuccess) { rc = fail("cudaMalloc"); break; }
+        if (cudaMalloc(&dD, (size_t)M * dim * sizeof(double)) != cudaSuccess) { rc = fail("cudaMalloc"); break; }
+        if (cudaMalloc(&dO, (size_t)M * sizeof(double)) != cudaSuccess) { rc = fail("cudaMalloc"); break; }
+        if (cudaMemcpy(dV, h_V, (size_t)nv * dim * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
+        if (cudaMemcpy(dD, h_dirs, (size_t)M * dim * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
+        rc = rtmpc_support_sweep(dV, nv, dim, dD, M, dO, nullptr);
+        if (rc) break;
+        if (cudaMemcpy(h_out, dO, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
+    } while (0);
+    cudaFree(dV); cudaFree(dD); cudaFree(dO);
+    return rc;
+}
+
+}  // extern "C"

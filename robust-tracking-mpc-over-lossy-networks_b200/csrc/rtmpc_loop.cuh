@@ -1,0 +1,362 @@
+// Fused closed-loop step: consistent actuator (buffer + consistency flag), nominal model,
+// ancillary law, plant step and remote estimator for every instance, one thread per instance.
+//
+// Reference semantics (one Python object per instance there):
+//   SmartActuator.update_Theta_t / update_s_t / update_local_information / compute_u_t   SmartActuator.py:57-107
+//   ConsistentActuator.process_packet / ancillary_controller / update_x_nom             SmartActuator.py:146-222
+//   Estimator.update_estimate / update_q_t                                               Estimator.py:43-92
+//   RobustEstimator.update_estimate                                                      Estimator.py:113-156
+//   plant step x+ = A x + B u + w                                                        Results/results_linear_system.py:248
+// O(1) equivalents of the reference's O(t) bookkeeping (checked against the literal restatement
+// in oracle/ref_loop.py by tests/test_loop_*.py):
+//   * Theta_t = theta_t * prod(theta[q_t+1 .. t])  ==  theta_t && (last lost step <= q_t)
+//   * the estimator's `controlSequences[s_t]` is by construction the actuator's current buffer.
+#pragma once
+#include "rtmpc_common.cuh"
+#include "../../include/rtmpc.h"
+
+namespace rtmpc {
+
+constexpr int LOOP_MAX_NX = 8;
+constexpr int LOOP_MAX_NU = 4;
+
+struct LoopDev {
+    int nx, nu, N, actuator, plant, nz_rows;
+    const double *A, *Bm, *K, *Kp, *Hz, *hz, *w_half;
+    double cart[8];
+    double *x, *x_nom, *x_hat, *buf, *u_last, *err_acc, *tube_max;
+    int *q_t, *s_t, *Theta, *alive, *last_loss, *gamma_last;
+};
+
+__device__ __forceinline__ void cartpole_substeps(double* x, double F, const double* c) {
+    const double M = c[0], m = c[1], I = c[2], g = c[3], l = c[4], dt = c[5];
+    const int nsub = (int)c[6];
+    double pos = x[0], vel = x[1], phi = x[2], om = x[3];
+    for (int s = 0; s < nsub; ++s) {
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        const double D = (M + m) * (I + m * l * l) - (m * l * cs) * (m * l * cs);
+        const double fe = F + m * l * om * om * sn;
+        const double acc = ((I + m * l * l) * fe - (m * l) * (m * l) * g * sn * cs) / D;
+        const double alp = ((M + m) * m * g * l * sn - m * l * cs * fe) / D;
+        vel += dt * acc;
+        om += dt * alp;
+        pos += dt * vel;
+        phi += dt * om;
+    }
+    x[0] = pos; x[1] = vel; x[2] = phi; x[3] = om;
+}
+
+__global__ void loop_step_kernel(LoopDev L, int B, int t, const double* __restrict__ U_t,
+                                 const int* __restrict__ status, const double* __restrict__ x_nom0,
+                                 long long x_nom0_stride, const double* __restrict__ ref,
+                                 const int* __restrict__ theta_in, const int* __restrict__ gamma_in,
+                                 const double* __restrict__ w_in, const double* __restrict__ p_loss,
+                                 unsigned long long seed, long long id_offset, double* __restrict__ traj,
+                                 long long traj_stride) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nx = L.nx, nu = L.nu, N = L.N;
+    if (!L.alive[b]) return;
+    double x[LOOP_MAX_NX], xn[LOOP_MAX_NX], xh[LOOP_MAX_NX], w[LOOP_MAX_NX];
+    for (int k = 0; k < nx; ++k) {
+        x[k] = L.x[(size_t)b * nx + k];
+        xn[k] = L.x_nom[(size_t)b * nx + k];
+        xh[k] = L.x_hat[(size_t)b * nx + k];
+    }
+    if (traj && t == 0) for (int k = 0; k < nx; ++k) traj[(size_t)b * traj_stride + k] = x[k];
+    // controller returned None (infeasible): the reference stops this controller's run
+    if (status && status[b] == RTMPC_INFEASIBLE) { L.alive[b] = 0; return; }
+
+    // statistics on the pre-step state (x_traj[:, t] in the reference's scripts)
+    if (ref) {
+        double e = 0.0;
+        for (int k = 0; k < nx; ++k) { double d = x[k] - ref[(size_t)b * nx + k]; e = fma(d, d, e); }
+        L.err_acc[b] += e;
+    }
+    if (L.nz_rows > 0) {
+        double worst = L.tube_max[b];
+        for (int i = 0; i < L.nz_rows; ++i) {
+            double acc = -L.hz[i];
+            for (int k = 0; k < nx; ++k) acc = fma(L.Hz[i * nx + k], x[k] - xn[k], acc);
+            worst = fmax(worst, acc);
+        }
+        L.tube_max[b] = worst;
+    }
+
+    // network and disturbance realisation
+    int theta, gamma;
+    if (theta_in) {
+        theta = theta_in[b];
+        gamma = gamma_in[b];
+        for (int k = 0; k < nx; ++k) w[k] = w_in ? w_in[(size_t)b * nx + k] : 0.0;
+    } else {
+        const unsigned long long id = (unsigned long long)(id_offset + b);
+        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        Philox4 r = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, 0u, k0, k1);
+        const double p = p_loss ? p_loss[b] : 0.0;
+        theta = (t == 0) ? 1 : (u01_from_bits(r.x, r.y) < p ? 0 : 1);
+        gamma = (t == 0) ? 1 : (u01_from_bits(r.z, r.w) < p ? 0 : 1);
+        for (int k = 0; k < nx; k += 2) {
+            Philox4 q = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, 1u + (uint32_t)(k >> 1), k0, k1);
+            w[k] = L.w_half[k] * (2.0 * u01_from_bits(q.x, q.y) - 1.0);
+            if (k + 1 < nx) w[k + 1] = L.w_half[k + 1] * (2.0 * u01_from_bits(q.z, q.w) - 1.0);
+        }
+    }
+
+    // ---- local side ---------------------------------------------------------------------
+    const int q_pkt = L.q_t[b];                 // q_t carried by the controller packet
+    int last_loss = L.last_loss[b];
+    int Theta = 0;
+    if (theta == 1) Theta = (last_loss <= q_pkt) ? 1 : 0;
+    else last_loss = t;
+    int s_t = L.s_t[b];
+    double* buf = L.buf + (size_t)b * (N + 1) * nu;
+    const double* Ub = U_t + (size_t)b * (N + 1) * nu;
+    if (Theta) {
+        s_t = t;
+        for (int i = 0; i < (N + 1) * nu; ++i) buf[i] = Ub[i];
+        if (L.actuator != RTMPC_ACT_SMART && x_nom0)    // packet carries x_nom_0 (SmartActuator.py:183-187,219-222)
+            for (int k = 0; k < nx; ++k) xn[k] = x_nom0[(size_t)b * x_nom0_stride + k];
+    }
+    const int kk = t - s_t;
+    const double* xfb = (L.actuator == RTMPC_ACT_SMART) ? x : xn;   // state fed to compute_u_t
+    double u_nom[LOOP_MAX_NU], u[LOOP_MAX_NU];
+    for (int j = 0; j < nu; ++j) {
+        if (kk < N) u_nom[j] = buf[kk * nu + j];
+        else {
+            double acc = buf[N * nu + j];
+            for (int k = 0; k < nx; ++k) acc = fma(-L.K[j * nx + k], xfb[k], acc);
+            u_nom[j] = acc;
+        }
+        if (L.actuator == RTMPC_ACT_SMART) u[j] = u_nom[j];
+        else {
+            double acc = u_nom[j];
+            for (int k = 0; k < nx; ++k) acc = fma(-L.Kp[j * nx + k], x[k] - xn[k], acc);
+            u[j] = acc;
+        }
+    }
+    // plant packet content (pre-update values)
+    double xp[LOOP_MAX_NX], xnp[LOOP_MAX_NX];
+    for (int k = 0; k < nx; ++k) {
+        xnp[k] = xn[k];
+        xp[k] = (L.actuator == RTMPC_ACT_CONSISTENT) ? xn[k] : x[k];
+    }
+    // nominal model
+    if (L.actuator != RTMPC_ACT_SMART) {
+        double nxt[LOOP_MAX_NX];
+        for (int i = 0; i < nx; ++i) {
+            double acc = 0.0;
+            for (int k = 0; k < nx; ++k) acc = fma(L.A[i * nx + k], xnp[k], acc);
+            for (int j = 0; j < nu; ++j) acc = fma(L.Bm[i * nu + j], u_nom[j], acc);
+            nxt[i] = acc;
+        }
+        for (int i = 0; i < nx; ++i) xn[i] = nxt[i];
+    }
+    // ---- plant ----------------------------------------------------------------------------
+    double xnew[LOOP_MAX_NX];
+    if (L.plant == RTMPC_PLANT_CARTPOLE) {
+        for (int k = 0; k < nx; ++k) xnew[k] = x[k];
+        cartpole_substeps(xnew, u[0], L.cart);
+    } else {
+        for (int i = 0; i < nx; ++i) {
+            double acc = 0.0;
+            for (int k = 0; k < nx; ++k) acc = fma(L.A[i * nx + k], x[k], acc);
+            for (int j = 0; j < nu; ++j) acc = fma(L.Bm[i * nu + j], u[j], acc);
+            xnew[i] = acc + w[i];
+        }
+    }
+    // ---- remote side ----------------------------------------------------------------------
+    double uh[LOOP_MAX_NU];
+    const double* xbase;
+    double xn0[LOOP_MAX_NX];
+    if (gamma == 1) {
+        // \hat u(k|k) from the sequence the plant is using (== buf) and the packet's state
+        for (int j = 0; j < nu; ++j) {
+            double un;
+            if (kk < N) un = buf[kk * nu + j];
+            else {
+                double acc = buf[N * nu + j];
+                const double* xs = (L.actuator == RTMPC_ACT_EXTENDED) ? xnp : xp;
+                for (int k = 0; k < nx; ++k) acc = fma(-L.K[j * nx + k], xs[k], acc);
+                un = acc;
+            }
+            if (L.actuator == RTMPC_ACT_EXTENDED) {
+                double acc = un;
+                for (int k = 0; k < nx; ++k) acc = fma(-L.Kp[j * nx + k], xp[k] - xnp[k], acc);
+                un = acc;
+            }
+            uh[j] = un;
+        }
+        xbase = xp;
+    } else {
+        for (int j = 0; j < nu; ++j) uh[j] = Ub[j];           // first input of the latest sent sequence
+        if (L.actuator == RTMPC_ACT_EXTENDED && x_nom0) {
+            for (int k = 0; k < nx; ++k) xn0[k] = x_nom0[(size_t)b * x_nom0_stride + k];
+            xbase = xn0;
+        } else xbase = xh;
+    }
+    double xhn[LOOP_MAX_NX];
+    for (int i = 0; i < nx; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < nx; ++k) acc = fma(L.A[i * nx + k], xbase[k], acc);
+        for (int j = 0; j < nu; ++j) acc = fma(L.Bm[i * nu + j], uh[j], acc);
+        xhn[i] = acc;
+    }
+    // ---- write back -----------------------------------------------------------------------
+    for (int k = 0; k < nx; ++k) {
+        L.x[(size_t)b * nx + k] = xnew[k];
+        L.x_nom[(size_t)b * nx + k] = xn[k];
+        L.x_hat[(size_t)b * nx + k] = xhn[k];
+    }
+    for (int j = 0; j < nu; ++j) L.u_last[(size_t)b * nu + j] = u[j];
+    if (gamma == 1) L.q_t[b] = t;
+    L.s_t[b] = s_t;
+    L.Theta[b] = Theta;
+    L.last_loss[b] = last_loss;
+    L.gamma_last[b] = gamma;
+    if (traj) for (int k = 0; k < nx; ++k) traj[(size_t)b * traj_stride + (size_t)(t + 1) * nx + k] = xnew[k];
+}
+
+// out[j] = max_v <dirs[j,:], V[v,:]> ; one thread per direction, vertices staged in shared memory
+__global__ void support_sweep_kernel(const double* __restrict__ V, int nv, int dim,
+                                     const double* __restrict__ dirs, long long M, double* __restrict__ out) {
+    extern __shared__ __align__(16) double sv[];
+    for (int i = threadIdx.x; i < nv * dim; i += blockDim.x) sv[i] = V[i];
+    __syncthreads();
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (long long)gridDim.x * blockDim.x) {
+        double a[16];
+        for (int k = 0; k < dim; ++k) a[k] = dirs[j * dim + k];
+        double best = -RTMPC_INF;
+        for (int v = 0; v < nv; ++v) {
+            double acc = 0.0;
+            for (int k = 0; k < dim; ++k) acc = fma(a[k], sv[v * dim + k], acc);
+            best = fmax(best, acc);
+        }
+        out[j] = best;
+    }
+}
+
+}  // namespace rtmpc
+
+// ------------------------------------------------------------------------------------------------
+// Split entry points for the reference's per-object call order
+//   u, plant_packet = actuator.process_packet(packet, x, theta)   (SmartActuator.py:31-54, :174-213)
+//   ... caller steps the plant ...
+//   estimator.update_estimate(plant_packet, gamma)                 (Estimator.py:43-78, :113-156)
+// They operate on caller-owned device arrays (the Python classes keep them in torch tensors).
+// ------------------------------------------------------------------------------------------------
+namespace rtmpc {
+
+struct ActArgs {
+    int nx, nu, N, kind, t, has_xnom0;
+    const double *A, *Bm, *K, *Kp;
+    const double *x_t, *U_t, *x_nom0;
+    const int *q_pkt, *theta;
+    double *buf, *x_nom, *u_out, *pkt_x, *pkt_xnom;
+    int *s_t, *Theta, *last_loss;
+};
+
+__global__ void actuator_process_kernel(ActArgs a, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nx = a.nx, nu = a.nu, N = a.N;
+    double x[LOOP_MAX_NX], xn[LOOP_MAX_NX];
+    for (int k = 0; k < nx; ++k) {
+        x[k] = a.x_t[(size_t)b * nx + k];
+        xn[k] = (a.kind == RTMPC_ACT_SMART) ? 0.0 : a.x_nom[(size_t)b * nx + k];
+    }
+    int last_loss = a.last_loss[b], Theta = 0, s_t = a.s_t[b];
+    if (a.theta[b] == 1) Theta = (last_loss <= a.q_pkt[b]) ? 1 : 0;
+    else last_loss = a.t;
+    double* buf = a.buf + (size_t)b * (N + 1) * nu;
+    if (Theta) {
+        s_t = a.t;
+        for (int i = 0; i < (N + 1) * nu; ++i) buf[i] = a.U_t[(size_t)b * (N + 1) * nu + i];
+        if (a.kind != RTMPC_ACT_SMART && a.has_xnom0)
+            for (int k = 0; k < nx; ++k) xn[k] = a.x_nom0[(size_t)b * nx + k];
+    }
+    const int kk = a.t - s_t;
+    const double* xfb = (a.kind == RTMPC_ACT_SMART) ? x : xn;
+    double u_nom[LOOP_MAX_NU];
+    for (int j = 0; j < nu; ++j) {
+        if (kk < N) u_nom[j] = buf[kk * nu + j];
+        else {
+            double acc = buf[N * nu + j];
+            for (int k = 0; k < nx; ++k) acc = fma(-a.K[j * nx + k], xfb[k], acc);
+            u_nom[j] = acc;
+        }
+        double u = u_nom[j];
+        if (a.kind != RTMPC_ACT_SMART)
+            for (int k = 0; k < nx; ++k) u = fma(-a.Kp[j * nx + k], x[k] - xn[k], u);
+        a.u_out[(size_t)b * nu + j] = u;
+    }
+    for (int k = 0; k < nx; ++k) {
+        a.pkt_x[(size_t)b * nx + k] = (a.kind == RTMPC_ACT_CONSISTENT) ? xn[k] : x[k];
+        if (a.pkt_xnom) a.pkt_xnom[(size_t)b * nx + k] = xn[k];
+    }
+    if (a.kind != RTMPC_ACT_SMART) {
+        for (int i = 0; i < nx; ++i) {
+            double acc = 0.0;
+            for (int k = 0; k < nx; ++k) acc = fma(a.A[i * nx + k], xn[k], acc);
+            for (int j = 0; j < nu; ++j) acc = fma(a.Bm[i * nu + j], u_nom[j], acc);
+            a.x_nom[(size_t)b * nx + i] = acc;
+        }
+    }
+    a.s_t[b] = s_t;
+    a.Theta[b] = Theta;
+    a.last_loss[b] = last_loss;
+}
+
+struct EstArgs {
+    int nx, nu, N, robust, t, n_hist;
+    const double *A, *Bm, *K, *Kp;
+    const double *pkt_x, *pkt_xnom, *x_nom0_mpc, *hist;   // hist[(time)*B*(N+1)*nu + b*(N+1)*nu + ...]
+    const int *pkt_s, *gamma;
+    double* x_hat;
+    int* q_t;
+};
+
+__global__ void estimator_update_kernel(EstArgs e, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nx = e.nx, nu = e.nu, N = e.N;
+    const size_t seq = (size_t)(N + 1) * nu;
+    double base[LOOP_MAX_NX], uh[LOOP_MAX_NU];
+    if (e.gamma[b] == 1) {
+        const int s_t = e.pkt_s[b];
+        const double* sq = e.hist + ((size_t)s_t * B + b) * seq;
+        const int kk = e.t - s_t;
+        for (int k = 0; k < nx; ++k) base[k] = e.pkt_x[(size_t)b * nx + k];
+        for (int j = 0; j < nu; ++j) {
+            double un;
+            if (kk < N) un = sq[kk * nu + j];
+            else {
+                double acc = sq[N * nu + j];
+                const double* xs = e.robust ? e.pkt_xnom : e.pkt_x;
+                for (int k = 0; k < nx; ++k) acc = fma(-e.K[j * nx + k], xs[(size_t)b * nx + k], acc);
+                un = acc;
+            }
+            if (e.robust)
+                for (int k = 0; k < nx; ++k)
+                    un = fma(-e.Kp[j * nx + k], e.pkt_x[(size_t)b * nx + k] - e.pkt_xnom[(size_t)b * nx + k], un);
+            uh[j] = un;
+        }
+    } else {
+        const double* sq = e.hist + ((size_t)(e.n_hist - 1) * B + b) * seq;
+        for (int j = 0; j < nu; ++j) uh[j] = sq[j];
+        for (int k = 0; k < nx; ++k)
+            base[k] = e.robust ? e.x_nom0_mpc[(size_t)b * nx + k] : e.x_hat[(size_t)b * nx + k];
+    }
+    double out[LOOP_MAX_NX];
+    for (int i = 0; i < nx; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < nx; ++k) acc = fma(e.A[i * nx + k], base[k], acc);
+        for (int j = 0; j < nu; ++j) acc = fma(e.Bm[i * nu + j], uh[j], acc);
+        out[i] = acc;
+    }
+    for (int i = 0; i < nx; ++i) e.x_hat[(size_t)b * nx + i] = out[i];
+    if (e.gamma[b] == 1) e.q_t[b] = e.t;
+}
+
+}  // namespace rtmpc

@@ -1,0 +1,99 @@
+"""Device-resident batched QP: the object behind every controller class' ``_prob``.
+
+``BatchedQP(spec)`` condenses and equilibrates the problem on the host (once), uploads it through
+``rtmpc_qp_create`` and then solves any number of (x_init, ref) instances per call on the GPU.
+It plays the role of the cvxpy ``Problem`` + Clarabel pair in the reference
+(``TubeTrackingMPC.py:153,183``) and has no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .condense import MPCSpec, condense
+from .ipm_data import prepare
+
+
+class BatchedQP:
+    def __init__(self, spec: MPCSpec, Kss=None, max_iter=60):
+        self.spec = spec
+        self.cq = condense(spec)
+        self.data = prepare(self.cq)
+        cq, d = self.cq, self.data
+        self.nx, self.nu, self.N = cq.nx, cq.nu, cq.N
+        self.nz = cq.Phi.shape[0]
+        self.has_ss = spec.T_ss is not None
+        self.n, self.m = cq.n, cq.m
+        L = _lib.lib()
+        _lib.require_cuda()
+        Phi = np.zeros((self.nz, d.npad))
+        Phi[:, :cq.n] = cq.Phi
+        Dp = np.zeros(d.npad)
+        Dp[:cq.n] = d.D
+        Hs = np.zeros((d.npad, d.npad))
+        Hs[:cq.n, :cq.n] = d.Hs
+        if self.has_ss and Kss is None:
+            raise ValueError("Kss (steady-state gain) is required for the tracking variants")
+        keep = dict(Hs=_lib.f64(Hs), Hinv=_lib.f64(d.Hinv), G=_lib.f64(d.Gs), Y=_lib.f64(d.Y), Fx=_lib.f64(d.Fx),
+                    Fr=_lib.f64(d.Fr), lo0=_lib.f64(d.lo0), up0=_lib.f64(d.up0), Lx=_lib.f64(d.Lx),
+                    Ux=_lib.f64(d.Ux), parC=_lib.f64(d.par_C), parh=_lib.f64(d.par_h), Dscale=_lib.f64(Dp),
+                    Phi=_lib.f64(Phi), Psi=_lib.f64(cq.Psi))
+        if Kss is not None:
+            keep["Kss"] = _lib.f64(np.atleast_2d(Kss))
+        has_lo = np.ascontiguousarray(d.has_lo, np.uint8)
+        has_up = np.ascontiguousarray(d.has_up, np.uint8)
+        desc = _lib.QPDesc()
+        desc.nx, desc.nu, desc.N = cq.nx, cq.nu, cq.N
+        desc.n, desc.npad, desc.m, desc.mpad = cq.n, d.npad, cq.m, d.mpad
+        desc.np, desc.nz, desc.nss = len(d.par_h), self.nz, (cq.nx + cq.nu) if self.has_ss else 0
+        dp = C.POINTER(C.c_double)
+        for k, v in keep.items():
+            setattr(desc, k, v.ctypes.data_as(dp) if v.size else None)
+        desc.has_lo = has_lo.ctypes.data_as(C.POINTER(C.c_uint8))
+        desc.has_up = has_up.ctypes.data_as(C.POINTER(C.c_uint8))
+        desc.s_floor, desc.sc_b, desc.max_iter = d.s_floor, d.sc_b, max_iter
+        h = C.c_void_p()
+        _lib.check(L.rtmpc_qp_create(C.byref(desc), C.byref(h)), "rtmpc_qp_create")
+        self._h = h
+        self._L = L
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.rtmpc_qp_destroy(h)
+            self._h = None
+
+    # -- host buffers (numpy in / numpy out): the reference-facing call ----------------------
+    def solve_host(self, x_init, ref=None, sel=None, sel_value=1, want_z=True):
+        x_init = _lib.f64(np.atleast_2d(x_init))
+        B = x_init.shape[0]
+        ref = None if ref is None else _lib.f64(np.broadcast_to(np.atleast_2d(ref), x_init.shape))
+        z = np.empty((B, self.nz)) if want_z else None
+        U = np.empty((B, self.N + 1, self.nu))
+        if not self.has_ss:
+            U[:, self.N, :] = np.nan
+        status = np.full(B, -1, np.int32)
+        iters = np.zeros(B, np.int32)
+        selp = None if sel is None else np.ascontiguousarray(sel, np.int32)
+        _lib.check(self._L.rtmpc_qp_solve_host(self._h, B, _lib.ptr(x_init), _lib.ptr(ref), _lib.ptr(selp), sel_value,
+                                               _lib.ptr(z), _lib.ptr(U), _lib.ptr(status), _lib.ptr(iters)),
+                   "rtmpc_qp_solve_host")
+        return z, U, status, iters
+
+    # -- device buffers (torch tensors used purely as memory) ---------------------------------
+    def solve_device(self, x_init, ref, z, U, status, iters, sel=None, sel_value=1, stream=None):
+        B = x_init.shape[0]
+        _lib.check(self._L.rtmpc_qp_solve(self._h, B, _lib.ptr(x_init), _lib.ptr(ref), _lib.ptr(sel), sel_value,
+                                          _lib.ptr(z), _lib.ptr(U), _lib.ptr(status), _lib.ptr(iters), stream),
+                   "rtmpc_qp_solve")
+
+    def split(self, z):
+        """[B,nz] -> x[B,nx,N+1], u[B,nu,N], (x_bar[B,nx], u_bar[B,nu])"""
+        nx, nu, N = self.nx, self.nu, self.N
+        B = z.shape[0]
+        x = z[:, :nx * (N + 1)].reshape(B, N + 1, nx).transpose(0, 2, 1)
+        u = z[:, nx * (N + 1):nx * (N + 1) + nu * N].reshape(B, N, nu).transpose(0, 2, 1)
+        if self.has_ss:
+            o = nx * (N + 1) + nu * N
+            return x, u, z[:, o:o + nx], z[:, o + nx:o + nx + nu]
+        return x, u

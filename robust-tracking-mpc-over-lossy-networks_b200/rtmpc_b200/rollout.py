@@ -1,0 +1,162 @@
+"""Batched closed-loop rollouts: thousands of Monte-Carlo instances of the reference's experiment
+loop (``Results/results_linear_system.py:209-255``, ``..._with_extendedMPC.py:247-378``) at once.
+
+Per control step, for all B instances: one QP launch (two for the extended variant, switched per
+instance on gamma_{t-1}) followed by one fused loop-step launch (consistent actuator, nominal
+model, ancillary law, plant, estimator).  Everything stays on the GPU between steps; the estimate
+x_hat the next solve needs is read straight from the loop's device state.  torch only provides
+the output buffers and the stream.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CART_PARAMS = (1.0, 0.1, 0.001, 9.8, 0.5, 1.0 / 500.0, 10.0, 0.0)   # M, m, I, g, l, dt, sub-steps
+
+
+class _DeviceArray:
+    """Minimal ``__cuda_array_interface__`` carrier for library-owned device memory."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _view(ptr, shape, dtype, dev):
+    """torch view (no copy) of a device array owned by the C library."""
+    return torch.as_tensor(_DeviceArray(ptr, shape, "<f8" if dtype == torch.float64 else "<i4"), device=dev)
+
+
+class RemoteLoop:
+    """B closed-loop instances of one controller.
+
+    mpc       TubeTrackingMPC / ExtendedTubeTrackingMPC / TrackingMPC object from :mod:`rtmpc_b200.mpc`
+              with its optimisation problem(s) generated
+    kind      'tube' (ConsistentActuator + Estimator), 'extended' (+ RobustEstimator, x_nom_0 in the
+              packet, gamma-switched QP) or 'track' (SmartActuator + Estimator, Pezzutto remote MPC)
+    plant     'linear' or 'cartpole' (analytic ODE, 10 sub-steps of 1/500 s, no disturbance)
+    """
+
+    def __init__(self, mpc, B, kind="tube", plant="linear", w_half=None, Z=None, K_plant=None):
+        _lib.require_cuda()
+        self.L = _lib.lib()
+        self.mpc = mpc
+        self.B = int(B)
+        self.kind = kind
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        A, Bm, K = np.asarray(mpc._A, float), np.asarray(mpc._B, float), np.atleast_2d(mpc._K)
+        self.nx, self.nu = Bm.shape
+        self.N = mpc._N
+        if K_plant is None:
+            K_plant = mpc.get_ancillary_controller_gain() if hasattr(mpc, "get_ancillary_controller_gain") else K
+        d = _lib.LoopDesc()
+        d.nx, d.nu, d.N = self.nx, self.nu, self.N
+        d.actuator = {"track": _lib.ACT_SMART, "tube": _lib.ACT_CONSISTENT, "extended": _lib.ACT_EXTENDED}[kind]
+        d.plant = {"linear": _lib.PLANT_LINEAR, "cartpole": _lib.PLANT_CARTPOLE}[plant]
+        keep = [_lib.f64(A), _lib.f64(Bm), _lib.f64(K), _lib.f64(np.atleast_2d(K_plant)),
+                _lib.f64(np.zeros(self.nx) if w_half is None else w_half)]
+        dp = C.POINTER(C.c_double)
+        d.A, d.B, d.K, d.K_plant, d.w_half = (k.ctypes.data_as(dp) for k in keep)
+        if Z is not None:
+            Hz, hz = _lib.f64(Z.A), _lib.f64(np.asarray(Z.b).flatten())
+            d.nz_rows, d.Hz, d.hz = Hz.shape[0], Hz.ctypes.data_as(dp), hz.ctypes.data_as(dp)
+            keep += [Hz, hz]
+        for i, v in enumerate(CART_PARAMS):
+            d.cart_params[i] = v
+        h = C.c_void_p()
+        _lib.check(self.L.rtmpc_loop_create(C.byref(d), self.B, C.byref(h)), "rtmpc_loop_create")
+        self._h = h
+        f64, i32 = torch.float64, torch.int32
+        B_, nx, nu, N = self.B, self.nx, self.nu, self.N
+        g = lambda name: getattr(self.L, "rtmpc_loop_" + name)(self._h)        # noqa: E731
+        self.x = _view(g("x"), (B_, nx), f64, self.dev)
+        self.x_nom = _view(g("x_nom"), (B_, nx), f64, self.dev)
+        self.x_hat = _view(g("x_hat"), (B_, nx), f64, self.dev)
+        self.q_t = _view(g("q_t"), (B_,), i32, self.dev)
+        self.s_t = _view(g("s_t"), (B_,), i32, self.dev)
+        self.Theta = _view(g("Theta"), (B_,), i32, self.dev)
+        self.alive = _view(g("alive"), (B_,), i32, self.dev)
+        self.err_acc = _view(g("err_acc"), (B_,), f64, self.dev)
+        self.tube_max = _view(g("tube_max"), (B_,), f64, self.dev)
+        self.u = _view(g("u"), (B_, nu), f64, self.dev)
+        self.gamma_last = _view(g("gamma"), (B_,), i32, self.dev)
+        nz = mpc._prob.nz
+        self.z = torch.zeros(B_, nz, device=self.dev, dtype=f64)
+        self.U = torch.zeros(B_, N + 1, nu, device=self.dev, dtype=f64)
+        self.status = torch.zeros(B_, device=self.dev, dtype=i32)
+        self.iters = torch.zeros(B_, device=self.dev, dtype=i32)
+        self.iters_total = torch.zeros((), device=self.dev, dtype=torch.int64)
+        self.status_count = torch.zeros(4, device=self.dev, dtype=torch.int64)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self.L.rtmpc_loop_destroy(h)
+            self._h = None
+
+    def reset(self, x0=None):
+        x0 = np.zeros((self.B, self.nx)) if x0 is None else np.broadcast_to(np.asarray(x0, float).reshape(-1, self.nx),
+                                                                              (self.B, self.nx))
+        x0 = _lib.f64(x0)
+        _lib.check(self.L.rtmpc_loop_reset(self._h, _lib.ptr(x0)), "rtmpc_loop_reset")
+        self.iters_total.zero_()
+        self.status_count.zero_()
+
+    @property
+    def t(self):
+        return int(self.L.rtmpc_loop_time(self._h))
+
+    def step(self, ref_d, theta=None, gamma=None, w=None, p_loss=None, seed=0, id_offset=0, traj=None, stats=True):
+        """One control step for all instances.  ``ref_d`` [B,nx] device tensor.  Either explicit
+        device arrays theta/gamma [B] int32 and w [B,nx], or p_loss [B] for on-device Philox draws."""
+        stream = torch.cuda.current_stream().cuda_stream
+        p = _lib.ptr
+        if self.kind == "extended":
+            self.mpc._prob_packet_received.solve_device(self.x_hat, ref_d, self.z, self.U, self.status, self.iters,
+                                                        sel=self.gamma_last, sel_value=1, stream=stream)
+            self.mpc._prob.solve_device(self.x_hat, ref_d, self.z, self.U, self.status, self.iters,
+                                        sel=self.gamma_last, sel_value=0, stream=stream)
+            x_nom0, stride = self.z, self.z.shape[1]
+        else:
+            self.mpc._prob.solve_device(self.x_hat, ref_d, self.z, self.U, self.status, self.iters, stream=stream)
+            x_nom0, stride = None, 0
+        if stats:
+            self.iters_total += self.iters.sum()
+            self.status_count += torch.bincount(self.status, minlength=4)[:4]
+        _lib.check(self.L.rtmpc_loop_step(self._h, p(self.U), p(self.status), p(x_nom0), stride, p(ref_d), p(theta),
+                                          p(gamma), p(w), p(p_loss), int(seed), int(id_offset), p(traj),
+                                          0 if traj is None else traj.shape[1] * traj.shape[2], stream),
+                   "rtmpc_loop_step")
+
+    def run(self, T, ref, p_loss=None, theta=None, gamma=None, w=None, seed=0, id_offset=0, record=False, stats=True):
+        """T steps.  ``ref`` [nx], [T,nx] or [T,B,nx]; explicit arrays theta/gamma [T,B], w [T,B,nx] (host or
+        device) or p_loss [B].  Returns the trajectory tensor [B,T+1,nx] when ``record``."""
+        f64 = torch.float64
+        ref = np.asarray(ref, float)
+        if ref.ndim == 1:
+            ref = np.broadcast_to(ref, (T, self.nx))
+        if ref.ndim == 2:
+            ref = np.broadcast_to(ref[:, None, :], (T, self.B, self.nx))
+        ref_d = torch.as_tensor(np.ascontiguousarray(ref), device=self.dev, dtype=f64)
+        traj = torch.zeros(self.B, T + 1, self.nx, device=self.dev, dtype=f64) if record else None
+        if theta is not None:
+            theta = torch.as_tensor(np.ascontiguousarray(theta), device=self.dev).to(torch.int32).contiguous()
+            gamma = torch.as_tensor(np.ascontiguousarray(gamma), device=self.dev).to(torch.int32).contiguous()
+            w = None if w is None else torch.as_tensor(np.ascontiguousarray(w), device=self.dev, dtype=f64).contiguous()
+        elif p_loss is not None:
+            p_loss = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(p_loss, (self.B,))), device=self.dev, dtype=f64)
+        else:
+            p_loss = torch.zeros(self.B, device=self.dev, dtype=f64)
+        for k in range(T):
+            if theta is not None:
+                self.step(ref_d[k], theta[k], gamma[k], None if w is None else w[k], traj=traj, stats=stats)
+            else:
+                self.step(ref_d[k], p_loss=p_loss, seed=seed, id_offset=id_offset, traj=traj, stats=stats)
+        return traj
+
+    def tracking_error(self, T):
+        """1/T sqrt(sum_t ||x_t - ref_t||^2) per instance (``Results/results_linear_system.py:291``)."""
+        return torch.sqrt(self.err_acc) / T

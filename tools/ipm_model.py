@@ -7,7 +7,8 @@ infeasibility test) can be exercised on a CPU-only box.  Nothing in the product 
 import numpy as np
 
 
-def ipm_model(d, x_init, ref, max_iter=60, tol_res=1e-9, tol_gap=1e-12, verbose=False, warm=None):
+def ipm_model(d, x_init, ref, max_iter=60, tol_res=1e-9, tol_gap=1e-12, verbose=False, warm=None,
+              return_state=False):
     n, m = d.n, d.m
     G = d.Gs[:m, :n]
     H = d.Hs
@@ -49,12 +50,22 @@ def ipm_model(d, x_init, ref, max_iter=60, tol_res=1e-9, tol_gap=1e-12, verbose=
             print(it, res, relgap, mu)
         merit = max(res, relgap)
         if best is None or merit < best[0]:
-            best = (merit, zeta.copy(), it)
+            best = (merit, zeta.copy(), it, (su.copy(), sl.copy(), lu.copy(), ll.copy()))
         if res <= tol_res and relgap <= tol_gap:
             status = 0
             break
         if best[0] <= 1e-8 and merit > 1e3 * best[0]:
             status = 0
+            break
+        # primal infeasibility certificate on the normalised multiplier direction
+        y = lu - ll
+        yn = np.abs(y).max()
+        if yn > 1e6 * sc_q and it >= 3:
+            cert = (np.where(hu, up * lu, 0.0).sum() - np.where(hl, lo * ll, 0.0).sum())
+            if np.abs(G.T @ y).max() <= 1e-7 * yn and cert < -1e-7 * yn * d.sc_b:
+                status = 2
+                break
+        if not np.isfinite(mu) or mu > 1e40:
             break
         dd = np.where(hu, lu / su, 0.0) + np.where(hl, ll / sl, 0.0)
         S = H + (G.T * dd) @ G
@@ -99,16 +110,117 @@ def ipm_model(d, x_init, ref, max_iter=60, tol_res=1e-9, tol_gap=1e-12, verbose=
         sl = np.where(hl, sl + ap * dsl, 1.0)
         lu = np.where(hu, lu + ad * dlu, 0.0)
         ll = np.where(hl, ll + ad * dll, 0.0)
-    if status != 0 and best is not None and best[0] <= 1e-7:
+    if status == 1 and best is not None and best[0] <= 1e-7:
         status = 0
     if status == 0 and best is not None:
         zeta = best[1]
     info = dict(path="ipm", merit=best[0] if best else None)
-    if status != 0:
+    if return_state and best is not None:
+        info["state"] = best[3]
+    if status == 1:
         y = lu - ll
         yn = np.abs(y).max()
         cert = (np.where(hu, up * lu, 0.0).sum() - np.where(hl, lo * ll, 0.0).sum())
         info["cert"] = (np.abs(G.T @ y).max() / yn, cert / yn)
-        if np.abs(G.T @ y).max() <= 1e-6 * yn and cert < -1e-6 * yn:
+        if np.abs(G.T @ y).max() <= 1e-6 * yn and cert < -1e-6 * yn * d.sc_b:
             status = 2
     return zeta, status, it + 1, info
+
+
+def polish_model(d, x_init, ref, act, max_rounds=24, tol_p=1e-9, tol_d=1e-9):
+    """Active-set endgame of the kernel: ``act`` is a list of (row, sign) pairs (sign +1: upper bound
+    active, -1: lower).  Schur complement on Hinv with dependency-dropping Cholesky, one step of
+    iterative refinement, then drop-most-negative / add-most-violated."""
+    n, m = d.n, d.m
+    G = d.Gs[:m, :n]
+    Y = d.Y[:m, :n]
+    q = d.Fx[:n] @ x_init + d.Fr[:n] @ ref
+    lo = d.lo0[:m] + d.Lx[:m] @ x_init
+    up = d.up0[:m] + d.Ux[:m] @ x_init
+    hl = d.has_lo[:m].astype(bool)
+    hu = d.has_up[:m].astype(bool)
+    zu = -(d.Hinv[:n, :n] @ q)
+    act = list(act)
+    for rnd in range(max_rounds):
+        na = len(act)
+        if na > n:
+            return None, rnd, "too_many"
+        rows = np.array([a[0] for a in act], int)
+        sg = np.array([a[1] for a in act], float)
+        b = np.where(sg > 0, up[rows], -lo[rows]) if na else np.zeros(0)
+        Gt = sg[:, None] * G[rows] if na else np.zeros((0, n))
+        Yt = sg[:, None] * Y[rows] if na else np.zeros((0, n))
+        S = Yt @ Gt.T
+        # Cholesky with dependency dropping
+        L = np.zeros((na, na))
+        keep = np.ones(na, bool)
+        dmax = np.max(np.diag(S)) if na else 1.0
+        for j in range(na):
+            v = S[j, j] - L[j, :j] @ L[j, :j]
+            if v <= 1e-11 * S[j, j] or v <= 1e-14 * dmax:
+                keep[j] = False
+                L[j, :] = 0.0
+                L[:, j] = 0.0
+                L[j, j] = 1.0
+                continue
+            L[j, j] = np.sqrt(v)
+            for i in range(j + 1, na):
+                L[i, j] = (S[i, j] - L[i, :j] @ L[j, :j]) / L[j, j]
+
+        def ssolve(r):
+            r = np.where(keep, r, 0.0)
+            y = np.linalg.solve(L, r) if na else r
+            x = np.linalg.solve(L.T, y) if na else y
+            return np.where(keep, x, 0.0)
+        lam = ssolve(Gt @ zu - b)
+        z = zu - Yt.T @ lam
+        for _ in range(2):
+            dl = ssolve(Gt @ z - b)
+            lam = lam + dl
+            z = z - Yt.T @ dl
+        t = G @ z
+        viol_u = np.where(hu, t - up, -np.inf)
+        viol_l = np.where(hl, lo - t, -np.inf)
+        # rows kept active are satisfied by construction
+        for (r_, s_), k_ in zip(act, keep):
+            if k_:
+                if s_ > 0:
+                    viol_u[r_] = -np.inf
+                else:
+                    viol_l[r_] = -np.inf
+        wu = int(np.argmax(viol_u))
+        wl = int(np.argmax(viol_l))
+        vmax = max(viol_u[wu], viol_l[wl])
+        lam_min = lam[keep].min() if keep.any() else 0.0
+        if lam_min < -tol_d * (1.0 + np.abs(lam).max(initial=0.0)):
+            j = int(np.argmin(np.where(keep, lam, np.inf)))
+            act.pop(j)
+            continue
+        if vmax > tol_p * d.sc_b:
+            # drop dependent rows first, then add the most violated
+            act = [a for a, k_ in zip(act, keep) if k_]
+            new = (wu, 1) if viol_u[wu] >= viol_l[wl] else (wl, -1)
+            if new in act:
+                return None, rnd, "cycle"
+            act.append(new)
+            continue
+        return z, rnd + 1, "ok"
+    return None, max_rounds, "rounds"
+
+
+def solve_model(d, x_init, ref, gap_stop=1e-8):
+    """IPM to a moderate tolerance, then the active-set endgame; falls back to a tight IPM."""
+    z, status, it, info = ipm_model(d, x_init, ref, tol_res=1e-7, tol_gap=gap_stop, return_state=True)
+    if info.get("path") == "unconstrained" or status != 0:
+        return z, status, it, info
+    su, sl, lu, ll = info["state"]
+    hl = d.has_lo[:d.m].astype(bool)
+    hu = d.has_up[:d.m].astype(bool)
+    act = [(i, 1) for i in np.nonzero(hu & (lu > su))[0]] + [(i, -1) for i in np.nonzero(hl & (ll > sl))[0]]
+    zp, rounds, why = polish_model(d, x_init, ref, act)
+    info["polish"] = (rounds, why, len(act))
+    if zp is not None:
+        return zp, 0, it, info
+    z2, status2, it2, info2 = ipm_model(d, x_init, ref)
+    info2["polish"] = info["polish"]
+    return z2, status2, it + it2, info2
