@@ -346,8 +346,14 @@ def _polish(out, P, q, E, e, G, h, s, max_rounds=40):
         U_, sv, Vt = np.linalg.svd(C, full_matrices=True)
         rk = int((sv > 1e-11 * sv[0]).sum()) if sv.size else 0
         z_p = Vt[:rk].T @ ((U_[:, :rk].T @ dvec) / sv[:rk])
-        if np.abs(C @ z_p - dvec).max(initial=0.0) > 1e-9 * (1.0 + np.abs(dvec).max(initial=0.0)):
-            return False                       # inconsistent active rows
+        incons = np.abs(C @ z_p - dvec)
+        if incons.max(initial=0.0) > 1e-9 * (1.0 + np.abs(dvec).max(initial=0.0)):
+            # the guessed rows cannot all hold with equality (near-parallel facets of the terminal
+            # set): release the guessed inequality row that fits worst and try again
+            if na == 0:
+                return False
+            act.pop(int(np.argmax(incons[p:])))
+            continue
         Nn = Vt[rk:].T
         if Nn.shape[1]:
             Hr = Nn.T @ P @ Nn

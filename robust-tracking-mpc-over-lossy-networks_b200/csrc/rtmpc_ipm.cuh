@@ -40,7 +40,7 @@ struct QPDev {
 
 // per-warp shared memory, in doubles
 __host__ __device__ inline int ipm_warp_doubles(const QPDev& P) {
-    return 9 * P.npad + 16 + P.npad * P.ss + 2 * P.va_len + 2 * P.mpad + 2 * P.npad /*act lists as ints*/;
+    return 9 * P.npad + 16 + P.npad * P.ss + 2 * P.va_len + 2 * P.mpad + 4 * P.npad /*act lists as ints*/;
 }
 __host__ __device__ inline int ipm_block_doubles(const QPDev& P) { return P.mpad * P.gs + P.npad * P.npad; }
 
@@ -181,7 +181,7 @@ __device__ __forceinline__ double chol_solve_warp(const double* __restrict__ S, 
 
 struct WarpSmem {
     double *zeta, *zu, *q, *hz, *rhs, *dz, *best, *xr, *S, *va, *vb, *vlo, *vup;
-    int *act_row, *act_sgn;
+    int *act_row, *act_sgn, *best_row, *best_sgn;
 };
 
 __device__ __forceinline__ WarpSmem carve(double* base, const QPDev& P) {
@@ -203,6 +203,8 @@ __device__ __forceinline__ WarpSmem carve(double* base, const QPDev& P) {
     w.vup = base; base += P.mpad;
     w.act_row = reinterpret_cast<int*>(base);
     w.act_sgn = w.act_row + 2 * P.npad;
+    w.best_row = w.act_sgn + 2 * P.npad;
+    w.best_sgn = w.best_row + 2 * P.npad;
     return w;
 }
 
@@ -345,7 +347,8 @@ __device__ bool polish_warp(const QPDev& P, const double* __restrict__ Gs, WarpS
 
 // build the active-set estimate {lam > s} from the interior-point state
 template <int R>
-__device__ __forceinline__ int build_active(const RowRegs<R>& st, WarpSmem& w, int lane, unsigned mask_u,
+__device__ __forceinline__ int build_active(const RowRegs<R>& st, int* __restrict__ out_row,
+                                            int* __restrict__ out_sgn, int lane, unsigned mask_u,
                                             unsigned mask_l, int nslots, int cap) {
     int na = 0;
 #pragma unroll
@@ -356,11 +359,11 @@ __device__ __forceinline__ int build_active(const RowRegs<R>& st, WarpSmem& w, i
             const bool al = ((mask_l >> r) & 1u) && st.ll[r] > st.sl[r];
             unsigned bu = __ballot_sync(RTMPC_FULL_MASK, au);
             int pu = na + __popc(bu & ((1u << lane) - 1u));
-            if (au && pu < cap) { w.act_row[pu] = row; w.act_sgn[pu] = 1; }
+            if (au && pu < cap) { out_row[pu] = row; out_sgn[pu] = 1; }
             na += __popc(bu);
             unsigned bl = __ballot_sync(RTMPC_FULL_MASK, al);
             int pl = na + __popc(bl & ((1u << lane) - 1u));
-            if (al && pl < cap) { w.act_row[pl] = row; w.act_sgn[pl] = -1; }
+            if (al && pl < cap) { out_row[pl] = row; out_sgn[pl] = -1; }
             na += __popc(bl);
         }
     }
@@ -488,7 +491,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
         }
 
         // ---- interior point ---------------------------------------------------------------
-        int phase = 1;
+        int next_try = 0, best_na = -1;
         double best_merit = RTMPC_INF;
         while (!done) {
             // A. residuals
@@ -536,42 +539,57 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
             ymax = warp_max(ymax);
             cert = warp_sum(cert);
             const double gy_max = warp_max(fabs(gy));
-            const double res = fmax(res_d / sc_q, rp / P.sc_b);
+            const double rd_rel = res_d / sc_q, rp_rel = rp / P.sc_b;
+            const double res = fmax(rd_rel, rp_rel);
             const double relgap = gap / (1.0 + fabs(pobj));
             const double merit = fmax(res, relgap);
-            if (merit < best_merit) { best_merit = merit; if (lane < npad) w.best[lane] = w.zeta[lane]; }
-            const bool conv1 = (res <= 1e-7 && relgap <= 1e-8);
-            const bool conv2 = (res <= 1e-9 && relgap <= 1e-12) || (best_merit <= 1e-8 && merit > 1e3 * best_merit);
-            if (!(mu == mu) || mu > 1e40) { status = RTMPC_MAX_ITER; break; }
-            if (ymax > 1e6 * sc_q && iters >= 3 && (gy_max <= 1e-7 * ymax) && (cert < -1e-7 * ymax * P.sc_b)) {
+            const bool bad = !(mu == mu) || !(mu <= 1e40) || !(merit == merit);
+            if (!bad && merit < best_merit) {
+                best_merit = merit;
+                if (lane < npad) w.best[lane] = w.zeta[lane];
+                if (merit <= 1e-3) best_na = build_active<R>(st, w.best_row, w.best_sgn, lane, mask_u, mask_l, nslots, 2 * npad);
+            }
+            // primal infeasibility certificate on the multiplier direction (Farkas)
+            if (!bad && ymax > 1e6 * sc_q && iters >= 3 && gy_max <= 1e-7 * ymax && cert < -1e-7 * ymax * P.sc_b) {
                 status = RTMPC_INFEASIBLE;
                 break;
             }
-            if (phase == 1 && conv1 && iters < P.max_iter) {
-                // moderate tolerance reached: the active set is usually identified -> endgame
-                int na = build_active<R>(st, w, lane, mask_u, mask_l, nslots, 2 * npad);
+            // conv1: accurate enough for the active set to be identified.  The second clause covers
+            // problems whose feasible set has no interior along some rows (multipliers unbounded):
+            // there the dual residual stalls while primal residual and gap collapse.
+            const bool conv1 = (res <= 1e-7 && relgap <= 1e-8) || (rp_rel <= 1e-8 && relgap <= 1e-9 && rd_rel <= 1e-3);
+            const bool conv2 = (res <= 1e-9 && relgap <= 1e-12);
+            const bool diverged = bad || merit > 1e3 * best_merit;
+            if (!diverged && conv1 && !conv2 && iters >= next_try && iters < P.max_iter) {
+                int na = build_active<R>(st, w.act_row, w.act_sgn, lane, mask_u, mask_l, nslots, 2 * npad);
                 int rounds = 0;
                 if (na <= n && polish_warp<R>(P, Gs, w, na, lane, mask_u, mask_l, nslots, &rounds)) {
                     status = RTMPC_OPTIMAL;
                     break;
                 }
-                phase = 2;   // keep iterating to the numerical floor, then try once more
-            } else if ((phase == 2 && conv2) || iters >= P.max_iter) {
-                if (best_merit <= 1e-7) {
-                    int na = build_active<R>(st, w, lane, mask_u, mask_l, nslots, 2 * npad);
+                next_try = iters + 3;
+            }
+            if (conv2 || diverged || iters >= P.max_iter) {
+                if (best_merit <= 1e-5 && best_na >= 0) {
+                    int na;
+                    if (conv2 && !diverged) {
+                        na = build_active<R>(st, w.act_row, w.act_sgn, lane, mask_u, mask_l, nslots, 2 * npad);
+                    } else {
+                        na = best_na;
+                        for (int i = lane; i < na && i < 2 * npad; i += 32) { w.act_row[i] = w.best_row[i]; w.act_sgn[i] = w.best_sgn[i]; }
+                        __syncwarp();
+                    }
                     int rounds = 0;
                     if (na <= n && polish_warp<R>(P, Gs, w, na, lane, mask_u, mask_l, nslots, &rounds)) {
                         status = RTMPC_OPTIMAL;
-                    } else {
-                        if (lane < npad) w.zeta[lane] = w.best[lane];
-                        __syncwarp();
-                        status = RTMPC_OPTIMAL_INACCURATE;
+                        break;
                     }
-                } else if ((gy_max <= 1e-6 * ymax) && (cert < -1e-6 * ymax * P.sc_b)) {
-                    status = RTMPC_INFEASIBLE;
-                } else {
-                    status = RTMPC_MAX_ITER;
                 }
+                if (lane < npad) w.zeta[lane] = w.best[lane];
+                __syncwarp();
+                if (best_merit <= 1e-7) status = RTMPC_OPTIMAL_INACCURATE;
+                else if (!bad && gy_max <= 1e-6 * ymax && cert < -1e-6 * ymax * P.sc_b) status = RTMPC_INFEASIBLE;
+                else status = RTMPC_MAX_ITER;
                 break;
             }
             iters += 1;

@@ -1,0 +1,172 @@
+"""Closed-loop parity: fused loop kernel + QP kernel against the oracle's golden runs on identical
+(theta, gamma, w) arrays.  Stated tolerance: trajectories within 1e-4 absolute over the
+whole horizon and identical integer sequences (Theta_t, s_t, q_t); asserted tighter (1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def _run(loop, T, refs, theta, gamma, w):
+    B = loop.B
+    rec = dict(x=[loop.x.cpu().numpy().copy()], x_nom=[loop.x_nom.cpu().numpy().copy()],
+               x_hat=[loop.x_hat.cpu().numpy().copy()], Theta=[], s_t=[], q_t=[], alive=[])
+    dev = loop.dev
+    for t in range(T):
+        rec["q_t"].append(loop.q_t.cpu().numpy().copy())
+        ref_d = torch.as_tensor(np.broadcast_to(refs[t], (B, loop.nx)).copy(), device=dev)
+        th = torch.as_tensor(theta[:, t].astype(np.int32).copy(), device=dev)
+        ga = torch.as_tensor(gamma[:, t].astype(np.int32).copy(), device=dev)
+        ww = torch.as_tensor(np.ascontiguousarray(w[:, t]), device=dev)
+        loop.step(ref_d, th, ga, ww)
+        for k, v in (("x", loop.x), ("x_nom", loop.x_nom), ("x_hat", loop.x_hat), ("Theta", loop.Theta), ("s_t", loop.s_t),
+                     ("alive", loop.alive)):
+            rec[k].append(v.cpu().numpy().copy())
+    return {k: np.stack(v, axis=1) for k, v in rec.items()}
+
+
+def test_config1_double_integrator_as_shipped():
+    from rtmpc_b200.rollout import RemoteLoop
+    s, g = H.load("sets_di.npz"), H.load("loop_di_tube.npz")
+    mpc = H.make_tube_mpc(s)
+    loop = RemoteLoop(mpc, 1, kind="tube", Z=H.poly(s, "Z"))
+    loop.reset(np.array([[1.0, 2.0]]))
+    r = _run(loop, 120, g["refs"], g["theta"][None], g["gamma"][None], g["w"][None])
+    assert np.abs(r["x"][0] - g["x"]).max() <= TOL
+    assert np.abs(r["x_nom"][0] - g["x_nom"]).max() <= TOL
+    assert np.abs(r["x_hat"][0] - g["x_hat"]).max() <= TOL
+    assert np.array_equal(r["Theta"][0], g["Theta"]) and np.array_equal(r["s_t"][0], g["s_t"])
+    assert np.array_equal(r["q_t"][0], g["q_t"])
+    assert loop.tube_max.item() < 1e-7                      # x - x_nom in Z at every step (the example's check)
+    err = loop.tracking_error(120).item()
+    ref_err = np.sqrt(((g["x"][:-1] - g["refs"]) ** 2).sum()) / 120
+    assert abs(err - ref_err) <= 1e-8
+
+
+def test_config2_cartpole_tube_and_track_four_loss_rates():
+    from rtmpc_b200.rollout import RemoteLoop
+    s, g = H.load("sets_cp.npz"), H.load("loop_cp_tube.npz")
+    mpc = H.make_tube_mpc(s)
+    loop = RemoteLoop(mpc, 4, kind="tube", Z=H.poly(s, "Z"))
+    loop.reset(np.zeros((4, 4)))
+    r = _run(loop, 250, g["refs"], g["theta"], g["gamma"], g["w"])
+    assert np.abs(r["x"] - g["tube_x"]).max() <= TOL
+    assert np.abs(r["x_hat"] - g["tube_x_hat"]).max() <= TOL
+    assert np.array_equal(r["Theta"], g["tube_Theta"]) and np.array_equal(r["s_t"], g["tube_s_t"])
+    assert np.array_equal(r["q_t"], g["tube_q_t"])
+    assert loop.tube_max.max().item() < 1e-7
+    assert loop.status_count[0].item() == 1000
+    trk = H.make_track_mpc(s)
+    loop = RemoteLoop(trk, 4, kind="track")
+    loop.reset(np.zeros((4, 4)))
+    r = _run(loop, 250, g["refs"], g["theta"], g["gamma"], g["w"])
+    assert np.abs(r["x"] - g["track_x"]).max() <= TOL
+    assert np.abs(r["x_hat"] - g["track_x_hat"]).max() <= TOL
+    assert np.array_equal(r["Theta"], g["track_Theta"])
+
+
+def test_config3_extended_cartpole_and_double_integrator():
+    from rtmpc_b200.rollout import RemoteLoop
+    for sets, golden, B in (("sets_di.npz", "loop_di_ext.npz", 1), ("sets_cp.npz", "loop_cp_ext.npz", 2)):
+        s, g = H.load(sets), H.load(golden)
+        mpc = H.make_tube_mpc(s, extended=True)
+        nx = s["A"].shape[0]
+        if B == 1:
+            th, ga, w, x, xh, xn, Th = (g[k][None] for k in ("theta", "gamma", "w", "x", "x_hat", "x_nom", "Theta"))
+            x0 = np.array([[1.0, 2.0]])
+        else:
+            th, ga, w, x, xh, xn, Th = (g[k] for k in ("theta", "gamma", "w", "x", "x_hat", "x_nom", "Theta"))
+            x0 = np.zeros((B, nx))
+        loop = RemoteLoop(mpc, B, kind="extended", Z=H.poly(s, "Z"))
+        loop.reset(x0)
+        r = _run(loop, th.shape[1], g["refs"], th, ga, w)
+        assert np.abs(r["x"] - x).max() <= TOL, golden
+        assert np.abs(r["x_hat"] - xh).max() <= TOL
+        assert np.abs(r["x_nom"] - xn).max() <= TOL
+        assert np.array_equal(r["Theta"], Th)
+        assert loop.tube_max.max().item() < 1e-7
+
+
+def test_reference_call_order_with_class_objects():
+    """The reference's own loop body (Example_of_Tube_Tracking_MPC_Over_Lossy_Network.py:118-163)
+    written against the drop-in classes, single instance."""
+    from rtmpc_b200.local_remote import ConsistentActuator, Estimator
+    s, g = H.load("sets_di.npz"), H.load("loop_di_tube.npz")
+    A, B = s["A"], s["B"]
+    mpc = H.make_tube_mpc(s)
+    K_ss = mpc.get_steady_state_controller_gain()
+    x0 = np.array([[1.0], [2.0]])
+    estim = Estimator(A, B, K_ss, x0[:], 10)
+    act = ConsistentActuator(A, B, K_ss, mpc.get_ancillary_controller_gain(), x0[:])
+    x = x0.copy()
+    x_hat = estim.get_estimate()
+    T = 40
+    for t in range(T):
+        qt = estim.get_qt()
+        pkt = mpc.determine_packet(x_hat, np.hstack((g["refs"][t, 0], 0)), qt)
+        estim.store_sent_control_sequence(pkt["U_t"])
+        u_t, plant_packet = act.process_packet(pkt, x, int(g["theta"][t]))
+        assert pkt["U_t"].shape == (1, 11) and u_t.shape == (1, 1)
+        x = A @ x + B @ u_t + g["w"][t].reshape(2, 1)
+        estim.update_estimate(plant_packet, int(g["gamma"][t]))
+        x_hat = estim.get_estimate()
+        assert act.get_Theta_t() == g["Theta"][t] and act.get_s_t() == g["s_t"][t]
+        assert np.abs(x[:, 0] - g["x"][t + 1]).max() <= TOL
+        assert np.abs(x_hat[:, 0] - g["x_hat"][t + 1]).max() <= TOL
+        assert np.abs(act.get_x_nom()[:, 0] - g["x_nom"][t + 1]).max() <= TOL
+    assert len(mpc.get_computational_times()) == T
+
+
+def test_device_rng_matches_host_restatement_and_sharding():
+    """RNG mode == explicit mode fed with the numpy Philox restatement; and splitting the batch over two
+    'ranks' with id_offset reproduces the unsplit run bit for bit (results independent of #GPUs)."""
+    from rtmpc_b200.rollout import RemoteLoop
+    s = H.load("sets_cp.npz")
+    mpc = H.make_tube_mpc(s)
+    Bn, T, seed = 64, 40, 679
+    hw = np.array([1e-4, 2.7e-3, 3e-4, 4.3e-2])
+    p = np.array([0.1 * (i % 10) for i in range(Bn)])
+    ref = np.array([0.5, 0, 0, 0])
+    a = RemoteLoop(mpc, Bn, kind="tube", w_half=hw)
+    a.reset()
+    ta = a.run(T, ref, p_loss=p, seed=seed, record=True).cpu().numpy()
+    th, ga, w = H.device_draws(seed, np.arange(Bn), T, p, hw)
+    b = RemoteLoop(mpc, Bn, kind="tube")
+    b.reset()
+    tb = b.run(T, ref, theta=th, gamma=ga, w=w, record=True).cpu().numpy()
+    assert np.abs(ta - tb).max() <= 1e-12
+    halves = []
+    for r in range(2):
+        c = RemoteLoop(mpc, Bn // 2, kind="tube", w_half=hw)
+        c.reset()
+        halves.append(c.run(T, ref, p_loss=p[r * 32:(r + 1) * 32], seed=seed, id_offset=r * 32, record=True).cpu().numpy())
+    assert np.array_equal(np.concatenate(halves), ta)
+
+
+def test_nonlinear_cartpole_plant_config4_slice():
+    """Config 4 loop structure: analytic cartpole ODE plant (10 sub-steps), controller from the
+    linear model.  Checked against the oracle's ODE restatement driving the same applied inputs."""
+    from oracle import ref_loop as rl
+    from rtmpc_b200.rollout import RemoteLoop
+    s = H.load("sets_cp.npz")
+    mpc = H.make_tube_mpc(s)
+    loop = RemoteLoop(mpc, 8, kind="tube", plant="cartpole")
+    loop.reset()
+    ref = torch.as_tensor(np.tile([0.5, 0, 0, 0.0], (8, 1)), device=loop.dev)
+    p = torch.as_tensor(np.linspace(0, 0.7, 8), device=loop.dev)
+    x = np.zeros((8, 4))
+    for t in range(60):
+        loop.step(ref, p_loss=p, seed=124)
+        u = loop.u.cpu().numpy()
+        for b in range(8):
+            xb = x[b]
+            for _ in range(10):
+                xb = rl.cartpole_ode_step(xb, u[b, 0])
+            x[b] = xb
+        assert np.abs(loop.x.cpu().numpy() - x).max() <= 1e-10
+    assert loop.status_count[2].item() == 0
+    assert np.abs(x[:, 0] - 0.5).max() < 0.45          # all carts moved towards the reference
