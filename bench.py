@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched tube-MPC QP solves per second (= closed-loop steps per second).
+
+Workload (BASELINE.json configs[1], SURVEY 8d "C2"): the reference's linearised-cartpole remote tube
+MPC experiment (Results/results_linear_system.py: nx=4, nu=1, N=20, T=250 control steps, x0=0,
+ref=(0.5,0,0,0), loss probability {0,...,0.9}[i mod 10], theta/gamma ~ Bernoulli, w ~ U(-hw,hw)) with
+4096 independent closed-loop instances per GPU.  One bench "step" = one full 250-step rollout of the
+batch = 1 024 000 QP solves per GPU.  Weak scaling: every rank runs its own 4096 instances (global
+instance id = rank*4096 + i seeds the Philox draws), no collective on the hot path; one NCCL
+all-gather of the per-instance tracking errors after the timed region.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps K --warmup W     # CPU arm: the oracle port on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "robust-tracking-mpc-over-lossy-networks_b200"))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched tube-MPC QP solves/sec (closed-loop steps/s)"
+B_PER_GPU = 4096
+T_STEPS = 250
+HW = np.array([1e-4, 2.7e-3, 3e-4, 4.3e-2])
+REF = np.array([0.5, 0.0, 0.0, 0.0])
+SEED = 679
+
+
+def load_sets():
+    return np.load(os.path.join(ROOT, "tests", "golden", "sets_cp.npz"))
+
+
+def ipm_flops_per_iteration(n, m):
+    """Algorithmic FP64 flops of one interior-point iteration of the condensed QP:
+    Schur assembly 2*m*n(n+1)/2, five G mat-vecs 2*m*n each (t, ta, tz, two G' products; the third
+    G' product shares its pass), Cholesky n^3/3, two triangular solve pairs 2*2*n^2."""
+    return 2 * m * n * (n + 1) // 2 + 5 * 2 * m * n + n ** 3 // 3 + 4 * n * n
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference's own cvxpy+Clarabel path cannot be installed here)
+# --------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        _W["tp"] = threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import ref_qp as rq
+    from oracle.ref_polytope import Polytope
+    s = load_sets()
+    P = lambda k: Polytope(s[k + "_A"], s[k + "_b"], normalize=False)      # noqa: E731
+    _W["qp"] = rq.build_tube_tracking(s["A"], s["B"], s["Q"], s["R"], int(s["N"]), s["P"], P("Xc"), P("Uc"), P("Xf"),
+                                      None, True)
+    _W["rq"] = rq
+
+
+def _cpu_worker_solve(args):
+    xs, refs = args
+    rq, qp = _W["rq"], _W["qp"]
+    n = 0
+    for x, r in zip(xs, refs):
+        sol, res = rq.solve_param(qp, x.copy(), r.copy())
+        n += 1
+    return n
+
+
+def cpu_sample_states(count):
+    """(x_hat, ref) pairs of the benchmark workload: states visited by the golden closed-loop runs at
+    the four loss rates, cycled to `count` (same distribution of easy/hard solves as the GPU run)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "loop_cp_tube.npz"))
+    xs = g["tube_xhat_in"].reshape(-1, 4)
+    refs = np.tile(g["refs"], (4, 1))
+    idx = (np.arange(count) * 7) % len(xs)
+    return xs[idx], refs[idx]
+
+
+def run_cpu_arm(solves_per_step, steps, warmup, cores=None):
+    import multiprocessing as mp
+    cores = cores or os.cpu_count()
+    xs, refs = cpu_sample_states(solves_per_step)
+    chunks = [(xs[i::cores], refs[i::cores]) for i in range(cores)]
+    ctx = mp.get_context("spawn")      # the parent may hold a CUDA context
+    with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_worker_solve, [(c[0][:2], c[1][:2]) for c in chunks])
+        t0 = time.perf_counter()
+        total = 0
+        for _ in range(steps):
+            total += sum(pool.map(_cpu_worker_solve, chunks))
+        dt = time.perf_counter() - t0
+    return total / dt, dt / steps, cores, total
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=3)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def build_controller():
+    from rtmpc_b200 import mpc
+    from rtmpc_b200.polytope import Polytope
+    s = load_sets()
+    P = lambda k: Polytope(s[k + "_A"], s[k + "_b"], normalize=False)      # noqa: E731
+    c = mpc.TubeTrackingMPC(s["A"], s["B"], s["Q"], s["R"], int(s["N"]))
+    c.set_input_constraints(P("U"))
+    c.set_state_constraints(P("X"))
+    c.load_sets(P("Z"), P("Xc"), P("Uc"), P("Xf"), fixed_initial_state=True)
+    return c, P("Z")
+
+
+def measure_fp64_peak(torch, dev):
+    """FP64 denominator: cuBLAS DGEMM 6144^3 (best of 5), measured in this run -- MEASURED_PEAKS.json
+    only holds HBM and bf16 figures."""
+    n = 6144
+    a = torch.randn(n, n, device=dev, dtype=torch.float64)
+    b = torch.randn(n, n, device=dev, dtype=torch.float64)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from rtmpc_b200 import _lib
+    from rtmpc_b200.rollout import RemoteLoop
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the GPU arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    mpc, Z = build_controller()
+    B, T = B_PER_GPU, T_STEPS
+    loop = RemoteLoop(mpc, B, kind="tube", w_half=HW, Z=Z)
+    ids0 = rank * B
+    p_loss = torch.as_tensor(np.array([0.1 * ((ids0 + i) % 10) for i in range(B)]), device=dev)
+    ref_d = torch.as_tensor(np.tile(REF, (B, 1)), device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)    # > 126 MB L2
+    n, m = mpc._prob.n, mpc._prob.m
+    f_it = ipm_flops_per_iteration(n, m)
+    stream = torch.cuda.current_stream()
+
+    def rollout(seed, solve_events=None):
+        loop.reset()
+        for t in range(T):
+            if solve_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            mpc._prob.solve_device(loop.x_hat, ref_d, loop.z, loop.U, loop.status, loop.iters, stream=stream.cuda_stream)
+            if solve_events is not None:
+                e1.record(stream)
+                solve_events.append((e0, e1))
+            loop.iters_total += loop.iters.sum()
+            loop.status_count += torch.bincount(loop.status, minlength=4)[:4]
+            _lib.check(L.rtmpc_loop_step(loop._h, loop.U.data_ptr(), loop.status.data_ptr(), None, 0, ref_d.data_ptr(),
+                                         None, None, None, p_loss.data_ptr(), seed, ids0, None, 0, stream.cuda_stream),
+                       "rtmpc_loop_step")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for wi in range(args.warmup):
+        rollout(SEED + 1000 + wi)
+    barrier()
+    fp64_peak = measure_fp64_peak(torch, dev) if rank == 0 else None
+    # ---- timed region: K rollouts, device-timed, L2 flushed between them -------------------------
+    launches0 = L.rtmpc_launch_count()
+    total_ms = 0.0
+    solve_ms = 0.0
+    iters_sum = 0
+    status_sum = np.zeros(4, np.int64)
+    with ClockSampler(local) as clk:
+        barrier()
+        for k in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ev = []
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rollout(SEED + k, ev)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            solve_ms += sum(a.elapsed_time(b) for a, b in ev)
+            iters_sum += int(loop.iters_total.item())
+            status_sum += loop.status_count.cpu().numpy()
+        barrier()
+    launches = L.rtmpc_launch_count() - launches0
+    err = loop.tracking_error(T)
+    tube_max = float(loop.tube_max.max().item())
+    t_ms = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        gathered = [torch.empty_like(err) for _ in range(world)]
+        g0 = time.perf_counter()
+        dist.all_gather(gathered, err)              # the only collective: statistics after the timed region
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - g0) * 1e3
+        err_all = torch.cat(gathered)
+    else:
+        gather_ms, err_all = 0.0, err
+    total_ms_max = float(t_ms.item())
+    solves = B * T * args.steps
+    value = solves * world / (total_ms_max * 1e-3)
+
+    # ---- e2e: same rollout through the host-buffer plugin call, H2D/D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        xh_h = torch.zeros(B, 4, dtype=torch.float64).pin_memory()
+        ref_h = torch.as_tensor(np.tile(REF, (B, 1))).pin_memory()
+        U_h = torch.zeros(B, 21, 1, dtype=torch.float64).pin_memory()
+        st_h = torch.zeros(B, dtype=torch.int32).pin_memory()
+        it_h = torch.zeros(B, dtype=torch.int32).pin_memory()
+        qp = mpc._prob
+        h2d = B * 4 * 8 * 2 + B * 21 * 8 + B * 4
+        d2h = B * 21 * 8 + B * 4 * 2 + B * 4 * 8
+
+        def rollout_host(seed):
+            loop.reset()
+            xh_h.zero_()
+            for t in range(T):
+                _lib.check(L.rtmpc_qp_solve_host(qp._h, B, xh_h.data_ptr(), ref_h.data_ptr(), None, 1, None,
+                                                 U_h.data_ptr(), st_h.data_ptr(), it_h.data_ptr()), "solve_host")
+                loop.U.copy_(U_h, non_blocking=True)
+                loop.status.copy_(st_h, non_blocking=True)
+                _lib.check(L.rtmpc_loop_step(loop._h, loop.U.data_ptr(), loop.status.data_ptr(), None, 0,
+                                             ref_d.data_ptr(), None, None, None, p_loss.data_ptr(), seed, ids0, None, 0,
+                                             stream.cuda_stream), "rtmpc_loop_step")
+                xh_h.copy_(loop.x_hat, non_blocking=True)
+                torch.cuda.synchronize()
+        rollout_host(SEED + 500)
+        barrier()
+        t0 = time.perf_counter()
+        ksteps = max(1, min(args.steps, 2))
+        for k in range(ksteps):
+            rollout_host(SEED + k)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * T * ksteps * world / float(dt.item()), "unit": "solves/s",
+               "h2d_bytes_per_step": h2d * T, "d2h_bytes_per_step": d2h * T,
+               "api": "rtmpc_qp_solve_host per control step (pinned host x_hat/ref in, U_t/status out) + loop step"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        flops = f_it * iters_sum                        # rank 0's timed region
+        achieved = flops / (solve_ms * 1e-3) / 1e12 if solve_ms > 0 else 0.0
+        cpu_value, cpu_step_s, cores, cpu_n = run_cpu_arm(args.cpu_solves, 1, 1)
+        out = {
+            "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "results_linear_system.py remote tube MPC (linearised cartpole nx=4 nu=1 N=20), "
+                                   f"{B} closed-loop instances per GPU x {T} control steps per bench step",
+                       "instances_per_gpu": B, "control_steps": T, "qp_n": n, "qp_rows_two_sided": m,
+                       "l2": "256 MB buffer written between timed rollouts (L2 flush)",
+                       "rng": "Philox4x32-10 on device, seed 679, counter = global instance id"},
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": "ipm_solve_kernel<3,9>",
+                         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure; "
+                                        f"its hbm_gbs={peaks.get('hbm_gbs')}, bf16_tflops={peaks.get('bf16_tflops')})",
+                         "flops_per_ipm_iteration": f_it, "ipm_iterations_in_timed_region": iters_sum,
+                         "kernel_ms_in_timed_region": solve_ms, "kernel_share_of_step": solve_ms / total_ms,
+                         "mean_iterations_per_solve": iters_sum / solves},
+            "cpu_baseline": {"value": cpu_value, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": f"{cpu_n} QP solves of the same workload (states of the golden closed-loop runs at "
+                                       "loss 0/0.3/0.6/0.9), oracle IPM + certified polish, one process per core"},
+            "checks": {"status_counts[optimal,max_iter,infeasible,inaccurate]": status_sum.tolist(),
+                       "max_tube_violation": tube_max, "mean_tracking_error": float(err_all.mean().item()),
+                       "stats_all_gather_ms": gather_ms},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    value, step_s, cores, total = run_cpu_arm(args.cpu_solves, args.steps, args.warmup)
+    s = load_sets()
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "results_linear_system.py remote tube MPC (linearised cartpole nx=4 nu=1 N=20); CPU arm "
+                                  f"solves a bounded sample of {args.cpu_solves} QPs of that workload per step",
+                      "note": "the reference's cvxpy+Clarabel stack cannot be installed offline; this is the oracle port "
+                              "of the same QP (dense Mehrotra IPM + certified polish) on all host cores"},
+           "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
+                            "sample": f"{args.cpu_solves} QP solves per step, {args.steps} steps"},
+           "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "terminal_rows": int(s["Xf_A"].shape[0])}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-solves", type=int, default=1024, dest="cpu_solves")
+    ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

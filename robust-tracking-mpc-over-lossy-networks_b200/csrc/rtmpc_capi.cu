@@ -137,7 +137,8 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
     }
     if (wpb < 1) { rtmpc_qp_destroy(q); return fail("rtmpc_qp_create: problem does not fit in shared memory"); }
     q->wpb = wpb; q->smem = smem;
-    cudaError_t e = cudaFuncSetAttribute((const void*)kc->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // several QPs may share one instantiation: always opt in to the device maximum
+    cudaError_t e = cudaFuncSetAttribute((const void*)kc->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) { rtmpc_qp_destroy(q); return fail("cudaFuncSetAttribute", e); }
     *out = q;
     return 0;
