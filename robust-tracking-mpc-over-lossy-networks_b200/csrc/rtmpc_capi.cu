@@ -197,7 +197,11 @@ int rtmpc_qp_solve_host(rtmpc_qp* q, int32_t B, const double* h_x_init, const do
     cudaStream_t s = q->stream;
     CU(cudaMemcpyAsync(q->s_x, h_x_init, (size_t)B * P.nx * sizeof(double), cudaMemcpyHostToDevice, s));
     if (h_ref) CU(cudaMemcpyAsync(q->s_ref, h_ref, (size_t)B * P.nx * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (h_sel) CU(cudaMemcpyAsync(q->s_sel, h_sel, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (h_sel) {
+        CU(cudaMemcpyAsync(q->s_sel, h_sel, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(q->s_status, 0xFF, (size_t)B * sizeof(int), s));   // unselected instances report -1
+        CU(cudaMemsetAsync(q->s_iters, 0, (size_t)B * sizeof(int), s));
+    }
     if (rtmpc_qp_solve(q, B, q->s_x, h_ref ? q->s_ref : nullptr, h_sel ? q->s_sel : nullptr, sel_value,
                        h_z ? q->s_z : nullptr, h_U_t ? q->s_U : nullptr, q->s_status, q->s_iters, s))
         return -1;

@@ -217,7 +217,7 @@ __device__ bool polish_warp(const QPDev& P, const double* __restrict__ Gs, WarpS
                             unsigned mask_u, unsigned mask_l, int nslots, int* rounds_out) {
     const int n = P.n, ss = P.ss, gs = P.gs, npad = P.npad;
     double* S = w.S;
-    const double tol_p = 1e-9 * P.sc_b;
+    const double tol_p = 1e-11 * P.sc_b;   // a row left inactive may be violated by at most this (scaled units)
     int rounds = 0;
     bool success = false;
     for (; rounds < 24; ++rounds) {

@@ -21,7 +21,7 @@ def _problem(d, x_init, ref):
     return n, m, G, q, lo, up, hl, hu
 
 
-def polish_model(d, x_init, ref, act, max_rounds=24, tol_p=1e-9, tol_d=1e-9):
+def polish_model(d, x_init, ref, act, max_rounds=24, tol_p=1e-11, tol_d=1e-9):
     """Active-set endgame of the kernel: ``act`` is a list of (row, sign) pairs (sign +1: upper bound
     active, -1: lower).  Schur complement on Hinv with dependency-dropping Cholesky, two steps of
     iterative refinement, then drop-most-negative / add-most-violated."""
