@@ -336,6 +336,7 @@ def _polish(out, P, q, E, e, G, h, s, max_rounds=40):
     n, p = P.shape[0], E.shape[0]
     act = list(np.nonzero(out.lam > s)[0])
     scale = 1.0 + np.abs(q).max(initial=0.0)
+    seen = set()
     for _ in range(max_rounds):
         na = len(act)
         Ga = G[act]
@@ -374,36 +375,42 @@ def _polish(out, P, q, E, e, G, h, s, max_rounds=40):
         lam_a = np.linalg.lstsq(C.T, -(P @ z + q), rcond=None)[0][p:] if na else np.zeros(0)
         viol = (G @ z - h) / (1.0 + np.abs(h))
         worst = int(np.argmax(viol)) if viol.size else -1
-        if worst >= 0 and viol[worst] > 1e-10:
-            if worst in act:
-                return False                   # inconsistent active rows
-            act.append(worst)
-            continue
+        feasible = not (worst >= 0 and viol[worst] > 1e-10)
         g = P @ z + q
-        if na:
-            M = np.c_[E.T, -E.T, Ga.T]
-            colscale = np.maximum(np.linalg.norm(M, axis=0), 1e-300)
-            xs, rn = nnls(M / colscale, -g, maxiter=20 * M.shape[1])
-            if rn <= 1e-9 * scale:
-                xs = xs / colscale
-                lam = np.zeros(G.shape[0])
-                lam[act] = xs[2 * p:]
-                out.z, out.lam, out.y = z, lam, xs[:p] - xs[p:2 * p]
-                out.res = 0.0
-                out.polished = True
-                return True
-            if lam_a.min() < 0:
-                act.pop(int(np.argmin(lam_a)))
-                continue
-            return False
+        if feasible:
+            # KKT certificate: a non-negative multiplier on the guessed rows closing stationarity
+            if na:
+                M = np.c_[E.T, -E.T, Ga.T]
+                colscale = np.maximum(np.linalg.norm(M, axis=0), 1e-300)
+                xs, rn = nnls(M / colscale, -g, maxiter=20 * M.shape[1])
+                if rn <= 1e-9 * scale:
+                    xs = xs / colscale
+                    lam = np.zeros(G.shape[0])
+                    lam[act] = xs[2 * p:]
+                    out.z, out.lam, out.y = z, lam, xs[:p] - xs[p:2 * p]
+                    out.res = 0.0
+                    out.polished = True
+                    return True
+            else:
+                yv = np.linalg.lstsq(E.T, -g, rcond=None)[0] if p else np.zeros(0)
+                if np.abs(g + (E.T @ yv if p else 0.0)).max() <= 1e-9 * scale:
+                    out.z, out.lam, out.y = z, np.zeros(G.shape[0]), yv
+                    out.res = 0.0
+                    out.polished = True
+                    return True
+                return False
+        # not optimal yet: first release a row whose multiplier has the wrong sign, else add the
+        # most violated row; never revisit an active set (anti-cycling)
+        if na and lam_a.min() < -1e-9 * scale:
+            act.pop(int(np.argmin(lam_a)))
+        elif not feasible and worst not in act:
+            act.append(worst)
         else:
-            yv = np.linalg.lstsq(E.T, -g, rcond=None)[0] if p else np.zeros(0)
-            if np.abs(g + (E.T @ yv if p else 0.0)).max() <= 1e-9 * scale:
-                out.z, out.lam, out.y = z, np.zeros(G.shape[0]), yv
-                out.res = 0.0
-                out.polished = True
-                return True
             return False
+        key = tuple(sorted(int(a) for a in act))
+        if key in seen:
+            return False
+        seen.add(key)
     return False
 
 

@@ -492,6 +492,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
 
         // ---- interior point ---------------------------------------------------------------
         int next_try = 0, best_na = -1;
+        bool boost = false;
         double best_merit = RTMPC_INF;
         while (!done) {
             // A. residuals
@@ -659,6 +660,13 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
             mu_aff = warp_sum(mu_aff) / (double)P.mtot;
             double sigma = mu_aff / mu;
             sigma = sigma * sigma * sigma;
+            double cross = 1.0;
+            if (boost) {
+                // safeguard against Mehrotra limit cycles: after a short step take a well-centred,
+                // first-order step (sigma >= 0.8, no second-order term)
+                sigma = fmax(sigma, 0.8);
+                cross = 0.0;
+            }
             const double smu = sigma * mu;
             // G. corrector right-hand side
 #pragma unroll
@@ -670,14 +678,14 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                         const double rpu = st.t[r] + st.su[r] - w.vup[row];
                         const double ds = -rpu - st.ta[r];
                         const double dl = -st.lu[r] * (1.0 + ds / st.su[r]);
-                        const double rc = st.su[r] * st.lu[r] + ds * dl - smu;
+                        const double rc = st.su[r] * st.lu[r] + cross * ds * dl - smu;
                         e2 += (-rc + st.lu[r] * rpu) / st.su[r] + st.lu[r];
                     }
                     if ((mask_l >> r) & 1u) {
                         const double rpl = -st.t[r] + st.sl[r] + w.vlo[row];
                         const double ds = -rpl + st.ta[r];
                         const double dl = -st.ll[r] * (1.0 + ds / st.sl[r]);
-                        const double rc = st.sl[r] * st.ll[r] + ds * dl - smu;
+                        const double rc = st.sl[r] * st.ll[r] + cross * ds * dl - smu;
                         e2 -= (-rc + st.ll[r] * rpl) / st.sl[r] + st.ll[r];
                     }
                     w.va[row] = e2;
@@ -701,7 +709,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                         const double rpu = st.t[r] + st.su[r] - w.vup[row];
                         const double dsa = -rpu - st.ta[r];
                         const double dla = -st.lu[r] * (1.0 + dsa / st.su[r]);
-                        const double rc = st.su[r] * st.lu[r] + dsa * dla - smu;
+                        const double rc = st.su[r] * st.lu[r] + cross * dsa * dla - smu;
                         const double ds = -rpu - st.tz[r];
                         const double dl = (-rc - st.lu[r] * ds) / st.su[r];
                         if (ds < 0.0) ap = fmin(ap, -st.su[r] / ds);
@@ -711,7 +719,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                         const double rpl = -st.t[r] + st.sl[r] + w.vlo[row];
                         const double dsa = -rpl + st.ta[r];
                         const double dla = -st.ll[r] * (1.0 + dsa / st.sl[r]);
-                        const double rc = st.sl[r] * st.ll[r] + dsa * dla - smu;
+                        const double rc = st.sl[r] * st.ll[r] + cross * dsa * dla - smu;
                         const double ds = -rpl + st.tz[r];
                         const double dl = (-rc - st.ll[r] * ds) / st.sl[r];
                         if (ds < 0.0) ap = fmin(ap, -st.sl[r] / ds);
@@ -722,6 +730,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
             const double eta = (mu < 1.0) ? fmin(0.9995, fmax(0.995, 1.0 - mu)) : 0.995;
             ap = fmin(1.0, eta * warp_min(ap));
             ad = fmin(1.0, eta * warp_min(ad));
+            boost = fmin(ap, ad) < 0.3;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (r < nslots) {
@@ -730,7 +739,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                         const double rpu = st.t[r] + st.su[r] - w.vup[row];
                         const double dsa = -rpu - st.ta[r];
                         const double dla = -st.lu[r] * (1.0 + dsa / st.su[r]);
-                        const double rc = st.su[r] * st.lu[r] + dsa * dla - smu;
+                        const double rc = st.su[r] * st.lu[r] + cross * dsa * dla - smu;
                         const double ds = -rpu - st.tz[r];
                         const double dl = (-rc - st.lu[r] * ds) / st.su[r];
                         st.su[r] += ap * ds;
@@ -740,7 +749,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                         const double rpl = -st.t[r] + st.sl[r] + w.vlo[row];
                         const double dsa = -rpl + st.ta[r];
                         const double dla = -st.ll[r] * (1.0 + dsa / st.sl[r]);
-                        const double rc = st.sl[r] * st.ll[r] + dsa * dla - smu;
+                        const double rc = st.sl[r] * st.ll[r] + cross * dsa * dla - smu;
                         const double ds = -rpl + st.tz[r];
                         const double dl = (-rc - st.ll[r] * ds) / st.sl[r];
                         st.sl[r] += ap * ds;

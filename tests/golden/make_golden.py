@@ -228,6 +228,7 @@ def main():
         xs = rng.uniform(-1, 1, (40, 2)) * np.array([6.0, 1.5])
         zr = np.full((40, reg.nz), np.nan)
         zt = np.full((40, tr["qp"].nz), np.nan)
+        pol = np.zeros((40, 2), int)
         for i, x in enumerate(xs):
             sol, r1 = rq.solve_param(reg, x.copy())
             if r1.status == "optimal":
@@ -235,7 +236,8 @@ def main():
             sol, r2 = rq.solve_param(tr["qp"], x.copy())
             if r2.status == "optimal":
                 zt[i] = r2.z
-        out = dict(xs=xs, z_reg=zr, z_tube=zt, P=tr["P"], K=tr["K"])
+            pol[i] = [r1.polished, r2.polished]
+        out = dict(xs=xs, z_reg=zr, z_tube=zt, P=tr["P"], K=tr["K"], polished=pol)
         for k in ("Z", "Xc", "Uc", "Xf"):
             out.update(_pk(k + "_mayne", tr[k]))
         np.savez_compressed(os.path.join(OUT, "qp_di_regulators.npz"), **out)

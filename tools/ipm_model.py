@@ -111,6 +111,7 @@ def solve_model(d, x_init, ref, max_iter=60, verbose=False):
     sc_q = 1.0 + np.abs(q).max()
     status = MAX_ITER
     phase, iters, next_try = 1, 0, 0
+    boost = False
     best_merit, best_zeta, best_act = np.inf, zeta.copy(), None
 
     def active():
@@ -200,8 +201,14 @@ def solve_model(d, x_init, ref, max_iter=60, verbose=False):
         mu_aff = (np.where(hu, (su + ap * dsu_a) * (lu + ad * dlu_a), 0.0).sum()
                   + np.where(hl, (sl + ap * dsl_a) * (ll + ad * dll_a), 0.0).sum()) / mtot
         sigma = (mu_aff / mu) ** 3
-        rcu = su * lu + dsu_a * dlu_a - sigma * mu
-        rcl = sl * ll + dsl_a * dll_a - sigma * mu
+        cross = 1.0
+        if boost:
+            # safeguard against Mehrotra's limit cycles: after a short step take a well-centred,
+            # first-order step (sigma >= 0.8, no second-order term)
+            sigma = max(sigma, 0.8)
+            cross = 0.0
+        rcu = su * lu + cross * dsu_a * dlu_a - sigma * mu
+        rcl = sl * ll + cross * dsl_a * dll_a - sigma * mu
         e2 = np.where(hu, (-rcu + lu * rpu) / su + lu, 0.0) - np.where(hl, (-rcl + ll * rpl) / sl + ll, 0.0)
         dz = solve(-hz - q - G.T @ e2)
         tz = G @ dz
@@ -212,6 +219,7 @@ def solve_model(d, x_init, ref, max_iter=60, verbose=False):
         eta = min(0.9995, max(0.995, 1.0 - mu)) if mu < 1 else 0.995
         ap = min(1.0, eta * min(maxstep(su, dsu, hu), maxstep(sl, dsl, hl)))
         ad = min(1.0, eta * min(maxstep(lu, dlu, hu), maxstep(ll, dll, hl)))
+        boost = min(ap, ad) < 0.3
         zeta = zeta + ap * dz
         su = np.where(hu, su + ap * dsu, 1.0)
         sl = np.where(hl, sl + ap * dsl, 1.0)
