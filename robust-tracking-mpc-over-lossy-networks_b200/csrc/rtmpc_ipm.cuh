@@ -55,12 +55,14 @@ __device__ __forceinline__ void gemv_rows(const double* __restrict__ Gs, int gs,
                                           const double* __restrict__ vec, int lane, double (&out)[R]) {
 #pragma unroll
     for (int r = 0; r < R; ++r) out[r] = 0.0;
+    const double* __restrict__ grow = Gs + lane * gs;
+    const int rstride = 32 * gs;
     for (int j = 0; j < npad; j += 2) {
         const double2 v = *reinterpret_cast<const double2*>(vec + j);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (r < nslots) {
-                const double2 g = *reinterpret_cast<const double2*>(Gs + (size_t)(r * 32 + lane) * gs + j);
+                const double2 g = *reinterpret_cast<const double2*>(grow + r * rstride + j);
                 out[r] = fma(g.x, v.x, out[r]);
                 out[r] = fma(g.y, v.y, out[r]);
             }
@@ -78,22 +80,22 @@ __device__ __forceinline__ void gemv_cols2(const double* __restrict__ Gs, int gs
     int i = 0;
     if (b) {
         for (; i + 1 < m; i += 2) {
-            double g0 = g[(size_t)i * gs], g1 = g[(size_t)(i + 1) * gs];
+            double g0 = g[i * gs], g1 = g[(i + 1) * gs];
             s0 = fma(g0, a[i], s0);
             u0 = fma(g0, b[i], u0);
             s1 = fma(g1, a[i + 1], s1);
             u1 = fma(g1, b[i + 1], u1);
         }
-        if (i < m) { double g0 = g[(size_t)i * gs]; s0 = fma(g0, a[i], s0); u0 = fma(g0, b[i], u0); }
+        if (i < m) { double g0 = g[i * gs]; s0 = fma(g0, a[i], s0); u0 = fma(g0, b[i], u0); }
     } else {
         double s2 = 0, s3 = 0;
         for (; i + 3 < m; i += 4) {
-            s0 = fma(g[(size_t)i * gs], a[i], s0);
-            s1 = fma(g[(size_t)(i + 1) * gs], a[i + 1], s1);
-            s2 = fma(g[(size_t)(i + 2) * gs], a[i + 2], s2);
-            s3 = fma(g[(size_t)(i + 3) * gs], a[i + 3], s3);
+            s0 = fma(g[i * gs], a[i], s0);
+            s1 = fma(g[(i + 1) * gs], a[i + 1], s1);
+            s2 = fma(g[(i + 2) * gs], a[i + 2], s2);
+            s3 = fma(g[(i + 3) * gs], a[i + 3], s3);
         }
-        for (; i < m; ++i) s0 = fma(g[(size_t)i * gs], a[i], s0);
+        for (; i < m; ++i) s0 = fma(g[i * gs], a[i], s0);
         s0 += s2; s1 += s3;
     }
     o1 = on ? (s0 + s1) : 0.0;
@@ -118,7 +120,7 @@ __device__ __forceinline__ void form_schur(const double* __restrict__ Gs, int gs
             const double di = dvec[i];
             double av[BS], bv[BS];
 #pragma unroll
-            for (int x = 0; x < BS; ++x) { av[x] = di * ga[(size_t)i * gs + x]; bv[x] = gb[(size_t)i * gs + x]; }
+            for (int x = 0; x < BS; ++x) { av[x] = di * ga[i * gs + x]; bv[x] = gb[i * gs + x]; }
 #pragma unroll
             for (int x = 0; x < BS; ++x)
 #pragma unroll
@@ -157,8 +159,9 @@ __device__ __forceinline__ bool chol_warp(double* __restrict__ S, int ss, int n,
         }
         double pk = __shfl_sync(RTMPC_FULL_MASK, s, k);
         if (!(pk > 0.0)) { ok = false; pk = 1e-300; }
-        const double dk = sqrt(pk);
-        if (lane >= k && lane < n) S[lane * ss + k] = (lane == k) ? dk : s / dk;
+        // the diagonal stores 1/L_kk: the substitutions multiply instead of divide
+        const double idk = __drcp_rn(sqrt(pk));
+        if (lane >= k && lane < n) S[lane * ss + k] = (lane == k) ? idk : s * idk;
         __syncwarp();
     }
     return ok;
@@ -167,12 +170,12 @@ __device__ __forceinline__ bool chol_warp(double* __restrict__ S, int ss, int n,
 // x = (L L')^{-1} rhs ; lane j holds rhs_j on entry and x_j on exit.
 __device__ __forceinline__ double chol_solve_warp(const double* __restrict__ S, int ss, int n, int lane, double r) {
     for (int k = 0; k < n; ++k) {                      // forward: L y = r
-        double yk = __shfl_sync(RTMPC_FULL_MASK, r, k) / S[k * ss + k];
+        double yk = __shfl_sync(RTMPC_FULL_MASK, r, k) * S[k * ss + k];
         if (lane == k) r = yk;
         else if (lane > k && lane < n) r = fma(-S[lane * ss + k], yk, r);
     }
     for (int k = n - 1; k >= 0; --k) {                 // backward: L' x = y
-        double xk = __shfl_sync(RTMPC_FULL_MASK, r, k) / S[k * ss + k];
+        double xk = __shfl_sync(RTMPC_FULL_MASK, r, k) * S[k * ss + k];
         if (lane == k) r = xk;
         else if (lane < k) r = fma(-S[k * ss + lane], xk, r);
     }
@@ -257,8 +260,8 @@ __device__ bool polish_warp(const QPDev& P, const double* __restrict__ Gs, WarpS
             const bool good = (pk > 1e-11 * skk) && (pk > 1e-14 * dmax);
             if (good) {
                 keep |= (1u << k);
-                const double dk = sqrt(pk);
-                if (lane >= k && mine) S[lane * ss + k] = (lane == k) ? dk : s / dk;
+                const double idk = __drcp_rn(sqrt(pk));
+                if (lane >= k && mine) S[lane * ss + k] = (lane == k) ? idk : s * idk;
             } else {
                 if (lane >= k && mine) S[lane * ss + k] = (lane == k) ? 1.0 : 0.0;
                 if (lane == k) for (int j = 0; j < k; ++j) S[k * ss + j] = 0.0;
@@ -392,7 +395,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
     // stage the shared matrices once per CTA
     for (int idx = threadIdx.x; idx < mpad * npad; idx += blockDim.x) {
         int i = idx / npad, j = idx - i * npad;
-        Gs[(size_t)i * gs + j] = P.G[idx];
+        Gs[i * gs + j] = P.G[idx];
     }
     for (int idx = threadIdx.x; idx < mpad * 2; idx += blockDim.x) Gs[(size_t)(idx >> 1) * gs + npad + (idx & 1)] = 0.0;
     for (int idx = threadIdx.x; idx < npad * npad; idx += blockDim.x) Hs_s[idx] = P.Hs[idx];
@@ -495,8 +498,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
         bool boost = false;
         double best_merit = RTMPC_INF;
         while (!done) {
-            // A. residuals
-            gemv_rows<R>(Gs, gs, npad, nslots, w.zeta, lane, st.t);
+            // A. residuals (t = G zeta is kept up to date incrementally: t += alpha_p * G dz)
             double acc_mu = 0.0, rp_max = 0.0, ymax = 0.0, cert = 0.0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -504,18 +506,20 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                     const int row = r * 32 + lane;
                     double e1 = 0.0;
                     if ((mask_u >> r) & 1u) {
-                        const double rpu = st.t[r] + st.su[r] - w.vup[row];
-                        e1 += st.lu[r] * rpu / st.su[r];
+                        const double up = w.vup[row];
+                        const double rpu = st.t[r] + st.su[r] - up;
+                        e1 = fma(st.lu[r] * __drcp_rn(st.su[r]), rpu, e1);
                         acc_mu = fma(st.su[r], st.lu[r], acc_mu);
                         rp_max = fmax(rp_max, fabs(rpu));
-                        cert = fma(w.vup[row], st.lu[r], cert);
+                        cert = fma(up, st.lu[r], cert);
                     }
                     if ((mask_l >> r) & 1u) {
-                        const double rpl = -st.t[r] + st.sl[r] + w.vlo[row];
-                        e1 -= st.ll[r] * rpl / st.sl[r];
+                        const double lo = w.vlo[row];
+                        const double rpl = -st.t[r] + st.sl[r] + lo;
+                        e1 = fma(-st.ll[r] * __drcp_rn(st.sl[r]), rpl, e1);
                         acc_mu = fma(st.sl[r], st.ll[r], acc_mu);
                         rp_max = fmax(rp_max, fabs(rpl));
-                        cert = fma(-w.vlo[row], st.ll[r], cert);
+                        cert = fma(-lo, st.ll[r], cert);
                     }
                     const double y = st.lu[r] - st.ll[r];
                     ymax = fmax(ymax, fabs(y));
@@ -594,70 +598,60 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                 break;
             }
             iters += 1;
-            // C. Schur complement
+            // C. Schur complement  S = Hs + G' diag(d) G,  d = lam_u/s_u + lam_l/s_l
             if (lane < npad) { w.hz[lane] = hzj; w.rhs[lane] = -hzj - qv - ge; }
             __syncwarp();   // va/vb consumed by every lane
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (r < nslots) {
                     double d = 0.0;
-                    if ((mask_u >> r) & 1u) d += st.lu[r] / st.su[r];
-                    if ((mask_l >> r) & 1u) d += st.ll[r] / st.sl[r];
+                    if ((mask_u >> r) & 1u) d = st.lu[r] * __drcp_rn(st.su[r]);
+                    if ((mask_l >> r) & 1u) d = fma(st.ll[r], __drcp_rn(st.sl[r]), d);
                     w.va[r * 32 + lane] = d;
                 }
             }
             __syncwarp();
             form_schur<BS>(Gs, gs, m, npad, Hs_s, w.va, w.S, ss, n, lane, blk_a, blk_b, blk_on);
             __syncwarp();
-            if (!chol_warp(w.S, ss, n, lane)) { /* regularised pivot: carry on, residual test decides */ }
-            // E. predictor
+            chol_warp(w.S, ss, n, lane);
+            // E. predictor (affine scaling direction)
             double dza = chol_solve_warp(w.S, ss, n, lane, (lane < n) ? w.rhs[lane] : 0.0);
             if (lane < npad) w.dz[lane] = dza;
             __syncwarp();
             gemv_rows<R>(Gs, gs, npad, nslots, w.dz, lane, st.ta);
-            double ap = 1.0, ad = 1.0;
+            // F. step lengths of the affine direction and mu_aff in one pass.  With
+            //    g = 1 + ds/s the affine multiplier step is dl = -lam*g, so
+            //    -s/ds = 1/(1-g)   (primal ratio, only where g < 1),   -lam/dl = 1/g (dual ratio, g > 0)
+            //    (s + ap ds)(lam + ad dl) = s*lam*(1 + ap*(g-1))*(1 - ad*g)
+            double pmax = 0.0, dmax = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (r < nslots) {
                     const int row = r * 32 + lane;
                     if ((mask_u >> r) & 1u) {
                         const double rpu = st.t[r] + st.su[r] - w.vup[row];
-                        const double ds = -rpu - st.ta[r];
-                        const double dl = -st.lu[r] * (1.0 + ds / st.su[r]);
-                        if (ds < 0.0) ap = fmin(ap, -st.su[r] / ds);
-                        if (dl < 0.0) ad = fmin(ad, -st.lu[r] / dl);
+                        const double h = (-rpu - st.ta[r]) * __drcp_rn(st.su[r]);     // ds/s
+                        const double g = 1.0 + h, sl_ = st.su[r] * st.lu[r];
+                        pmax = fmax(pmax, -h);
+                        dmax = fmax(dmax, g);
+                        c0 += sl_; c1 = fma(sl_, h, c1); c2 = fma(sl_, g, c2); c3 = fma(sl_ * h, g, c3);
                     }
                     if ((mask_l >> r) & 1u) {
                         const double rpl = -st.t[r] + st.sl[r] + w.vlo[row];
-                        const double ds = -rpl + st.ta[r];
-                        const double dl = -st.ll[r] * (1.0 + ds / st.sl[r]);
-                        if (ds < 0.0) ap = fmin(ap, -st.sl[r] / ds);
-                        if (dl < 0.0) ad = fmin(ad, -st.ll[r] / dl);
+                        const double h = (-rpl + st.ta[r]) * __drcp_rn(st.sl[r]);
+                        const double g = 1.0 + h, sl_ = st.sl[r] * st.ll[r];
+                        pmax = fmax(pmax, -h);
+                        dmax = fmax(dmax, g);
+                        c0 += sl_; c1 = fma(sl_, h, c1); c2 = fma(sl_, g, c2); c3 = fma(sl_ * h, g, c3);
                     }
                 }
             }
-            ap = warp_min(ap);
-            ad = warp_min(ad);
-            double mu_aff = 0.0;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (r < nslots) {
-                    const int row = r * 32 + lane;
-                    if ((mask_u >> r) & 1u) {
-                        const double rpu = st.t[r] + st.su[r] - w.vup[row];
-                        const double ds = -rpu - st.ta[r];
-                        const double dl = -st.lu[r] * (1.0 + ds / st.su[r]);
-                        mu_aff = fma(st.su[r] + ap * ds, st.lu[r] + ad * dl, mu_aff);
-                    }
-                    if ((mask_l >> r) & 1u) {
-                        const double rpl = -st.t[r] + st.sl[r] + w.vlo[row];
-                        const double ds = -rpl + st.ta[r];
-                        const double dl = -st.ll[r] * (1.0 + ds / st.sl[r]);
-                        mu_aff = fma(st.sl[r] + ap * ds, st.ll[r] + ad * dl, mu_aff);
-                    }
-                }
-            }
-            mu_aff = warp_sum(mu_aff) / (double)P.mtot;
+            pmax = warp_max(pmax);
+            dmax = warp_max(dmax);
+            double ap = (pmax > 1.0) ? 1.0 / pmax : 1.0;
+            double ad = (dmax > 1.0) ? 1.0 / dmax : 1.0;
+            c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); c3 = warp_sum(c3);
+            const double mu_aff = (c0 + ap * c1 - ad * c2 - ap * ad * c3) / (double)P.mtot;
             double sigma = mu_aff / mu;
             sigma = sigma * sigma * sigma;
             double cross = 1.0;
@@ -668,25 +662,26 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                 cross = 0.0;
             }
             const double smu = sigma * mu;
-            // G. corrector right-hand side
+            // G. corrector right-hand side.  With du = lam/s:
+            //    e2 = lam + (-rc + lam*rp)/s = du*rp + smu/s + cross*du*ds_a*g      (rc = s*lam + cross*ds_a*dl_a - smu)
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (r < nslots) {
                     const int row = r * 32 + lane;
                     double e2 = 0.0;
                     if ((mask_u >> r) & 1u) {
+                        const double is = __drcp_rn(st.su[r]);
                         const double rpu = st.t[r] + st.su[r] - w.vup[row];
-                        const double ds = -rpu - st.ta[r];
-                        const double dl = -st.lu[r] * (1.0 + ds / st.su[r]);
-                        const double rc = st.su[r] * st.lu[r] + cross * ds * dl - smu;
-                        e2 += (-rc + st.lu[r] * rpu) / st.su[r] + st.lu[r];
+                        const double dsa = -rpu - st.ta[r];
+                        const double du = st.lu[r] * is, g = fma(dsa, is, 1.0);
+                        e2 += fma(du, rpu, smu * is) + cross * du * dsa * g;
                     }
                     if ((mask_l >> r) & 1u) {
+                        const double is = __drcp_rn(st.sl[r]);
                         const double rpl = -st.t[r] + st.sl[r] + w.vlo[row];
-                        const double ds = -rpl + st.ta[r];
-                        const double dl = -st.ll[r] * (1.0 + ds / st.sl[r]);
-                        const double rc = st.sl[r] * st.ll[r] + cross * ds * dl - smu;
-                        e2 -= (-rc + st.ll[r] * rpl) / st.sl[r] + st.ll[r];
+                        const double dsa = -rpl + st.ta[r];
+                        const double du = st.ll[r] * is, g = fma(dsa, is, 1.0);
+                        e2 -= fma(du, rpl, smu * is) + cross * du * dsa * g;
                     }
                     w.va[row] = e2;
                 }
@@ -699,62 +694,67 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
             if (lane < npad) w.dz[lane] = dzc;
             __syncwarp();
             gemv_rows<R>(Gs, gs, npad, nslots, w.dz, lane, st.tz);
-            // H. step lengths and update
-            ap = RTMPC_INF; ad = RTMPC_INF;
+            // H. combined step:  ds = -rp -/+ tz,  dl = -lam - du*ds + smu/s + cross*du*ds_a*g
+            //    ratios: -s/ds = 1/(-ds/s), -lam/dl = 1/(-dl/lam)
+            pmax = 0.0; dmax = 0.0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (r < nslots) {
                     const int row = r * 32 + lane;
                     if ((mask_u >> r) & 1u) {
+                        const double is = __drcp_rn(st.su[r]);
                         const double rpu = st.t[r] + st.su[r] - w.vup[row];
                         const double dsa = -rpu - st.ta[r];
-                        const double dla = -st.lu[r] * (1.0 + dsa / st.su[r]);
-                        const double rc = st.su[r] * st.lu[r] + cross * dsa * dla - smu;
+                        const double du = st.lu[r] * is, g = fma(dsa, is, 1.0);
                         const double ds = -rpu - st.tz[r];
-                        const double dl = (-rc - st.lu[r] * ds) / st.su[r];
-                        if (ds < 0.0) ap = fmin(ap, -st.su[r] / ds);
-                        if (dl < 0.0) ad = fmin(ad, -st.lu[r] / dl);
+                        const double dl = -st.lu[r] - du * ds + smu * is + cross * du * dsa * g;
+                        pmax = fmax(pmax, -ds * is);
+                        dmax = fmax(dmax, -dl * __drcp_rn(st.lu[r]));
                     }
                     if ((mask_l >> r) & 1u) {
+                        const double is = __drcp_rn(st.sl[r]);
                         const double rpl = -st.t[r] + st.sl[r] + w.vlo[row];
                         const double dsa = -rpl + st.ta[r];
-                        const double dla = -st.ll[r] * (1.0 + dsa / st.sl[r]);
-                        const double rc = st.sl[r] * st.ll[r] + cross * dsa * dla - smu;
+                        const double du = st.ll[r] * is, g = fma(dsa, is, 1.0);
                         const double ds = -rpl + st.tz[r];
-                        const double dl = (-rc - st.ll[r] * ds) / st.sl[r];
-                        if (ds < 0.0) ap = fmin(ap, -st.sl[r] / ds);
-                        if (dl < 0.0) ad = fmin(ad, -st.ll[r] / dl);
+                        const double dl = -st.ll[r] - du * ds + smu * is + cross * du * dsa * g;
+                        pmax = fmax(pmax, -ds * is);
+                        dmax = fmax(dmax, -dl * __drcp_rn(st.ll[r]));
                     }
                 }
             }
+            pmax = warp_max(pmax);
+            dmax = warp_max(dmax);
             const double eta = (mu < 1.0) ? fmin(0.9995, fmax(0.995, 1.0 - mu)) : 0.995;
-            ap = fmin(1.0, eta * warp_min(ap));
-            ad = fmin(1.0, eta * warp_min(ad));
+            ap = (eta < pmax) ? eta / pmax : 1.0;        // min(1, eta * min ratio)
+            ad = (eta < dmax) ? eta / dmax : 1.0;
             boost = fmin(ap, ad) < 0.3;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (r < nslots) {
                     const int row = r * 32 + lane;
+                    const double tr = st.t[r];
                     if ((mask_u >> r) & 1u) {
-                        const double rpu = st.t[r] + st.su[r] - w.vup[row];
+                        const double is = __drcp_rn(st.su[r]);
+                        const double rpu = tr + st.su[r] - w.vup[row];
                         const double dsa = -rpu - st.ta[r];
-                        const double dla = -st.lu[r] * (1.0 + dsa / st.su[r]);
-                        const double rc = st.su[r] * st.lu[r] + cross * dsa * dla - smu;
+                        const double du = st.lu[r] * is, g = fma(dsa, is, 1.0);
                         const double ds = -rpu - st.tz[r];
-                        const double dl = (-rc - st.lu[r] * ds) / st.su[r];
-                        st.su[r] += ap * ds;
-                        st.lu[r] += ad * dl;
+                        const double dl = -st.lu[r] - du * ds + smu * is + cross * du * dsa * g;
+                        st.su[r] = fma(ap, ds, st.su[r]);
+                        st.lu[r] = fma(ad, dl, st.lu[r]);
                     }
                     if ((mask_l >> r) & 1u) {
-                        const double rpl = -st.t[r] + st.sl[r] + w.vlo[row];
+                        const double is = __drcp_rn(st.sl[r]);
+                        const double rpl = -tr + st.sl[r] + w.vlo[row];
                         const double dsa = -rpl + st.ta[r];
-                        const double dla = -st.ll[r] * (1.0 + dsa / st.sl[r]);
-                        const double rc = st.sl[r] * st.ll[r] + cross * dsa * dla - smu;
+                        const double du = st.ll[r] * is, g = fma(dsa, is, 1.0);
                         const double ds = -rpl + st.tz[r];
-                        const double dl = (-rc - st.ll[r] * ds) / st.sl[r];
-                        st.sl[r] += ap * ds;
-                        st.ll[r] += ad * dl;
+                        const double dl = -st.ll[r] - du * ds + smu * is + cross * du * dsa * g;
+                        st.sl[r] = fma(ap, ds, st.sl[r]);
+                        st.ll[r] = fma(ad, dl, st.ll[r]);
                     }
+                    st.t[r] = fma(ap, st.tz[r], tr);      // t = G zeta stays consistent with zeta += ap dz
                 }
             }
             if (lane < npad) w.zeta[lane] += ap * dzc;
