@@ -217,11 +217,12 @@ def run_gpu_arm(args):
             if solve_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-            mpc._prob.solve_device(loop.x_hat, ref_d, loop.z, loop.U, loop.status, loop.iters, stream=stream.cuda_stream)
+            mpc._prob.solve_device(loop.x_hat, ref_d, None, loop.U, loop.status, loop.iters, stream=stream.cuda_stream,
+                                   warm=loop.warm)
             if solve_events is not None:
                 e1.record(stream)
                 solve_events.append((e0, e1))
-            loop.iters_total += loop.iters.sum()
+            loop.accumulate_iters()
             loop.status_count += torch.bincount(loop.status, minlength=4)[:4]
             _lib.check(L.rtmpc_loop_step(loop._h, loop.U.data_ptr(), loop.status.data_ptr(), None, 0, ref_d.data_ptr(),
                                          None, None, None, p_loss.data_ptr(), seed, ids0, None, 0, stream.cuda_stream),
@@ -232,15 +233,18 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    work = torch.zeros(1, device=dev, dtype=torch.int64)      # algorithmic flops executed by the active-set kernel
+    mpc._prob.set_work_counter(work)
     for wi in range(args.warmup):
         rollout(SEED + 1000 + wi)
     barrier()
+    work.zero_()
     fp64_peak = measure_fp64_peak(torch, dev) if rank == 0 else None
     # ---- timed region: K rollouts, device-timed, L2 flushed between them -------------------------
     launches0 = L.rtmpc_launch_count()
     total_ms = 0.0
     solve_ms = 0.0
-    iters_sum = 0
+    iters_sum = np.zeros(3, np.int64)
     status_sum = np.zeros(4, np.int64)
     with ClockSampler(local) as clk:
         barrier()
@@ -255,10 +259,12 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
             total_ms += e0.elapsed_time(e1)
             solve_ms += sum(a.elapsed_time(b) for a, b in ev)
-            iters_sum += int(loop.iters_total.item())
+            iters_sum += loop.iters_total.cpu().numpy()
             status_sum += loop.status_count.cpu().numpy()
         barrier()
     launches = L.rtmpc_launch_count() - launches0
+    as_flops = int(work.item())
+    mpc._prob.set_work_counter(None)
     err = loop.tracking_error(T)
     tube_max = float(loop.tube_max.max().item())
     t_ms = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -290,9 +296,10 @@ def run_gpu_arm(args):
 
         def rollout_host(seed):
             loop.reset()
+            qp.warm_reset()
             xh_h.zero_()
             for t in range(T):
-                _lib.check(L.rtmpc_qp_solve_host(qp._h, B, xh_h.data_ptr(), ref_h.data_ptr(), None, 1, None,
+                _lib.check(L.rtmpc_qp_solve_host(qp._h, B, xh_h.data_ptr(), ref_h.data_ptr(), None, 1, 1, None,
                                                  U_h.data_ptr(), st_h.data_ptr(), it_h.data_ptr()), "solve_host")
                 loop.U.copy_(U_h, non_blocking=True)
                 loop.status.copy_(st_h, non_blocking=True)
@@ -321,7 +328,7 @@ def run_gpu_arm(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        flops = f_it * iters_sum                        # rank 0's timed region
+        flops = as_flops + f_it * int(iters_sum[0])      # rank 0's timed region: active-set kernel + IPM fallback
         achieved = flops / (solve_ms * 1e-3) / 1e12 if solve_ms > 0 else 0.0
         cpu_value, cpu_step_s, cores, cpu_n = run_cpu_arm(args.cpu_solves, 1, 1)
         out = {
@@ -336,14 +343,17 @@ def run_gpu_arm(args):
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": "ipm_solve_kernel<3,9>",
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": "as_solve_kernel<9,28> (+ ipm_solve_kernel<3,9> on handed-over instances)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure; "
                                         f"its hbm_gbs={peaks.get('hbm_gbs')}, bf16_tflops={peaks.get('bf16_tflops')})",
-                         "flops_per_ipm_iteration": f_it, "ipm_iterations_in_timed_region": iters_sum,
+                         "algorithmic_flops_active_set": as_flops, "flops_per_ipm_iteration": f_it,
+                         "ipm_iterations_in_timed_region": int(iters_sum[0]),
+                         "active_set_steps_in_timed_region": int(iters_sum[1]),
+                         "certification_rounds_in_timed_region": int(iters_sum[2]),
                          "kernel_ms_in_timed_region": solve_ms, "kernel_share_of_step": solve_ms / total_ms,
-                         "mean_iterations_per_solve": iters_sum / solves},
+                         "mean_active_set_steps_per_solve": float(iters_sum[1]) / solves},
             "cpu_baseline": {"value": cpu_value, "unit": "solves/s", "cores": cores, "kind": "port",
                              "sample": f"{cpu_n} QP solves of the same workload (states of the golden closed-loop runs at "
                                        "loss 0/0.3/0.6/0.9), oracle IPM + certified polish, one process per core"},

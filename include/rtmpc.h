@@ -22,13 +22,19 @@
 extern "C" {
 #endif
 
-#define RTMPC_ABI_VERSION 1
+#define RTMPC_ABI_VERSION 2
 
 /* per-instance solver status (replaces cvxpy's `prob.status` string, TubeTrackingMPC.py:185) */
 #define RTMPC_OPTIMAL            0   /* KKT-certified active-set point                          */
 #define RTMPC_MAX_ITER           1   /* no convergence (reference: status printed, values kept) */
 #define RTMPC_INFEASIBLE         2   /* reference: `.value is None` -> U_t = None (:215-221)    */
 #define RTMPC_OPTIMAL_INACCURATE 3   /* interior-point tolerance reached, certificate not found */
+#define RTMPC_FALLBACK_STATUS  (-2)  /* transient, never returned: active-set kernel handed the instance
+                                        to the interior-point kernel inside rtmpc_qp_solve           */
+
+/* solution methods of rtmpc_qp_solve (rtmpc_qp_set_method) */
+#define RTMPC_METHOD_ACTIVE_SET      0  /* dual active-set kernel, interior point only as fallback (default) */
+#define RTMPC_METHOD_INTERIOR_POINT  1  /* interior-point kernel for every instance                          */
 
 typedef struct rtmpc_qp rtmpc_qp;       /* one condensed QP resident on one GPU                  */
 typedef struct rtmpc_loop rtmpc_loop;   /* closed-loop model + per-instance state on one GPU     */
@@ -71,6 +77,8 @@ typedef struct rtmpc_qp_desc {
     double sc_b;            /* 1 + typical |bound| (scaled units)                                */
     int32_t max_iter;       /* interior-point iteration cap (Clarabel default 200; we use 60)    */
     int32_t reserved;
+    const int32_t* shift;   /* [mpad] row holding the same constraint one stage earlier (-1: none),
+                               used to move a warm-start active set one control step on; or NULL    */
 } rtmpc_qp_desc;
 
 /* Library / device ------------------------------------------------------------------------- */
@@ -91,21 +99,38 @@ void rtmpc_qp_destroy(rtmpc_qp* qp);
  *   d_x_init [B*nx], d_ref [B*nx] (may be NULL for the regulator variants)
  *   d_sel    [B] or NULL: instance b is solved only if d_sel[b] == sel_value (the gamma_t switch of
  *                          ExtendedTubeTrackingMPC.solve_optimization_problem, :307-349)
+ *   d_warm   [B*rtmpc_qp_warm_stride()] int32 or NULL: per-instance warm-start state, read and
+ *            rewritten by every solve.  Entry 0 = number of active rows of the last certified
+ *            solution (-1 = none, initialise the array with -1), then the signed rows.  The next
+ *            solve moves that set one stage earlier (desc.shift) and starts from it; the result
+ *            does not depend on it (every solution is KKT-certified), only the work does.
  *   d_z      [B*nz]        un-condensed solution [x_0..x_N | u_0..u_{N-1} | x_bar | u_bar], or NULL
  *   d_U_t    [B*(N+1)*nu]  packet payload, time-major: U_t[b][k][:] ; last column u_bar + K x_bar
  *                          (only u_0..u_{N-1} are written when the variant has no steady state)
- *   d_status [B], d_iters [B]
+ *   d_status [B] (may be NULL)
+ *   d_iters  [B] (may be NULL): bits 0-11 interior-point iterations, bits 12-23 active-set steps
+ *            (rows added + rows dropped), bits 24-31 certification / endgame rounds
  * Infeasible instances get NaN payloads (the reference returns None).
  */
 int rtmpc_qp_solve(rtmpc_qp* qp, int32_t B, const double* d_x_init, const double* d_ref,
-                   const int32_t* d_sel, int32_t sel_value, double* d_z, double* d_U_t,
+                   const int32_t* d_sel, int32_t sel_value, int32_t* d_warm, double* d_z, double* d_U_t,
                    int32_t* d_status, int32_t* d_iters, void* stream);
+int32_t rtmpc_qp_warm_stride(rtmpc_qp* qp);     /* int32 entries per instance of d_warm (npad + 1) */
 
 /* Same call with HOST buffers: copies in, solves, copies out, synchronises.  This is the
- * reference-facing plugin call (numpy arrays in, numpy arrays out). */
+ * reference-facing plugin call (numpy arrays in, numpy arrays out).  warm != 0 keeps the
+ * warm-start state inside the handle between calls (instance b of consecutive calls with the same
+ * B is taken to be the same closed loop one control step later; rtmpc_qp_warm_reset forgets it). */
 int rtmpc_qp_solve_host(rtmpc_qp* qp, int32_t B, const double* h_x_init, const double* h_ref,
-                        const int32_t* h_sel, int32_t sel_value, double* h_z, double* h_U_t,
+                        const int32_t* h_sel, int32_t sel_value, int32_t warm, double* h_z, double* h_U_t,
                         int32_t* h_status, int32_t* h_iters);
+int rtmpc_qp_warm_reset(rtmpc_qp* qp);
+
+/* RTMPC_METHOD_*: which kernel rtmpc_qp_solve runs (default: active set + interior-point fallback) */
+int rtmpc_qp_set_method(rtmpc_qp* qp, int32_t method);
+/* device counter (or NULL) to which the active-set kernel adds the algorithmic FP64 flops it executes
+ * (bench.py's roofline numerator) */
+int rtmpc_qp_set_work_counter(rtmpc_qp* qp, uint64_t* d_counter);
 
 /* number of kernels this library has launched so far in this process (bench's gpu_launches) */
 int64_t rtmpc_launch_count(void);

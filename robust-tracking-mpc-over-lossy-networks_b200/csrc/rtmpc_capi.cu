@@ -6,7 +6,7 @@
 #include <string>
 #include <vector>
 
-#include "rtmpc_ipm.cuh"
+#include "rtmpc_launch.h"
 #include "rtmpc_loop.cuh"
 
 using namespace rtmpc;
@@ -28,13 +28,17 @@ static int fail(const char* what, cudaError_t e = cudaSuccess) {
 struct rtmpc_qp {
     QPDev dev;
     std::vector<void*> allocs;
-    int bs = 0, r = 0, wpb = 8;
-    size_t smem = 0;
     int device = 0, num_sms = 0;
-    // staging for the host-buffer entry point (grow-only)
-    int cap = 0;
+    int ipm_wpb = 8, as_wpb = 0, as_g_in_smem = 0;
+    size_t ipm_smem = 0, as_smem = 0;
+    int method = RTMPC_METHOD_ACTIVE_SET;
+    unsigned long long* d_work = nullptr;   // algorithmic flop counter of the active-set kernel
+    // grow-only scratch (status of callers that pass none; staging of the host-buffer entry point)
+    int cap = 0, warm_cap = 0;
+    int* s_tmp_status = nullptr;
     double *s_x = nullptr, *s_ref = nullptr, *s_z = nullptr, *s_U = nullptr;
-    int *s_sel = nullptr, *s_status = nullptr, *s_iters = nullptr;
+    int *s_sel = nullptr, *s_status = nullptr, *s_iters = nullptr, *s_warm = nullptr;
+    int tmp_cap = 0;
     cudaStream_t stream = nullptr;
 };
 
@@ -48,20 +52,6 @@ static int upload(rtmpc_qp* q, const T* src, size_t count, const T** dst) {
     CU(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
     *dst = static_cast<const T*>(p);
     return 0;
-}
-
-typedef void (*ipm_fn)(QPDev, int, const double*, const double*, const int*, int, double*, double*, int*, int*);
-struct KernelChoice { int bs, r; ipm_fn fn; };
-static const KernelChoice kChoices[] = {
-    {2, 4, ipm_solve_kernel<2, 4>},   {3, 9, ipm_solve_kernel<3, 9>},   {3, 16, ipm_solve_kernel<3, 16>},
-    {4, 24, ipm_solve_kernel<4, 24>}, {5, 32, ipm_solve_kernel<5, 32>},
-};
-
-static const KernelChoice* pick_kernel(int n, int mpad) {
-    const int bs_need = (n + 6) / 7, r_need = mpad / 32;
-    for (const auto& c : kChoices)
-        if (c.bs >= bs_need && c.r >= r_need) return &c;
-    return nullptr;
 }
 
 extern "C" {
@@ -86,9 +76,11 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
     if (d->n < 1 || d->n > 32 || d->npad < d->n || d->npad > 32 || (d->npad & 3))
         return fail("rtmpc_qp_create: need 1 <= n <= npad <= 32 and npad % 4 == 0");
     if (d->nx < 1 || d->nx > 8 || d->nu < 1 || d->nu > 4) return fail("rtmpc_qp_create: need nx <= 8, nu <= 4");
-    if (d->mpad < 32 || (d->mpad & 31) || d->m > d->mpad) return fail("rtmpc_qp_create: mpad must be a multiple of 32 >= m");
-    const KernelChoice* kc = pick_kernel(d->n, d->mpad);
-    if (!kc) return fail("rtmpc_qp_create: problem too large for the compiled kernel set (mpad <= 1024)");
+    if (d->mpad < 32 || (d->mpad & 31) || d->m > d->mpad || d->mpad > 1024)
+        return fail("rtmpc_qp_create: mpad must be a multiple of 32 with m <= mpad <= 1024");
+    if (!d->Hs || !d->Hinv || !d->G || !d->Y || !d->Fx || !d->Fr || !d->lo0 || !d->up0 || !d->Lx || !d->Ux ||
+        !d->has_lo || !d->has_up || !d->Dscale || !d->Phi || !d->Psi)
+        return fail("rtmpc_qp_create: null matrix in the description");
     rtmpc_qp* q = new rtmpc_qp();
     CU(cudaGetDevice(&q->device));
     CU(cudaDeviceGetAttribute(&q->num_sms, cudaDevAttrMultiProcessorCount, q->device));
@@ -103,43 +95,81 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
     int mtot = 0;
     for (int i = 0; i < d->mpad; ++i) mtot += (d->has_lo[i] ? 1 : 0) + (d->has_up[i] ? 1 : 0);
     P.mtot = mtot > 0 ? mtot : 1;
-    const size_t nn = (size_t)d->npad * d->npad, mn = (size_t)d->mpad * d->npad;
+    const int npad = d->npad, mpad = d->mpad, nx = d->nx, gs = P.gs;
+    const size_t nn = (size_t)npad * npad, mn = (size_t)mpad * npad;
+    // operators derived once on the host from the description (shared by every instance):
+    //   W = G Hinv G' (= G Y'), Zx = -Hinv Fx, Zr = -Hinv Fr, Tx = -Y Fx, Tr = -Y Fr, G with the on-chip row stride
+    std::vector<double> W((size_t)mpad * mpad), Zx((size_t)npad * nx), Zr((size_t)npad * nx), Tx((size_t)mpad * nx),
+        Tr((size_t)mpad * nx), Gpad((size_t)mpad * gs, 0.0);
+    for (int a = 0; a < mpad; ++a)
+        for (int b = a; b < mpad; ++b) {
+            double acc = 0.0;
+            for (int k = 0; k < npad; ++k) acc += d->G[(size_t)a * npad + k] * d->Y[(size_t)b * npad + k];
+            W[(size_t)a * mpad + b] = acc;
+            W[(size_t)b * mpad + a] = acc;
+        }
+    for (int j = 0; j < npad; ++j)
+        for (int k = 0; k < nx; ++k) {
+            double ax = 0.0, ar = 0.0;
+            for (int i = 0; i < npad; ++i) {
+                ax -= d->Hinv[(size_t)j * npad + i] * d->Fx[(size_t)i * nx + k];
+                ar -= d->Hinv[(size_t)j * npad + i] * d->Fr[(size_t)i * nx + k];
+            }
+            Zx[(size_t)j * nx + k] = ax;
+            Zr[(size_t)j * nx + k] = ar;
+        }
+    for (int r = 0; r < mpad; ++r) {
+        for (int k = 0; k < nx; ++k) {
+            double ax = 0.0, ar = 0.0;
+            for (int i = 0; i < npad; ++i) {
+                ax -= d->Y[(size_t)r * npad + i] * d->Fx[(size_t)i * nx + k];
+                ar -= d->Y[(size_t)r * npad + i] * d->Fr[(size_t)i * nx + k];
+            }
+            Tx[(size_t)r * nx + k] = ax;
+            Tr[(size_t)r * nx + k] = ar;
+        }
+        for (int k = 0; k < npad; ++k) Gpad[(size_t)r * gs + k] = d->G[(size_t)r * npad + k];
+    }
     int rc = 0;
     rc |= upload(q, d->Hs, nn, &P.Hs);
     rc |= upload(q, d->Hinv, nn, &P.Hinv);
     rc |= upload(q, d->G, mn, &P.G);
     rc |= upload(q, d->Y, mn, &P.Y);
-    rc |= upload(q, d->Fx, (size_t)d->npad * d->nx, &P.Fx);
-    rc |= upload(q, d->Fr, (size_t)d->npad * d->nx, &P.Fr);
-    rc |= upload(q, d->lo0, (size_t)d->mpad, &P.lo0);
-    rc |= upload(q, d->up0, (size_t)d->mpad, &P.up0);
-    rc |= upload(q, d->Lx, (size_t)d->mpad * d->nx, &P.Lx);
-    rc |= upload(q, d->Ux, (size_t)d->mpad * d->nx, &P.Ux);
-    rc |= upload(q, d->has_lo, (size_t)d->mpad, &P.has_lo);
-    rc |= upload(q, d->has_up, (size_t)d->mpad, &P.has_up);
-    rc |= upload(q, d->parC, (size_t)d->np * d->nx, &P.parC);
+    rc |= upload(q, d->Fx, (size_t)npad * nx, &P.Fx);
+    rc |= upload(q, d->Fr, (size_t)npad * nx, &P.Fr);
+    rc |= upload(q, d->lo0, (size_t)mpad, &P.lo0);
+    rc |= upload(q, d->up0, (size_t)mpad, &P.up0);
+    rc |= upload(q, d->Lx, (size_t)mpad * nx, &P.Lx);
+    rc |= upload(q, d->Ux, (size_t)mpad * nx, &P.Ux);
+    rc |= upload(q, d->has_lo, (size_t)mpad, &P.has_lo);
+    rc |= upload(q, d->has_up, (size_t)mpad, &P.has_up);
+    rc |= upload(q, d->parC, (size_t)d->np * nx, &P.parC);
     rc |= upload(q, d->parh, (size_t)d->np, &P.parh);
-    rc |= upload(q, d->Dscale, (size_t)d->npad, &P.D);
-    rc |= upload(q, d->Phi, (size_t)d->nz * d->npad, &P.Phi);
-    rc |= upload(q, d->Psi, (size_t)d->nz * d->nx, &P.Psi);
-    rc |= upload(q, d->Kss, (size_t)d->nu * d->nx, &P.Kss);
+    rc |= upload(q, d->Dscale, (size_t)npad, &P.D);
+    rc |= upload(q, d->Phi, (size_t)d->nz * npad, &P.Phi);
+    rc |= upload(q, d->Psi, (size_t)d->nz * nx, &P.Psi);
+    rc |= upload(q, d->Kss, (size_t)d->nu * nx, &P.Kss);
+    rc |= upload(q, d->shift, (size_t)mpad, &P.shift);
+    rc |= upload(q, W.data(), W.size(), &P.W);
+    rc |= upload(q, Gpad.data(), Gpad.size(), &P.Gpad);
+    rc |= upload(q, Zx.data(), Zx.size(), &P.Zx);
+    rc |= upload(q, Zr.data(), Zr.size(), &P.Zr);
+    rc |= upload(q, Tx.data(), Tx.size(), &P.Tx);
+    rc |= upload(q, Tr.data(), Tr.size(), &P.Tr);
     if (rc) { rtmpc_qp_destroy(q); return -1; }
     if (P.nss > 0 && !P.Kss) { rtmpc_qp_destroy(q); return fail("rtmpc_qp_create: Kss required when nss > 0"); }
 
-    q->bs = kc->bs; q->r = kc->r;
     int max_smem = 0;
     CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, q->device));
-    int wpb = 8;
-    size_t smem = 0;
-    for (; wpb >= 1; wpb >>= 1) {
-        smem = ((size_t)ipm_block_doubles(P) + 2 + (size_t)wpb * (ipm_warp_doubles(P) + 2)) * sizeof(double);
-        if (smem <= (size_t)max_smem) break;
+    cudaError_t e = cudaSuccess;
+    if (!ipm_configure(P, max_smem, &q->ipm_wpb, &q->ipm_smem, &e)) {
+        rtmpc_qp_destroy(q);
+        return fail("rtmpc_qp_create: problem does not fit the interior-point kernel (shared memory / mpad <= 1024)", e);
     }
-    if (wpb < 1) { rtmpc_qp_destroy(q); return fail("rtmpc_qp_create: problem does not fit in shared memory"); }
-    q->wpb = wpb; q->smem = smem;
-    // several QPs may share one instantiation: always opt in to the device maximum
-    cudaError_t e = cudaFuncSetAttribute((const void*)kc->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e != cudaSuccess) { rtmpc_qp_destroy(q); return fail("cudaFuncSetAttribute", e); }
+    if (!as_configure(P, max_smem, &q->as_wpb, &q->as_smem, &q->as_g_in_smem, &e)) {
+        rtmpc_qp_destroy(q);
+        return fail("rtmpc_qp_create: problem does not fit the active-set kernel", e);
+    }
     *out = q;
     return 0;
 }
@@ -148,25 +178,58 @@ void rtmpc_qp_destroy(rtmpc_qp* q) {
     if (!q) return;
     for (void* p : q->allocs) cudaFree(p);
     cudaFree(q->s_x); cudaFree(q->s_ref); cudaFree(q->s_z); cudaFree(q->s_U);
-    cudaFree(q->s_sel); cudaFree(q->s_status); cudaFree(q->s_iters);
+    cudaFree(q->s_sel); cudaFree(q->s_status); cudaFree(q->s_iters); cudaFree(q->s_warm);
+    cudaFree(q->s_tmp_status);
     if (q->stream) cudaStreamDestroy(q->stream);
     delete q;
 }
 
+int rtmpc_qp_set_method(rtmpc_qp* q, int32_t method) {
+    if (!q) return fail("rtmpc_qp_set_method: null handle");
+    if (method != RTMPC_METHOD_ACTIVE_SET && method != RTMPC_METHOD_INTERIOR_POINT)
+        return fail("rtmpc_qp_set_method: unknown method");
+    q->method = method;
+    return 0;
+}
+
+int rtmpc_qp_set_work_counter(rtmpc_qp* q, uint64_t* d_counter) {
+    if (!q) return fail("rtmpc_qp_set_work_counter: null handle");
+    q->d_work = reinterpret_cast<unsigned long long*>(d_counter);
+    return 0;
+}
+
+int32_t rtmpc_qp_warm_stride(rtmpc_qp* q) { return q ? q->dev.npad + 1 : -1; }
+
 int rtmpc_qp_solve(rtmpc_qp* q, int32_t B, const double* d_x_init, const double* d_ref, const int32_t* d_sel,
-                   int32_t sel_value, double* d_z, double* d_U_t, int32_t* d_status, int32_t* d_iters,
+                   int32_t sel_value, int32_t* d_warm, double* d_z, double* d_U_t, int32_t* d_status, int32_t* d_iters,
                    void* stream) {
     if (!q) return fail("rtmpc_qp_solve: null handle");
     if (B <= 0) return 0;
     if (!d_x_init) return fail("rtmpc_qp_solve: d_x_init is null");
-    const KernelChoice* kc = pick_kernel(q->dev.n, q->dev.mpad);
-    const int wpb = q->wpb;
-    int blocks = (B + wpb - 1) / wpb;
-    if (blocks > q->num_sms) blocks = q->num_sms;   // one resident CTA per SM, warps loop over instances
-    kc->fn<<<blocks, wpb * 32, q->smem, (cudaStream_t)stream>>>(q->dev, B, d_x_init, d_ref, d_sel, sel_value, d_z,
-                                                               d_U_t, d_status, d_iters);
-    g_launches.fetch_add(1);
-    CU(cudaGetLastError());
+    QPLaunch a;
+    a.B = B; a.x_init = d_x_init; a.ref = d_ref; a.sel = d_sel; a.sel_value = sel_value; a.z = d_z; a.U = d_U_t;
+    a.status = d_status; a.iters = d_iters; a.warm = d_warm; a.work = q->d_work; a.stream = (cudaStream_t)stream;
+    if (q->method == RTMPC_METHOD_INTERIOR_POINT) {
+        CU(ipm_launch(q->dev, q->ipm_wpb, q->ipm_smem, q->num_sms, a));
+        g_launches.fetch_add(1);
+        return 0;
+    }
+    if (!d_status) {
+        // the hand-over to the interior-point kernel goes through the status array
+        if (B > q->tmp_cap) {
+            cudaFree(q->s_tmp_status);
+            q->s_tmp_status = nullptr; q->tmp_cap = 0;
+            CU(cudaMalloc(&q->s_tmp_status, (size_t)B * sizeof(int)));
+            q->tmp_cap = B;
+        }
+        a.status = q->s_tmp_status;
+    }
+    CU(as_launch(q->dev, q->as_wpb, q->as_smem, q->as_g_in_smem, q->num_sms, a));
+    // instances the active-set kernel handed over (status RTMPC_FALLBACK); exits at once when there are none
+    QPLaunch f = a;
+    f.sel = a.status; f.sel_value = RTMPC_FALLBACK_STATUS; f.work = nullptr;
+    CU(ipm_launch(q->dev, q->ipm_wpb, q->ipm_smem, q->num_sms, f));
+    g_launches.fetch_add(2);
     return 0;
 }
 
@@ -174,8 +237,11 @@ static int ensure_staging(rtmpc_qp* q, int B) {
     if (!q->stream) CU(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
     if (B <= q->cap) return 0;
     cudaFree(q->s_x); cudaFree(q->s_ref); cudaFree(q->s_z); cudaFree(q->s_U);
-    cudaFree(q->s_sel); cudaFree(q->s_status); cudaFree(q->s_iters);
+    cudaFree(q->s_sel); cudaFree(q->s_status); cudaFree(q->s_iters); cudaFree(q->s_warm);
+    q->s_x = q->s_ref = q->s_z = q->s_U = nullptr;
+    q->s_sel = q->s_status = q->s_iters = q->s_warm = nullptr;
     q->cap = 0;
+    q->warm_cap = 0;
     const QPDev& P = q->dev;
     CU(cudaMalloc(&q->s_x, (size_t)B * P.nx * sizeof(double)));
     CU(cudaMalloc(&q->s_ref, (size_t)B * P.nx * sizeof(double)));
@@ -184,17 +250,24 @@ static int ensure_staging(rtmpc_qp* q, int B) {
     CU(cudaMalloc(&q->s_sel, (size_t)B * sizeof(int)));
     CU(cudaMalloc(&q->s_status, (size_t)B * sizeof(int)));
     CU(cudaMalloc(&q->s_iters, (size_t)B * sizeof(int)));
+    CU(cudaMalloc(&q->s_warm, (size_t)B * (P.npad + 1) * sizeof(int)));
     q->cap = B;
     return 0;
 }
 
 int rtmpc_qp_solve_host(rtmpc_qp* q, int32_t B, const double* h_x_init, const double* h_ref, const int32_t* h_sel,
-                        int32_t sel_value, double* h_z, double* h_U_t, int32_t* h_status, int32_t* h_iters) {
+                        int32_t sel_value, int32_t warm, double* h_z, double* h_U_t, int32_t* h_status,
+                        int32_t* h_iters) {
     if (!q) return fail("rtmpc_qp_solve_host: null handle");
     if (B <= 0) return 0;
     if (ensure_staging(q, B)) return -1;
     const QPDev& P = q->dev;
     cudaStream_t s = q->stream;
+    if (warm && q->warm_cap != B) {
+        // no state yet (or another batch size): every instance starts cold
+        CU(cudaMemsetAsync(q->s_warm, 0xFF, (size_t)B * (P.npad + 1) * sizeof(int), s));
+        q->warm_cap = B;
+    }
     CU(cudaMemcpyAsync(q->s_x, h_x_init, (size_t)B * P.nx * sizeof(double), cudaMemcpyHostToDevice, s));
     if (h_ref) CU(cudaMemcpyAsync(q->s_ref, h_ref, (size_t)B * P.nx * sizeof(double), cudaMemcpyHostToDevice, s));
     if (h_sel) {
@@ -203,13 +276,20 @@ int rtmpc_qp_solve_host(rtmpc_qp* q, int32_t B, const double* h_x_init, const do
         CU(cudaMemsetAsync(q->s_iters, 0, (size_t)B * sizeof(int), s));
     }
     if (rtmpc_qp_solve(q, B, q->s_x, h_ref ? q->s_ref : nullptr, h_sel ? q->s_sel : nullptr, sel_value,
-                       h_z ? q->s_z : nullptr, h_U_t ? q->s_U : nullptr, q->s_status, q->s_iters, s))
+                       warm ? q->s_warm : nullptr, h_z ? q->s_z : nullptr, h_U_t ? q->s_U : nullptr, q->s_status,
+                       q->s_iters, s))
         return -1;
     if (h_z) CU(cudaMemcpyAsync(h_z, q->s_z, (size_t)B * P.nz * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (h_U_t) CU(cudaMemcpyAsync(h_U_t, q->s_U, (size_t)B * (P.N + 1) * P.nu * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (h_status) CU(cudaMemcpyAsync(h_status, q->s_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (h_iters) CU(cudaMemcpyAsync(h_iters, q->s_iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int rtmpc_qp_warm_reset(rtmpc_qp* q) {
+    if (!q) return fail("rtmpc_qp_warm_reset: null handle");
+    q->warm_cap = 0;
     return 0;
 }
 

@@ -34,6 +34,11 @@ struct QPDev {
     const double *Hs, *Hinv, *G, *Y, *Fx, *Fr, *lo0, *up0, *Lx, *Ux;
     const unsigned char *has_lo, *has_up;
     const double *parC, *parh, *D, *Phi, *Psi, *Kss;
+    const double* W;      // [mpad*mpad]  G Hinv G'  (Schur entries of the active-set steps are look-ups)
+    const double* Gpad;   // [mpad*gs]    G with the shared-memory row stride (used when G does not fit on chip)
+    const double *Zx, *Zr;   // [npad*nx]  z_u = Zx x_init + Zr ref    (= -Hinv Fx, -Hinv Fr)
+    const double *Tx, *Tr;   // [mpad*nx]  G z_u = Tx x_init + Tr ref
+    const int* shift;     // [mpad] warm-start map: same constraint one stage earlier, -1 = none
     double s_floor, sc_b;
     int max_iter;
 };
@@ -217,13 +222,14 @@ __device__ __forceinline__ WarpSmem carve(double* base, const QPDev& P) {
 // ----------------------------------------------------------------------------------------------
 template <int R>
 __device__ bool polish_warp(const QPDev& P, const double* __restrict__ Gs, WarpSmem& w, int na, int lane,
-                            unsigned mask_u, unsigned mask_l, int nslots, int* rounds_out) {
+                            unsigned mask_u, unsigned mask_l, int nslots, int max_rounds, int* rounds_out,
+                            int* na_out) {
     const int n = P.n, ss = P.ss, gs = P.gs, npad = P.npad;
     double* S = w.S;
     const double tol_p = 1e-11 * P.sc_b;   // a row left inactive may be violated by at most this (scaled units)
     int rounds = 0;
     bool success = false;
-    for (; rounds < 24; ++rounds) {
+    for (; rounds < max_rounds; ++rounds) {
         if (na > n) break;
         const bool mine = lane < na;
         const int ra = mine ? w.act_row[lane] : 0;
@@ -232,13 +238,8 @@ __device__ bool polish_warp(const QPDev& P, const double* __restrict__ Gs, WarpS
         // S_A row a, and r_a = sa * G_a z_u - b_a
         double r0 = 0.0;
         if (mine) {
-            const double* Ya = P.Y + (size_t)ra * npad;
-            for (int b = 0; b < na; ++b) {
-                const double* Gb = Gs + (size_t)w.act_row[b] * gs;
-                double acc = 0.0;
-                for (int k = 0; k < n; ++k) acc = fma(Ya[k], Gb[k], acc);
-                S[lane * ss + b] = acc * sa * (double)w.act_sgn[b];
-            }
+            const double* Wa = P.W + (size_t)ra * P.mpad;
+            for (int b = 0; b < na; ++b) S[lane * ss + b] = Wa[w.act_row[b]] * sa * (double)w.act_sgn[b];
             const double* Ga = Gs + (size_t)ra * gs;
             double acc = 0.0;
             for (int k = 0; k < n; ++k) acc = fma(Ga[k], w.zu[k], acc);
@@ -338,13 +339,24 @@ __device__ bool polish_warp(const QPDev& P, const double* __restrict__ Gs, WarpS
             __syncwarp();
             continue;
         }
+        {
+            // certified: leave the kept rows compacted at the front of the list (next step's warm start)
+            const unsigned keptmask = __ballot_sync(RTMPC_FULL_MASK, kept);
+            const int pos = __popc(keptmask & ((1u << lane) - 1u));
+            const int myrow = ra, mysg = (int)sa;
+            __syncwarp();
+            if (kept) { w.act_row[pos] = myrow; w.act_sgn[pos] = mysg; }
+            na = __popc(keptmask);
+            __syncwarp();
+        }
         success = true;
         rounds += 1;
         break;
     }
     if (success && lane < npad) w.zeta[lane] = w.dz[lane];
     __syncwarp();
-    *rounds_out = rounds;
+    *rounds_out += rounds;
+    *na_out = na;
     return success;
 }
 
@@ -378,7 +390,8 @@ template <int BS, int R>
 __global__ void __launch_bounds__(256, 1)
 ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double* __restrict__ ref,
                  const int* __restrict__ sel, int sel_value, double* __restrict__ z_out,
-                 double* __restrict__ U_out, int* __restrict__ status_out, int* __restrict__ iters_out) {
+                 double* __restrict__ U_out, int* __restrict__ status_out, int* __restrict__ iters_out,
+                 int* __restrict__ warm) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -392,6 +405,16 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
     if ((((size_t)mpad * gs + npad * npad) & 1) != 0) wbase += 1;
     WarpSmem w = carve(wbase + (size_t)warp * (ipm_warp_doubles(P) + 2), P);
 
+    if (sel) {
+        // fallback launches usually select nothing: leave before staging anything
+        bool any = false;
+        for (int idx = threadIdx.x;; idx += blockDim.x) {
+            const int inst = ((idx / wpb) * gridDim.x + blockIdx.x) * wpb + (idx % wpb);
+            if (inst >= B) break;
+            if (sel[inst] == sel_value) any = true;
+        }
+        if (!__syncthreads_or(any)) return;
+    }
     // stage the shared matrices once per CTA
     for (int idx = threadIdx.x; idx < mpad * npad; idx += blockDim.x) {
         int i = idx / npad, j = idx - i * npad;
@@ -413,7 +436,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
 
     for (int inst = blockIdx.x * wpb + warp; inst < B; inst += gridDim.x * wpb) {
         if (sel && sel[inst] != sel_value) continue;
-        int status = RTMPC_MAX_ITER, iters = 0;
+        int status = RTMPC_MAX_ITER, iters = 0, rounds_total = 0, na_final = -1;
         // ---- parameters -----------------------------------------------------------------
         if (lane < nx) {
             w.xr[lane] = x_init[(size_t)inst * nx + lane];
@@ -476,8 +499,8 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                 }
             }
             smin = warp_min(smin);
-            if (smin > 0.0) { status = RTMPC_OPTIMAL; done = true; }
-            else {
+            if (smin > 0.0) { status = RTMPC_OPTIMAL; done = true; na_final = 0; }
+            if (!done) {
                 const double shift = fmax(-1.5 * smin, 0.0);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -567,8 +590,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
             const bool diverged = bad || merit > 1e3 * best_merit;
             if (!diverged && conv1 && !conv2 && iters >= next_try && iters < P.max_iter) {
                 int na = build_active<R>(st, w.act_row, w.act_sgn, lane, mask_u, mask_l, nslots, 2 * npad);
-                int rounds = 0;
-                if (na <= n && polish_warp<R>(P, Gs, w, na, lane, mask_u, mask_l, nslots, &rounds)) {
+                if (na <= n && polish_warp<R>(P, Gs, w, na, lane, mask_u, mask_l, nslots, 24, &rounds_total, &na_final)) {
                     status = RTMPC_OPTIMAL;
                     break;
                 }
@@ -584,8 +606,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                         for (int i = lane; i < na && i < 2 * npad; i += 32) { w.act_row[i] = w.best_row[i]; w.act_sgn[i] = w.best_sgn[i]; }
                         __syncwarp();
                     }
-                    int rounds = 0;
-                    if (na <= n && polish_warp<R>(P, Gs, w, na, lane, mask_u, mask_l, nslots, &rounds)) {
+                    if (na <= n && polish_warp<R>(P, Gs, w, na, lane, mask_u, mask_l, nslots, 24, &rounds_total, &na_final)) {
                         status = RTMPC_OPTIMAL;
                         break;
                     }
@@ -786,9 +807,15 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                 U_out[(size_t)inst * (N + 1) * nu + N * nu + lane] = acc;
             }
         }
+        if (warm) {
+            const int ws = npad + 1;
+            const int nw = (status == RTMPC_OPTIMAL) ? na_final : -1;
+            if (lane == 0) warm[(size_t)inst * ws] = nw;
+            if (lane < nw) warm[(size_t)inst * ws + 1 + lane] = 2 * w.act_row[lane] + (w.act_sgn[lane] < 0 ? 1 : 0);
+        }
         if (lane == 0) {
             if (status_out) status_out[inst] = status;
-            if (iters_out) iters_out[inst] = iters;
+            if (iters_out) iters_out[inst] = iters | (rounds_total << 24);   // bits 0-11 IPM iterations, 24-31 endgame rounds
         }
         __syncwarp();
     }

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "librtmpc_b200.so")
 EXPORTS = [
     "rtmpc_abi_version", "rtmpc_last_error", "rtmpc_device_count", "rtmpc_set_device",
     "rtmpc_qp_create", "rtmpc_qp_destroy", "rtmpc_qp_solve", "rtmpc_qp_solve_host", "rtmpc_launch_count",
+    "rtmpc_qp_warm_stride", "rtmpc_qp_warm_reset", "rtmpc_qp_set_method", "rtmpc_qp_set_work_counter",
     "rtmpc_loop_create", "rtmpc_loop_destroy", "rtmpc_loop_reset", "rtmpc_loop_x", "rtmpc_loop_x_nom",
     "rtmpc_loop_x_hat", "rtmpc_loop_q_t", "rtmpc_loop_s_t", "rtmpc_loop_Theta", "rtmpc_loop_alive",
     "rtmpc_loop_err_acc", "rtmpc_loop_tube_max", "rtmpc_loop_u", "rtmpc_loop_gamma", "rtmpc_loop_time",
@@ -24,6 +25,8 @@ EXPORTS = [
 ]
 
 OPTIMAL, MAX_ITER, INFEASIBLE, OPTIMAL_INACCURATE = 0, 1, 2, 3
+METHOD_ACTIVE_SET, METHOD_INTERIOR_POINT = 0, 1
+ABI_VERSION = 2
 ACT_SMART, ACT_CONSISTENT, ACT_EXTENDED = 0, 1, 2
 PLANT_LINEAR, PLANT_CARTPOLE = 0, 1
 
@@ -37,7 +40,8 @@ class QPDesc(C.Structure):
                [(k, _dp) for k in ("Hs", "Hinv", "G", "Y", "Fx", "Fr", "lo0", "up0", "Lx", "Ux")] + \
                [("has_lo", _bp), ("has_up", _bp)] + \
                [(k, _dp) for k in ("parC", "parh", "Dscale", "Phi", "Psi", "Kss")] + \
-               [("s_floor", C.c_double), ("sc_b", C.c_double), ("max_iter", C.c_int32), ("reserved", C.c_int32)]
+               [("s_floor", C.c_double), ("sc_b", C.c_double), ("max_iter", C.c_int32), ("reserved", C.c_int32),
+                ("shift", _ip)]
 
 
 class LoopDesc(C.Structure):
@@ -64,14 +68,21 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp = C.c_void_p
     L.rtmpc_abi_version.restype = C.c_int
+    if L.rtmpc_abi_version() != ABI_VERSION:
+        raise RtmpcError(f"{LIB_PATH} has ABI version {L.rtmpc_abi_version()}, expected {ABI_VERSION}: rebuild it")
     L.rtmpc_last_error.restype = C.c_char_p
     L.rtmpc_device_count.restype = C.c_int
     L.rtmpc_set_device.argtypes = [C.c_int]
     L.rtmpc_qp_create.argtypes = [C.POINTER(QPDesc), C.POINTER(vp)]
     L.rtmpc_qp_destroy.argtypes = [vp]
     L.rtmpc_qp_destroy.restype = None
-    L.rtmpc_qp_solve.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
-    L.rtmpc_qp_solve_host.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, vp]
+    L.rtmpc_qp_solve.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.rtmpc_qp_solve_host.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
+    L.rtmpc_qp_warm_stride.argtypes = [vp]
+    L.rtmpc_qp_warm_stride.restype = C.c_int32
+    L.rtmpc_qp_warm_reset.argtypes = [vp]
+    L.rtmpc_qp_set_method.argtypes = [vp, C.c_int32]
+    L.rtmpc_qp_set_work_counter.argtypes = [vp, vp]
     L.rtmpc_launch_count.restype = C.c_int64
     L.rtmpc_loop_create.argtypes = [C.POINTER(LoopDesc), C.c_int32, C.POINTER(vp)]
     L.rtmpc_loop_destroy.argtypes = [vp]

@@ -68,6 +68,7 @@ class CondensedQP:
     Phi: np.ndarray              # [nz,n]   z = Phi zeta + Psi x_init ;  z = [x_0..x_N | u | x_bar | u_bar]
     Psi: np.ndarray              # [nz,nx]
     Mss: np.ndarray              # [(nx+nu), nth]
+    shift: np.ndarray = None     # [m] int32: row holding the same constraint one stage earlier (-1: none)
     meta: dict = field(default_factory=dict)
 
     @property
@@ -147,10 +148,12 @@ def condense(spec: MPCSpec) -> CondensedQP:
 
     # one-sided rows  g' zeta <= h0 + hx' x_init
     rows_g, rows_h0, rows_hx = [], [], []
+    rows_tag = []            # (kind, stage, index within the block) per one-sided row, for the shift map
     eq_g, eq_h0, eq_hx = [], [], []
 
-    def ineq(C, c, Pz, Sz=None):
+    def ineq(C, c, Pz, Sz=None, kind="other", stage=0):
         C = np.asarray(C, float)
+        rows_tag.extend((kind, stage, j) for j in range(C.shape[0]))
         rows_g.append(C @ Pz)
         rows_h0.append(np.asarray(c, float).flatten())
         rows_hx.append(-C @ Sz if Sz is not None else np.zeros((C.shape[0], nx)))
@@ -159,14 +162,15 @@ def condense(spec: MPCSpec) -> CondensedQP:
         Hz, hz = spec.tube_init
         Hz = np.asarray(Hz, float)
         # Hz (x_init - x_0) <= hz   <=>   -Hz x_0 <= hz - Hz x_init
+        rows_tag.extend(("init", 0, j) for j in range(Hz.shape[0]))
         rows_g.append(-Hz @ Px[0])
         rows_h0.append(np.asarray(hz, float).flatten())
         rows_hx.append(-Hz)
     for i in range(N):
         if spec.stage_x is not None:
-            ineq(spec.stage_x[0], spec.stage_x[1], Px[i], Sx[i])
+            ineq(spec.stage_x[0], spec.stage_x[1], Px[i], Sx[i], kind="x", stage=i)
         if spec.stage_u is not None:
-            ineq(spec.stage_u[0], spec.stage_u[1], Pu[i])
+            ineq(spec.stage_u[0], spec.stage_u[1], Pu[i], kind="u", stage=i)
     if spec.terminal_eq:
         eq_g.append(Px[N] - Pxb)
         eq_h0.append(np.zeros(nx))
@@ -179,13 +183,14 @@ def condense(spec: MPCSpec) -> CondensedQP:
                 Cth = np.r_[np.eye(nth), -np.eye(nth)]
                 Pth = np.zeros((nth, n))
                 Pth[:, o_th:] = np.eye(nth)
-                ineq(Cth, np.r_[up_th, -lo_th], Pth)
+                ineq(Cth, np.r_[up_th, -lo_th], Pth, kind="term")
             else:
+                rows_tag.extend(("term", 0, j) for j in range(HN.shape[0]))
                 rows_g.append(HN[:, :nx] @ Px[N] + HN[:, nx:2 * nx] @ Pxb + HN[:, 2 * nx:] @ Pub)
                 rows_h0.append(hN)
                 rows_hx.append(-HN[:, :nx] @ Sx[N])
         else:
-            ineq(HN, hN, Px[N], Sx[N])
+            ineq(HN, hN, Px[N], Sx[N], kind="term")
 
     Gi = np.vstack(rows_g) if rows_g else np.zeros((0, n))
     h0 = np.hstack(rows_h0) if rows_h0 else np.zeros(0)
@@ -196,8 +201,18 @@ def condense(spec: MPCSpec) -> CondensedQP:
     const = gn < 1e-12
     par_h, par_C = h0[const].copy(), -hx[const].copy()       # par_C x_init <= par_h
     Gi, h0, hx = Gi[~const], h0[~const], hx[~const]
+    tags = [t for t, c in zip(rows_tag, const) if not c]
 
-    G, lo0, up0, Lx, Ux = _merge_two_sided(Gi, h0, hx)
+    G, lo0, up0, Lx, Ux, first = _merge_two_sided(Gi, h0, hx)
+    # shift map for warm starts: stage rows move one stage earlier, terminal / initial rows stay
+    where = {tags[i]: r for r, i in enumerate(first)}
+    shift = np.full(G.shape[0], -1, np.int32)
+    for r, i in enumerate(first):
+        kind, stage, j = tags[i]
+        if kind in ("x", "u"):
+            shift[r] = where.get((kind, stage - 1, j), -1)
+        else:
+            shift[r] = r
     if eq_g:
         Ge = np.vstack(eq_g)
         he = np.hstack(eq_h0)
@@ -207,6 +222,7 @@ def condense(spec: MPCSpec) -> CondensedQP:
         up0 = np.r_[up0, he]
         Lx = np.vstack([Lx, hxe])
         Ux = np.vstack([Ux, hxe])
+        shift = np.r_[shift, np.arange(len(shift), len(shift) + Ge.shape[0], dtype=np.int32)]
 
     nz = nx * (N + 1) + nu * N + ((nx + nu) if has_ss else 0)
     Phi = np.zeros((nz, n))
@@ -222,7 +238,7 @@ def condense(spec: MPCSpec) -> CondensedQP:
         Phi[o:o + nx] = Pxb
         Phi[o + nx:o + nx + nu] = Pub
     return CondensedQP(nx=nx, nu=nu, N=N, n=n, nth=nth, has_x0=has_x0, H=H, Fx=Fx, Fr=Fr, G=G, lo0=lo0,
-                       up0=up0, Lx=Lx, Ux=Ux, par_h=par_h, par_C=par_C, Phi=Phi, Psi=Psi, Mss=Mss,
+                       up0=up0, Lx=Lx, Ux=Ux, par_h=par_h, par_C=par_C, Phi=Phi, Psi=Psi, Mss=Mss, shift=shift,
                        meta=dict(rows_one_sided=int(Gi.shape[0]), rows_param=int(const.sum())))
 
 
@@ -231,7 +247,7 @@ def _merge_two_sided(Gi, h0, hx):
     m, n = Gi.shape
     nxp = hx.shape[1]
     if m == 0:
-        return Gi, np.zeros(0), np.zeros(0), np.zeros((0, nxp)), np.zeros((0, nxp))
+        return Gi, np.zeros(0), np.zeros(0), np.zeros((0, nxp)), np.zeros((0, nxp)), []
     nrm = np.linalg.norm(Gi, axis=1)
     U = Gi / nrm[:, None]
     # canonical sign: first entry with |.| > 1e-9 positive
@@ -272,7 +288,7 @@ def _merge_two_sided(Gi, h0, hx):
         if j is not None:
             lo0[r] = -h0[j]
             Lx[r] = -hx[j]
-    return G, lo0, up0, Lx, Ux
+    return G, lo0, up0, Lx, Ux, [i for i, _ in out_rows]
 
 
 def _project_terminal_on_theta(HN, hN, Mss, nx, nu):

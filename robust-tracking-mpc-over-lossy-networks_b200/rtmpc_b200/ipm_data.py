@@ -45,6 +45,7 @@ class IPMData:
     has_up: np.ndarray      # [mpad] uint8
     par_C: np.ndarray       # [mp,nx]  parameter rows  par_C x_init <= par_h (unscaled)
     par_h: np.ndarray       # [mp]
+    shift: np.ndarray       # [mpad] int32 warm-start map (row holding the same constraint one stage earlier)
     s_floor: float          # smallest initial slack (scaled units)
     sc_b: float             # 1 + typical |bound| (scaled units), for relative primal residuals
 
@@ -101,8 +102,11 @@ def prepare(cq: CondensedQP) -> IPMData:
     has_up = np.zeros(mpad, np.uint8)
     has_lo[:m] = fin_lo
     has_up[:m] = fin_up
+    shift = np.full(mpad, -1, np.int32)
+    if cq.shift is not None:
+        shift[:m] = cq.shift
     bmag = np.r_[np.abs(lo0[:m][fin_lo]), np.abs(up0[:m][fin_up])]
     sc_b = 1.0 + (float(np.median(bmag)) if bmag.size else 0.0)
     return IPMData(n=n, m=m, nx=nx, npad=npad, mpad=mpad, D=D, Ev=Ev, c=c, Hs=Hs, Gs=Gp, Hinv=Hinv, Y=Y,
                    Fx=Fx, Fr=Fr, lo0=lo0, up0=up0, Lx=Lx, Ux=Ux, has_lo=has_lo, has_up=has_up,
-                   par_C=cq.par_C.copy(), par_h=cq.par_h.copy(), s_floor=1e-3 * sc_b, sc_b=sc_b)
+                   par_C=cq.par_C.copy(), par_h=cq.par_h.copy(), shift=shift, s_floor=1e-3 * sc_b, sc_b=sc_b)

@@ -72,8 +72,10 @@ class RegulatorMPC:
 
     # -- solve --------------------------------------------------------------------------------
     def _solve_one(self, prob, x_init, ref=None):
+        # consecutive single-instance calls are consecutive control steps of one closed loop: keep the
+        # warm-start state in the handle (it only changes the work, never the certified result)
         z, U, st, it = prob.solve_host(np.asarray(x_init, float).reshape(1, -1),
-                                       None if ref is None else np.asarray(ref, float).reshape(1, -1))
+                                       None if ref is None else np.asarray(ref, float).reshape(1, -1), warm=True)
         self._last_status, self._last_iters = int(st[0]), int(it[0])
         return z, U
 

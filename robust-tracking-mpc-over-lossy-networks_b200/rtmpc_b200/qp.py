@@ -52,10 +52,30 @@ class BatchedQP:
         desc.has_lo = has_lo.ctypes.data_as(C.POINTER(C.c_uint8))
         desc.has_up = has_up.ctypes.data_as(C.POINTER(C.c_uint8))
         desc.s_floor, desc.sc_b, desc.max_iter = d.s_floor, d.sc_b, max_iter
+        shift = np.ascontiguousarray(d.shift, np.int32)
+        desc.shift = shift.ctypes.data_as(C.POINTER(C.c_int32))
         h = C.c_void_p()
         _lib.check(L.rtmpc_qp_create(C.byref(desc), C.byref(h)), "rtmpc_qp_create")
         self._h = h
         self._L = L
+        self.warm_stride = int(L.rtmpc_qp_warm_stride(h))
+
+    def set_method(self, method):
+        """'active_set' (default: dual active-set kernel, interior point as fallback) or 'interior_point'."""
+        m = {"active_set": _lib.METHOD_ACTIVE_SET, "interior_point": _lib.METHOD_INTERIOR_POINT}[method]
+        _lib.check(self._L.rtmpc_qp_set_method(self._h, m), "rtmpc_qp_set_method")
+
+    def set_work_counter(self, counter):
+        """uint64 device tensor (1 element) accumulating the active-set kernel's algorithmic flops, or None."""
+        _lib.check(self._L.rtmpc_qp_set_work_counter(self._h, _lib.ptr(counter)), "rtmpc_qp_set_work_counter")
+
+    def warm_reset(self):
+        _lib.check(self._L.rtmpc_qp_warm_reset(self._h), "rtmpc_qp_warm_reset")
+
+    @staticmethod
+    def decode_iters(iters):
+        """packed d_iters -> (interior-point iterations, active-set steps, certification rounds)"""
+        return iters & 0xFFF, (iters >> 12) & 0xFFF, (iters >> 24) & 0xFF
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -64,7 +84,7 @@ class BatchedQP:
             self._h = None
 
     # -- host buffers (numpy in / numpy out): the reference-facing call ----------------------
-    def solve_host(self, x_init, ref=None, sel=None, sel_value=1, want_z=True):
+    def solve_host(self, x_init, ref=None, sel=None, sel_value=1, want_z=True, warm=False):
         x_init = _lib.f64(np.atleast_2d(x_init))
         B = x_init.shape[0]
         ref = None if ref is None else _lib.f64(np.broadcast_to(np.atleast_2d(ref), x_init.shape))
@@ -76,15 +96,16 @@ class BatchedQP:
         iters = np.zeros(B, np.int32)
         selp = None if sel is None else np.ascontiguousarray(sel, np.int32)
         _lib.check(self._L.rtmpc_qp_solve_host(self._h, B, _lib.ptr(x_init), _lib.ptr(ref), _lib.ptr(selp), sel_value,
-                                               _lib.ptr(z), _lib.ptr(U), _lib.ptr(status), _lib.ptr(iters)),
+                                               1 if warm else 0, _lib.ptr(z), _lib.ptr(U), _lib.ptr(status), _lib.ptr(iters)),
                    "rtmpc_qp_solve_host")
         return z, U, status, iters
 
     # -- device buffers (torch tensors used purely as memory) ---------------------------------
-    def solve_device(self, x_init, ref, z, U, status, iters, sel=None, sel_value=1, stream=None):
+    def solve_device(self, x_init, ref, z, U, status, iters, sel=None, sel_value=1, stream=None, warm=None):
+        """``warm``: int32 device tensor [B, warm_stride] initialised with -1 (per-instance warm-start state)."""
         B = x_init.shape[0]
         _lib.check(self._L.rtmpc_qp_solve(self._h, B, _lib.ptr(x_init), _lib.ptr(ref), _lib.ptr(sel), sel_value,
-                                          _lib.ptr(z), _lib.ptr(U), _lib.ptr(status), _lib.ptr(iters), stream),
+                                          _lib.ptr(warm), _lib.ptr(z), _lib.ptr(U), _lib.ptr(status), _lib.ptr(iters), stream),
                    "rtmpc_qp_solve")
 
     def split(self, z):

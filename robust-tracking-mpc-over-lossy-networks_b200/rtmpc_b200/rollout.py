@@ -88,7 +88,11 @@ class RemoteLoop:
         self.U = torch.zeros(B_, N + 1, nu, device=self.dev, dtype=f64)
         self.status = torch.zeros(B_, device=self.dev, dtype=i32)
         self.iters = torch.zeros(B_, device=self.dev, dtype=i32)
-        self.iters_total = torch.zeros((), device=self.dev, dtype=torch.int64)
+        self.iters_total = torch.zeros(3, device=self.dev, dtype=torch.int64)   # IPM iterations, active-set steps, rounds
+        # per-instance warm-start state of each QP (last certified active set), -1 = none
+        self.warm = torch.full((B_, mpc._prob.warm_stride), -1, device=self.dev, dtype=i32)
+        pr = getattr(mpc, "_prob_packet_received", None)
+        self.warm_recv = None if pr is None else torch.full((B_, pr.warm_stride), -1, device=self.dev, dtype=i32)
         self.status_count = torch.zeros(4, device=self.dev, dtype=torch.int64)
 
     def __del__(self):
@@ -104,6 +108,9 @@ class RemoteLoop:
         _lib.check(self.L.rtmpc_loop_reset(self._h, _lib.ptr(x0)), "rtmpc_loop_reset")
         self.iters_total.zero_()
         self.status_count.zero_()
+        self.warm.fill_(-1)
+        if self.warm_recv is not None:
+            self.warm_recv.fill_(-1)
 
     @property
     def t(self):
@@ -116,20 +123,26 @@ class RemoteLoop:
         p = _lib.ptr
         if self.kind == "extended":
             self.mpc._prob_packet_received.solve_device(self.x_hat, ref_d, self.z, self.U, self.status, self.iters,
-                                                        sel=self.gamma_last, sel_value=1, stream=stream)
+                                                        sel=self.gamma_last, sel_value=1, stream=stream,
+                                                        warm=self.warm_recv)
             self.mpc._prob.solve_device(self.x_hat, ref_d, self.z, self.U, self.status, self.iters,
-                                        sel=self.gamma_last, sel_value=0, stream=stream)
+                                        sel=self.gamma_last, sel_value=0, stream=stream, warm=self.warm)
             x_nom0, stride = self.z, self.z.shape[1]
         else:
-            self.mpc._prob.solve_device(self.x_hat, ref_d, self.z, self.U, self.status, self.iters, stream=stream)
+            self.mpc._prob.solve_device(self.x_hat, ref_d, self.z, self.U, self.status, self.iters, stream=stream,
+                                        warm=self.warm)
             x_nom0, stride = None, 0
         if stats:
-            self.iters_total += self.iters.sum()
+            self.accumulate_iters()
             self.status_count += torch.bincount(self.status, minlength=4)[:4]
         _lib.check(self.L.rtmpc_loop_step(self._h, p(self.U), p(self.status), p(x_nom0), stride, p(ref_d), p(theta),
                                           p(gamma), p(w), p(p_loss), int(seed), int(id_offset), p(traj),
                                           0 if traj is None else traj.shape[1] * traj.shape[2], stream),
                    "rtmpc_loop_step")
+
+    def accumulate_iters(self):
+        it = self.iters
+        self.iters_total += torch.stack(((it & 0xFFF).sum(), ((it >> 12) & 0xFFF).sum(), ((it >> 24) & 0xFF).sum()))
 
     def run(self, T, ref, p_loss=None, theta=None, gamma=None, w=None, seed=0, id_offset=0, record=False, stats=True):
         """T steps.  ``ref`` [nx], [T,nx] or [T,B,nx]; explicit arrays theta/gamma [T,B], w [T,B,nx] (host or

@@ -32,7 +32,7 @@ def polish_model(d, x_init, ref, act, max_rounds=24, tol_p=1e-11, tol_d=1e-9):
     for rnd in range(max_rounds):
         na = len(act)
         if na > n:
-            return None, rnd, "too_many"
+            return None, rnd, "too_many", act
         rows = np.array([a[0] for a in act], int)
         sg = np.array([a[1] for a in act], float)
         b = np.where(sg > 0, up[rows], -lo[rows]) if na else np.zeros(0)
@@ -79,19 +79,21 @@ def polish_model(d, x_init, ref, act, max_rounds=24, tol_p=1e-11, tol_d=1e-9):
         if vmax > tol_p * d.sc_b:
             new = (wu, 1) if viol_u[wu] >= viol_l[wl] else (wl, -1)
             if any(a == new and k_ for a, k_ in zip(act, keep)):
-                return None, rnd, "cycle"
+                return None, rnd, "cycle", act
             act = [a for a, k_ in zip(act, keep) if k_]
             act.append(new)
             continue
-        return z, rnd + 1, "ok"
-    return None, max_rounds, "rounds"
+        return z, rnd + 1, "ok", [a for a, k_ in zip(act, keep) if k_]
+    return None, max_rounds, "rounds", act
 
 
-def solve_model(d, x_init, ref, max_iter=60, verbose=False):
-    """One instance, exactly the kernel's control flow.  Returns (zeta_scaled, status, iters, info)."""
+def solve_model(d, x_init, ref, max_iter=60, verbose=False, warm=None, shift=None, warm_rounds=10):
+    """One instance, exactly the kernel's control flow.  Returns (zeta_scaled, status, iters, info).
+    ``warm``: active set [(row, sign)] of the previous control step; it is shifted one stage with
+    ``shift`` and tried in the endgame before any interior-point iteration."""
     n, m, G, q, lo, up, hl, hu = _problem(d, x_init, ref)
     H = d.Hs
-    info = dict(path="ipm", polish=[])
+    info = dict(path="ipm", polish=[], active=None)
     if np.any(d.par_C @ x_init - d.par_h > 1e-9 * (1.0 + np.abs(d.par_h))):
         return np.full(n, np.nan), INFEASIBLE, 0, dict(path="param_rows")
     mtot = hl.sum() + hu.sum()
@@ -101,7 +103,15 @@ def solve_model(d, x_init, ref, max_iter=60, verbose=False):
     sl = np.where(hl, t - lo, 1.0)
     smin = min(su[hu].min(initial=np.inf), sl[hl].min(initial=np.inf))
     if smin > 0:
-        return zeta, OPTIMAL, 0, dict(path="unconstrained")
+        return zeta, OPTIMAL, 0, dict(path="unconstrained", active=[], polish=[])
+    if warm is not None:
+        cand = [(int(shift[r]), sg) for r, sg in warm if shift[r] >= 0] if shift is not None else list(warm)
+        zp, rounds, why, fin = polish_model(d, x_init, ref, cand, max_rounds=warm_rounds)
+        info["polish"].append((0, rounds, "warm-" + why, len(cand)))
+        if zp is not None:
+            info["path"] = "warm"
+            info["active"] = fin
+            return zp, OPTIMAL, 0, info
     shift = max(-1.5 * smin, 0.0)
     su = np.where(hu, np.maximum(su + shift, d.s_floor), 1.0)
     sl = np.where(hl, np.maximum(sl + shift, d.s_floor), 1.0)
@@ -118,8 +128,10 @@ def solve_model(d, x_init, ref, max_iter=60, verbose=False):
         return [(i, 1) for i in np.nonzero(hu & (lu > su))[0]] + [(i, -1) for i in np.nonzero(hl & (ll > sl))[0]]
 
     def try_polish(act):
-        zp, rounds, why = polish_model(d, x_init, ref, act)
+        zp, rounds, why, fin = polish_model(d, x_init, ref, act)
         info["polish"].append((iters, rounds, why, len(act)))
+        if zp is not None:
+            info["active"] = fin
         return zp
 
     while True:
