@@ -211,60 +211,46 @@ def run_gpu_arm(args):
     f_it = ipm_flops_per_iteration(n, m)
     stream = torch.cuda.current_stream()
 
-    def rollout(seed, solve_events=None):
+    def rollout(seed):
+        # one persistent launch: every warp takes its instance through all T control steps
         loop.reset()
-        for t in range(T):
-            if solve_events is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-            mpc._prob.solve_device(loop.x_hat, ref_d, None, loop.U, loop.status, loop.iters, stream=stream.cuda_stream,
-                                   warm=loop.warm)
-            if solve_events is not None:
-                e1.record(stream)
-                solve_events.append((e0, e1))
-            loop.accumulate_iters()
-            loop.status_count += torch.bincount(loop.status, minlength=4)[:4]
-            _lib.check(L.rtmpc_loop_step(loop._h, loop.U.data_ptr(), loop.status.data_ptr(), None, 0, ref_d.data_ptr(),
-                                         None, None, None, p_loss.data_ptr(), seed, ids0, None, 0, stream.cuda_stream),
-                       "rtmpc_loop_step")
+        loop.run(T, ref_d[0], p_loss=p_loss, seed=seed, id_offset=ids0, fused=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    work = torch.zeros(1, device=dev, dtype=torch.int64)      # algorithmic flops executed by the active-set kernel
-    mpc._prob.set_work_counter(work)
     for wi in range(args.warmup):
         rollout(SEED + 1000 + wi)
     barrier()
-    work.zero_()
     fp64_peak = measure_fp64_peak(torch, dev) if rank == 0 else None
     # ---- timed region: K rollouts, device-timed, L2 flushed between them -------------------------
     launches0 = L.rtmpc_launch_count()
     total_ms = 0.0
     solve_ms = 0.0
     iters_sum = np.zeros(3, np.int64)
+    as_flops = 0
     status_sum = np.zeros(4, np.int64)
     with ClockSampler(local) as clk:
         barrier()
         for k in range(args.steps):
             flush.zero_()
             torch.cuda.synchronize()
-            ev = []
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            loop.reset()
             e0.record(stream)
-            rollout(SEED + k, ev)
+            loop.run(T, ref_d[0], p_loss=p_loss, seed=SEED + k, id_offset=ids0, fused=True)
             e1.record(stream)
             torch.cuda.synchronize()
             total_ms += e0.elapsed_time(e1)
-            solve_ms += sum(a.elapsed_time(b) for a, b in ev)
-            iters_sum += loop.iters_total.cpu().numpy()
-            status_sum += loop.status_count.cpu().numpy()
+            solve_ms = total_ms                 # the rollout IS the kernel: one launch per bench step
+            st = loop.stats.cpu().numpy()
+            iters_sum += st[4:7]
+            status_sum += st[:4]
+            as_flops += int(st[7])
         barrier()
     launches = L.rtmpc_launch_count() - launches0
-    as_flops = int(work.item())
-    mpc._prob.set_work_counter(None)
     err = loop.tracking_error(T)
     tube_max = float(loop.tube_max.max().item())
     t_ms = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -282,36 +268,30 @@ def run_gpu_arm(args):
     solves = B * T * args.steps
     value = solves * world / (total_ms_max * 1e-3)
 
-    # ---- e2e: same rollout through the host-buffer plugin call, H2D/D2H inside the timed region ----
+    # ---- e2e: the same rollouts through the host-facing call: host x0 / loss rates / reference in,
+    # full state trajectories + tracking errors out (what the reference's script collects), copies timed ----
     e2e = None
     if not args.no_e2e:
-        xh_h = torch.zeros(B, 4, dtype=torch.float64).pin_memory()
-        ref_h = torch.as_tensor(np.tile(REF, (B, 1))).pin_memory()
-        U_h = torch.zeros(B, 21, 1, dtype=torch.float64).pin_memory()
-        st_h = torch.zeros(B, dtype=torch.int32).pin_memory()
-        it_h = torch.zeros(B, dtype=torch.int32).pin_memory()
-        qp = mpc._prob
-        h2d = B * 4 * 8 * 2 + B * 21 * 8 + B * 4
-        d2h = B * 21 * 8 + B * 4 * 2 + B * 4 * 8
+        x0_h = torch.zeros(B, 4, dtype=torch.float64).pin_memory()
+        p_h = torch.as_tensor(np.array([0.1 * ((ids0 + i) % 10) for i in range(B)])).pin_memory()
+        ref_h = torch.as_tensor(REF.copy()).pin_memory()
+        traj_h = torch.zeros(B, T + 1, 4, dtype=torch.float64).pin_memory()
+        err_h = torch.zeros(B, dtype=torch.float64).pin_memory()
+        h2d = x0_h.numel() * 8 + p_h.numel() * 8 + ref_h.numel() * 8
+        d2h = traj_h.numel() * 8 + err_h.numel() * 8
 
         def rollout_host(seed):
-            loop.reset()
-            qp.warm_reset()
-            xh_h.zero_()
-            for t in range(T):
-                _lib.check(L.rtmpc_qp_solve_host(qp._h, B, xh_h.data_ptr(), ref_h.data_ptr(), None, 1, 1, None,
-                                                 U_h.data_ptr(), st_h.data_ptr(), it_h.data_ptr()), "solve_host")
-                loop.U.copy_(U_h, non_blocking=True)
-                loop.status.copy_(st_h, non_blocking=True)
-                _lib.check(L.rtmpc_loop_step(loop._h, loop.U.data_ptr(), loop.status.data_ptr(), None, 0,
-                                             ref_d.data_ptr(), None, None, None, p_loss.data_ptr(), seed, ids0, None, 0,
-                                             stream.cuda_stream), "rtmpc_loop_step")
-                xh_h.copy_(loop.x_hat, non_blocking=True)
-                torch.cuda.synchronize()
+            loop.reset(x0_h.numpy())                                            # H2D of the initial states
+            p_d = p_h.to(dev, non_blocking=True)
+            r_d = ref_h.to(dev, non_blocking=True)
+            tr = loop.run(T, r_d, p_loss=p_d, seed=seed, id_offset=ids0, record=True, fused=True)
+            traj_h.copy_(tr, non_blocking=True)
+            err_h.copy_(loop.tracking_error(T), non_blocking=True)
+            torch.cuda.synchronize()
         rollout_host(SEED + 500)
         barrier()
         t0 = time.perf_counter()
-        ksteps = max(1, min(args.steps, 2))
+        ksteps = args.steps
         for k in range(ksteps):
             rollout_host(SEED + k)
         barrier()
@@ -319,8 +299,10 @@ def run_gpu_arm(args):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": B * T * ksteps * world / float(dt.item()), "unit": "solves/s",
-               "h2d_bytes_per_step": h2d * T, "d2h_bytes_per_step": d2h * T,
-               "api": "rtmpc_qp_solve_host per control step (pinned host x_hat/ref in, U_t/status out) + loop step"}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "RemoteLoop.reset(host x0) + RemoteLoop.run(T, host ref, host loss rates, record=True) -> "
+                      "rtmpc_loop_reset + rtmpc_loop_rollout; trajectories [B,T+1,nx] and tracking errors copied "
+                      "back to pinned host memory, wall clock"}
 
     if rank == 0:
         peaks = {}
@@ -343,7 +325,7 @@ def run_gpu_arm(args):
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": "as_solve_kernel<9,28> (+ ipm_solve_kernel<3,9> on handed-over instances)",
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": "rollout_kernel<9,28> (active-set QP + closed-loop step per control step; ipm_solve_kernel<3,9> on handed-over instances)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure; "

@@ -202,6 +202,29 @@ int rtmpc_loop_step(rtmpc_loop* loop, const double* d_U_t, const int32_t* d_stat
                     double* d_traj_x, int64_t traj_stride, void* stream);
 
 /*
+ * T closed-loop steps of every instance in ONE launch (the whole experiment loop of
+ * Results/results_linear_system.py:209-255 for B Monte-Carlo instances): per step and instance the
+ * controller's QP (TubeTrackingMPC.determine_packet, TubeTrackingMPC.py:196-209; TrackingMPC for the
+ * smart actuator) followed by the step of rtmpc_loop_step.  One warp owns one instance for all T
+ * steps; x_hat feeds the next solve on chip and each solve is warm-started from the previous one.
+ *   qp       the controller's problem (default method RTMPC_METHOD_ACTIVE_SET); sizes must match
+ *   d_ref    reference of instance b at step k (0-based within this call) at
+ *            d_ref[k*ref_stride_t + b*ref_stride_b + 0..nx)  (strides in doubles; 0 = shared)
+ *   d_theta, d_gamma [T*B], d_w [T*B*nx]: explicit realisations, or NULL for the device RNG of
+ *            rtmpc_loop_step (same counters, so a rollout equals T single steps bit for bit)
+ *   d_traj_x [B*traj_stride] or NULL: x_t at d_traj_x[b*traj_stride + t*nx + :], t = 0..T
+ *   d_stats  [8] uint64 or NULL, accumulated: solves by status [4], interior-point iterations,
+ *            active-set steps, certification rounds, algorithmic flops of the active-set method
+ * Instances the active-set method hands over are solved by the interior-point kernel between
+ * relaunches; the call synchronises `stream` before it returns.  Not available for
+ * RTMPC_ACT_EXTENDED (two QPs per step): use rtmpc_qp_solve + rtmpc_loop_step there.
+ */
+int rtmpc_loop_rollout(rtmpc_loop* loop, rtmpc_qp* qp, int32_t T, const double* d_ref, int64_t ref_stride_t,
+                       int64_t ref_stride_b, const int32_t* d_theta, const int32_t* d_gamma, const double* d_w,
+                       const double* d_p_loss, uint64_t seed, int64_t id_offset, double* d_traj_x,
+                       int64_t traj_stride, uint64_t* d_stats, void* stream);
+
+/*
  * The reference's per-object call order, on caller-owned device arrays (all [B*...], FP64/int32):
  *   u, plant_packet = actuator.process_packet(packet, x_t, theta_t)   SmartActuator.py:31-54 / :174-213
  * kind = RTMPC_ACT_SMART (d_A, d_B, d_K_plant, d_x_nom may be NULL) or RTMPC_ACT_CONSISTENT /

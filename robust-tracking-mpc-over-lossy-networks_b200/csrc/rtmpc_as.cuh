@@ -346,6 +346,196 @@ __device__ __forceinline__ int as_certify(const QPDev& P, const double* __restri
     return (worst > tolp) ? 1 : 0;
 }
 
+// One instance, one warp.  x_init / ref: this instance's parameters (ref may be NULL); warm_inst: this
+// instance's warm-start record (npad + 1 ints) or NULL; z_out_inst / U_out_inst: this instance's
+// outputs or NULL.  Returns the status; on RTMPC_FALLBACK nothing has been written.
+template <int R>
+__device__ __forceinline__ int as_solve_instance(const QPDev& P, const double* __restrict__ Gs, ASWarp& w, int lane,
+                                                 const double* x_init, const double* ref, int* warm_inst,
+                                                 double* z_out_inst, double* U_out_inst, ASCounters& cnt) {
+    const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ss = P.ss;
+    const int nslots = mpad >> 5;
+    const double tolp = 1e-11 * P.sc_b;
+    if (lane < nx) {
+        w.xr[lane] = x_init[lane];
+        w.xr[8 + lane] = ref ? ref[lane] : 0.0;
+    }
+    __syncwarp();
+    bool par_bad = false;
+    for (int i = lane; i < P.np; i += 32) {
+        double acc = -P.parh[i];
+        for (int k = 0; k < nx; ++k) acc = fma(P.parC[i * nx + k], w.xr[k], acc);
+        if (acc > 1e-9 * (1.0 + fabs(P.parh[i]))) par_bad = true;
+    }
+    par_bad = __any_sync(RTMPC_FULL_MASK, par_bad);
+    double zuj = 0.0;
+    if (lane < n) {
+        for (int k = 0; k < nx; ++k) {
+            zuj = fma(P.Zx[lane * nx + k], w.xr[k], zuj);
+            zuj = fma(P.Zr[lane * nx + k], w.xr[8 + k], zuj);
+        }
+    }
+    if (lane < npad) { w.zu[lane] = zuj; w.z[lane] = zuj; }
+    // row values and violations at z_u
+    double vu[R], vl[R];
+    double vmax = -RTMPC_INF;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        vu[r] = -RTMPC_INF; vl[r] = -RTMPC_INF;
+        if (r < nslots) {
+            const int row = r * 32 + lane;
+            double t = 0.0, lo = P.lo0[row], up = P.up0[row];
+            for (int k = 0; k < nx; ++k) {
+                t = fma(P.Tx[row * nx + k], w.xr[k], t);
+                t = fma(P.Tr[row * nx + k], w.xr[8 + k], t);
+                lo = fma(P.Lx[row * nx + k], w.xr[k], lo);
+                up = fma(P.Ux[row * nx + k], w.xr[k], up);
+            }
+            if (P.has_up[row]) vu[r] = t - up;
+            if (P.has_lo[row]) vl[r] = lo - t;
+            vmax = fmax(vmax, fmax(vu[r], vl[r]));
+        }
+    }
+    vmax = warp_max(vmax);
+    cnt.flops += 2ull * n * 2 * nx + 2ull * P.m * 4 * nx;
+    __syncwarp();
+
+    int status = RTMPC_OPTIMAL, na = 0;
+    unsigned actu = 0, actl = 0;
+    if (par_bad) status = RTMPC_INFEASIBLE;
+    else if (vmax < 0.0) status = RTMPC_OPTIMAL;      // the unconstrained minimiser is feasible
+    else {
+        // ---- 1. warm start ------------------------------------------------------------------
+        if (warm_inst && P.shift) {
+            const int wn = warm_inst[0];
+            if (wn > 0) {
+                int srow = -1, ssg = 1;
+                if (lane < wn && lane < npad) {
+                    const int code = warm_inst[1 + lane];
+                    const int row = code >> 1;
+                    ssg = (code & 1) ? -1 : 1;
+                    srow = (row >= 0 && row < mpad) ? P.shift[row] : -1;
+                    if (srow >= 0 && !(ssg > 0 ? P.has_up[srow] : P.has_lo[srow])) srow = -1;
+                }
+                const unsigned okm = __ballot_sync(RTMPC_FULL_MASK, srow >= 0);
+                const int pos = __popc(okm & ((1u << lane) - 1u));
+                if (srow >= 0) { w.act_row[pos] = srow; w.act_sgn[pos] = ssg; }
+                na = __popc(okm);
+                __syncwarp();
+                while (na > 0) {
+                    const unsigned keep = as_factor(P, w, na, lane);
+                    const bool mine = lane < na;
+                    const bool kept = mine && ((keep >> lane) & 1u);
+                    double rhs = 0.0;
+                    if (kept) {
+                        const int ra = w.act_row[lane], sg = w.act_sgn[lane];
+                        double t = 0.0;
+                        for (int k = 0; k < nx; ++k) {
+                            t = fma(P.Tx[ra * nx + k], w.xr[k], t);
+                            t = fma(P.Tr[ra * nx + k], w.xr[8 + k], t);
+                        }
+                        rhs = (double)sg * t - as_bound(P, w.xr, ra, sg);
+                    }
+                    double lamv = tri_bwd(w.S, ss, na, lane, tri_fwd(w.S, ss, na, lane, rhs));
+                    if (!kept) lamv = 0.0;
+                    const double lmaxabs = warp_max(fabs(lamv));
+                    const bool bad = mine && (!kept || lamv < -1e-9 * (1.0 + lmaxabs));
+                    cnt.flops += (unsigned long long)na * na * na / 3 + 4ull * na * na;
+                    cnt.steps += 1;
+                    if (!__any_sync(RTMPC_FULL_MASK, bad)) {
+                        if (mine) w.lam[lane] = fmax(lamv, 0.0);
+                        __syncwarp();
+                        break;
+                    }
+                    na = as_compact(w, na, lane, bad, lamv);
+                }
+                if (na > 0) {
+                    if (lane < npad) w.coef[lane] = (lane < na) ? (double)w.act_sgn[lane] * w.lam[lane] : 0.0;
+                    __syncwarp();
+                    as_apply_rows<R>(P, w, na, lane, nslots, vu, vl);
+                    cnt.flops += 2ull * P.m * na;
+                    for (int a = 0; a < na; ++a) {
+                        const int row = w.act_row[a];
+                        if (lane == (row & 31)) {
+                            if (w.act_sgn[a] > 0) actu |= 1u << (row >> 5); else actl |= 1u << (row >> 5);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        // ---- 2./3. Goldfarb-Idnani, then certification -----------------------------------------
+        const int max_steps = 8 * npad + 32;
+        for (int refresh = 0;; ++refresh) {
+            status = as_gi<R>(P, w, na, lane, nslots, vu, vl, actu, actl, tolp, max_steps, cnt);
+            if (status != 0) break;
+            const int c = as_certify<R>(P, Gs, w, na, lane, nslots, vu, vl, actu, actl, tolp, cnt);
+            if (c == 0) { status = RTMPC_OPTIMAL; break; }
+            if (c == 2 || refresh >= 3) { status = RTMPC_FALLBACK; break; }
+        }
+    }
+
+    // ---- outputs ------------------------------------------------------------------------------
+    if (status != RTMPC_FALLBACK) {
+        const bool has_sol = (status == RTMPC_OPTIMAL);
+        const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+        if (lane < npad) w.coef[lane] = (lane < n) ? w.z[lane] * P.D[lane] : 0.0;   // unscaled decision
+        __syncwarp();
+        const int nu = P.nu, N = P.N;
+        const int ou = nx * (N + 1);
+        const int first = z_out_inst ? 0 : ou;              // only the input rows are needed for the packet
+        for (int i = first + lane; i < P.nz; i += 32) {
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) acc = fma(P.Phi[(size_t)i * npad + k], w.coef[k], acc);
+            for (int k = 0; k < nx; ++k) acc = fma(P.Psi[(size_t)i * nx + k], w.xr[k], acc);
+            if (!has_sol) acc = nanv;
+            if (z_out_inst) z_out_inst[i] = acc;
+            if (U_out_inst && i >= ou && i < ou + N * nu) U_out_inst[i - ou] = acc;
+        }
+        if (U_out_inst && P.nss > 0) {
+            // last column of the packet: u_bar + K x_bar
+            const int oxb = ou + N * nu;
+            double val = 0.0;
+            if (lane < nx + nu) {
+                const int i = oxb + lane;
+                for (int k = 0; k < n; ++k) val = fma(P.Phi[(size_t)i * npad + k], w.coef[k], val);
+                for (int k = 0; k < nx; ++k) val = fma(P.Psi[(size_t)i * nx + k], w.xr[k], val);
+            }
+            for (int j = 0; j < nu; ++j) {
+                double acc = __shfl_sync(RTMPC_FULL_MASK, val, nx + j);
+                for (int k = 0; k < nx; ++k) acc = fma(P.Kss[j * nx + k], __shfl_sync(RTMPC_FULL_MASK, val, k), acc);
+                if (lane == 0) U_out_inst[N * nu + j] = has_sol ? acc : nanv;
+            }
+        }
+        cnt.flops += 2ull * (P.nz - first) * (n + nx);
+    }
+    if (warm_inst) {
+        const int nw = (status == RTMPC_OPTIMAL) ? na : -1;
+        if (lane == 0) warm_inst[0] = nw;
+        if (lane < nw) warm_inst[1 + lane] = 2 * w.act_row[lane] + (w.act_sgn[lane] < 0 ? 1 : 0);
+    }
+    __syncwarp();
+    return status;
+}
+
+// G staged on chip (or the padded global copy), and the per-warp scratch
+__device__ __forceinline__ const double* as_stage(const QPDev& P, double* smem, int g_in_smem, double** wbase) {
+    if (!g_in_smem) { *wbase = smem; return P.Gpad; }
+    const int npad = P.npad, mpad = P.mpad;
+    for (int idx = threadIdx.x; idx < mpad * npad; idx += blockDim.x) {
+        int i = idx / npad, j = idx - i * npad;
+        smem[i * P.gs + j] = P.G[idx];
+    }
+    for (int idx = threadIdx.x; idx < mpad * 2; idx += blockDim.x) smem[(size_t)(idx >> 1) * P.gs + npad + (idx & 1)] = 0.0;
+    __syncthreads();
+    *wbase = smem + (size_t)mpad * P.gs;
+    return smem;
+}
+
+__device__ __forceinline__ int as_pack_iters(const ASCounters& cnt) {
+    return ((cnt.steps > 4095 ? 4095 : cnt.steps) << 12) | ((cnt.rounds > 255 ? 255 : cnt.rounds) << 24);
+}
+
 template <int R, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 as_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double* __restrict__ ref,
@@ -356,194 +546,23 @@ as_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double*
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ss = P.ss;
-    const int nslots = mpad >> 5;
-    const double tolp = 1e-11 * P.sc_b;
-
-    const double* Gs;
-    double* wbase = smem;
-    if (g_in_smem) {
-        double* Gw = smem;
-        for (int idx = threadIdx.x; idx < mpad * npad; idx += blockDim.x) {
-            int i = idx / npad, j = idx - i * npad;
-            Gw[i * P.gs + j] = P.G[idx];
-        }
-        for (int idx = threadIdx.x; idx < mpad * 2; idx += blockDim.x) Gw[(size_t)(idx >> 1) * P.gs + npad + (idx & 1)] = 0.0;
-        Gs = Gw;
-        wbase = smem + (size_t)mpad * P.gs;
-        __syncthreads();
-    } else {
-        Gs = P.Gpad;    // global copy with the same row stride
-    }
+    const int nx = P.nx;
+    double* wbase;
+    const double* Gs = as_stage(P, smem, g_in_smem, &wbase);
     ASWarp w = as_carve(wbase + (size_t)warp * as_warp_doubles(P), P);
-
+    const size_t usz = (size_t)(P.N + 1) * P.nu;
     for (int inst = blockIdx.x * wpb + warp; inst < B; inst += gridDim.x * wpb) {
         if (sel && sel[inst] != sel_value) continue;
         ASCounters cnt;
         cnt.steps = 0; cnt.rounds = 0; cnt.flops = 0;
-        if (lane < nx) {
-            w.xr[lane] = x_init[(size_t)inst * nx + lane];
-            w.xr[8 + lane] = ref ? ref[(size_t)inst * nx + lane] : 0.0;
-        }
-        __syncwarp();
-        bool par_bad = false;
-        for (int i = lane; i < P.np; i += 32) {
-            double acc = -P.parh[i];
-            for (int k = 0; k < nx; ++k) acc = fma(P.parC[i * nx + k], w.xr[k], acc);
-            if (acc > 1e-9 * (1.0 + fabs(P.parh[i]))) par_bad = true;
-        }
-        par_bad = __any_sync(RTMPC_FULL_MASK, par_bad);
-        double zuj = 0.0;
-        if (lane < n) {
-            for (int k = 0; k < nx; ++k) {
-                zuj = fma(P.Zx[lane * nx + k], w.xr[k], zuj);
-                zuj = fma(P.Zr[lane * nx + k], w.xr[8 + k], zuj);
-            }
-        }
-        if (lane < npad) { w.zu[lane] = zuj; w.z[lane] = zuj; }
-        // row values and violations at z_u
-        double vu[R], vl[R];
-        double vmax = -RTMPC_INF;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            vu[r] = -RTMPC_INF; vl[r] = -RTMPC_INF;
-            if (r < nslots) {
-                const int row = r * 32 + lane;
-                double t = 0.0, lo = P.lo0[row], up = P.up0[row];
-                for (int k = 0; k < nx; ++k) {
-                    t = fma(P.Tx[row * nx + k], w.xr[k], t);
-                    t = fma(P.Tr[row * nx + k], w.xr[8 + k], t);
-                    lo = fma(P.Lx[row * nx + k], w.xr[k], lo);
-                    up = fma(P.Ux[row * nx + k], w.xr[k], up);
-                }
-                if (P.has_up[row]) vu[r] = t - up;
-                if (P.has_lo[row]) vl[r] = lo - t;
-                vmax = fmax(vmax, fmax(vu[r], vl[r]));
-            }
-        }
-        vmax = warp_max(vmax);
-        cnt.flops += 2ull * n * 2 * nx + 2ull * P.m * 4 * nx;
-        __syncwarp();
-
-        int status = RTMPC_OPTIMAL, na = 0;
-        unsigned actu = 0, actl = 0;
-        if (par_bad) status = RTMPC_INFEASIBLE;
-        else if (vmax < 0.0) status = RTMPC_OPTIMAL;      // the unconstrained minimiser is feasible
-        else {
-            // ---- 1. warm start ------------------------------------------------------------------
-            if (warm && P.shift) {
-                const int ws = npad + 1;
-                const int wn = warm[(size_t)inst * ws];
-                if (wn > 0) {
-                    int srow = -1, ssg = 1;
-                    if (lane < wn && lane < npad) {
-                        const int code = warm[(size_t)inst * ws + 1 + lane];
-                        const int row = code >> 1;
-                        ssg = (code & 1) ? -1 : 1;
-                        srow = (row >= 0 && row < mpad) ? P.shift[row] : -1;
-                        if (srow >= 0 && !(ssg > 0 ? P.has_up[srow] : P.has_lo[srow])) srow = -1;
-                    }
-                    const unsigned okm = __ballot_sync(RTMPC_FULL_MASK, srow >= 0);
-                    const int pos = __popc(okm & ((1u << lane) - 1u));
-                    if (srow >= 0) { w.act_row[pos] = srow; w.act_sgn[pos] = ssg; }
-                    na = __popc(okm);
-                    __syncwarp();
-                    while (na > 0) {
-                        const unsigned keep = as_factor(P, w, na, lane);
-                        const bool mine = lane < na;
-                        const bool kept = mine && ((keep >> lane) & 1u);
-                        double rhs = 0.0;
-                        if (kept) {
-                            const int ra = w.act_row[lane], sg = w.act_sgn[lane];
-                            double t = 0.0;
-                            for (int k = 0; k < nx; ++k) {
-                                t = fma(P.Tx[ra * nx + k], w.xr[k], t);
-                                t = fma(P.Tr[ra * nx + k], w.xr[8 + k], t);
-                            }
-                            rhs = (double)sg * t - as_bound(P, w.xr, ra, sg);
-                        }
-                        double lamv = tri_bwd(w.S, ss, na, lane, tri_fwd(w.S, ss, na, lane, rhs));
-                        if (!kept) lamv = 0.0;
-                        const double lmaxabs = warp_max(fabs(lamv));
-                        const bool bad = mine && (!kept || lamv < -1e-9 * (1.0 + lmaxabs));
-                        cnt.flops += (unsigned long long)na * na * na / 3 + 4ull * na * na;
-                        cnt.steps += 1;
-                        if (!__any_sync(RTMPC_FULL_MASK, bad)) {
-                            if (mine) w.lam[lane] = fmax(lamv, 0.0);
-                            __syncwarp();
-                            break;
-                        }
-                        na = as_compact(w, na, lane, bad, lamv);
-                    }
-                    if (na > 0) {
-                        if (lane < npad) w.coef[lane] = (lane < na) ? (double)w.act_sgn[lane] * w.lam[lane] : 0.0;
-                        __syncwarp();
-                        as_apply_rows<R>(P, w, na, lane, nslots, vu, vl);
-                        cnt.flops += 2ull * P.m * na;
-                        for (int a = 0; a < na; ++a) {
-                            const int row = w.act_row[a];
-                            if (lane == (row & 31)) {
-                                if (w.act_sgn[a] > 0) actu |= 1u << (row >> 5); else actl |= 1u << (row >> 5);
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-            // ---- 2./3. Goldfarb-Idnani, then certification -----------------------------------------
-            const int max_steps = 8 * npad + 32;
-            for (int refresh = 0;; ++refresh) {
-                status = as_gi<R>(P, w, na, lane, nslots, vu, vl, actu, actl, tolp, max_steps, cnt);
-                if (status != 0) break;
-                const int c = as_certify<R>(P, Gs, w, na, lane, nslots, vu, vl, actu, actl, tolp, cnt);
-                if (c == 0) { status = RTMPC_OPTIMAL; break; }
-                if (c == 2 || refresh >= 3) { status = RTMPC_FALLBACK; break; }
-            }
-        }
-
-        // ---- outputs ------------------------------------------------------------------------------
-        if (status != RTMPC_FALLBACK) {
-            const bool has_sol = (status == RTMPC_OPTIMAL);
-            const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-            if (lane < npad) w.coef[lane] = (lane < n) ? w.z[lane] * P.D[lane] : 0.0;   // unscaled decision
-            __syncwarp();
-            const int nu = P.nu, N = P.N;
-            const int ou = nx * (N + 1);
-            const int first = z_out ? 0 : ou;              // only the input rows are needed for the packet
-            for (int i = first + lane; i < P.nz; i += 32) {
-                double acc = 0.0;
-                for (int k = 0; k < n; ++k) acc = fma(P.Phi[(size_t)i * npad + k], w.coef[k], acc);
-                for (int k = 0; k < nx; ++k) acc = fma(P.Psi[(size_t)i * nx + k], w.xr[k], acc);
-                if (!has_sol) acc = nanv;
-                if (z_out) z_out[(size_t)inst * P.nz + i] = acc;
-                if (U_out && i >= ou && i < ou + N * nu) U_out[(size_t)inst * (N + 1) * nu + (i - ou)] = acc;
-            }
-            if (U_out && P.nss > 0) {
-                // last column of the packet: u_bar + K x_bar
-                const int oxb = ou + N * nu;
-                double val = 0.0;
-                if (lane < nx + nu) {
-                    const int i = oxb + lane;
-                    for (int k = 0; k < n; ++k) val = fma(P.Phi[(size_t)i * npad + k], w.coef[k], val);
-                    for (int k = 0; k < nx; ++k) val = fma(P.Psi[(size_t)i * nx + k], w.xr[k], val);
-                }
-                for (int j = 0; j < nu; ++j) {
-                    double acc = __shfl_sync(RTMPC_FULL_MASK, val, nx + j);
-                    for (int k = 0; k < nx; ++k) acc = fma(P.Kss[j * nx + k], __shfl_sync(RTMPC_FULL_MASK, val, k), acc);
-                    if (lane == 0) U_out[(size_t)inst * (N + 1) * nu + N * nu + j] = has_sol ? acc : nanv;
-                }
-            }
-            cnt.flops += 2ull * (P.nz - first) * (n + nx);
-        }
-        if (warm) {
-            const int ws = npad + 1;
-            const int nw = (status == RTMPC_OPTIMAL) ? na : -1;
-            if (lane == 0) warm[(size_t)inst * ws] = nw;
-            if (lane < nw) warm[(size_t)inst * ws + 1 + lane] = 2 * w.act_row[lane] + (w.act_sgn[lane] < 0 ? 1 : 0);
-        }
+        const int status = as_solve_instance<R>(P, Gs, w, lane, x_init + (size_t)inst * nx,
+                                                ref ? ref + (size_t)inst * nx : nullptr,
+                                                warm ? warm + (size_t)inst * (P.npad + 1) : nullptr,
+                                                z_out ? z_out + (size_t)inst * P.nz : nullptr,
+                                                U_out ? U_out + inst * usz : nullptr, cnt);
         if (lane == 0) {
             if (status_out) status_out[inst] = status;
-            if (iters_out) iters_out[inst] = ((cnt.steps > 4095 ? 4095 : cnt.steps) << 12) | (cnt.rounds << 24);
+            if (iters_out) iters_out[inst] = as_pack_iters(cnt);
             if (work) atomicAdd(work, cnt.flops);
         }
         __syncwarp();

@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 
+#define RTMPC_LOOP_KERNELS
 #include "rtmpc_launch.h"
 #include "rtmpc_loop.cuh"
 
@@ -170,6 +171,10 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
         rtmpc_qp_destroy(q);
         return fail("rtmpc_qp_create: problem does not fit the active-set kernel", e);
     }
+    if (!rollout_configure(P, max_smem, &e)) {
+        rtmpc_qp_destroy(q);
+        return fail("rtmpc_qp_create: problem does not fit the rollout kernel", e);
+    }
     *out = q;
     return 0;
 }
@@ -301,6 +306,12 @@ struct rtmpc_loop {
     LoopDev dev;
     std::vector<void*> allocs;
     int B = 0, t = 0;
+    // scratch of rtmpc_loop_rollout
+    double *r_U = nullptr, *r_ref = nullptr;
+    int *r_status = nullptr, *r_iters = nullptr, *r_inst_t = nullptr, *r_pending = nullptr, *r_npend = nullptr;
+    int* r_warm = nullptr;
+    int r_warm_stride = 0;
+    int* h_npend = nullptr;     // pinned
 };
 
 template <typename T>
@@ -357,7 +368,15 @@ int rtmpc_loop_create(const rtmpc_loop_desc* d, int32_t B, rtmpc_loop** out) {
     rc |= lalloc(l, (size_t)B, &L.alive);
     rc |= lalloc(l, (size_t)B, &L.last_loss);
     rc |= lalloc(l, (size_t)B, &L.gamma_last);
+    rc |= lalloc(l, (size_t)B * (d->N + 1) * nu, &l->r_U);
+    rc |= lalloc(l, (size_t)B * nx, &l->r_ref);
+    rc |= lalloc(l, (size_t)B, &l->r_status);
+    rc |= lalloc(l, (size_t)B, &l->r_iters);
+    rc |= lalloc(l, (size_t)B, &l->r_inst_t);
+    rc |= lalloc(l, (size_t)B, &l->r_pending);
+    rc |= lalloc(l, (size_t)1, &l->r_npend);
     if (rc) { rtmpc_loop_destroy(l); return -1; }
+    if (cudaMallocHost(&l->h_npend, sizeof(int)) != cudaSuccess) { rtmpc_loop_destroy(l); return fail("cudaMallocHost"); }
     *out = l;
     std::vector<double> x0((size_t)B * nx, 0.0);
     return rtmpc_loop_reset(l, x0.data());
@@ -366,6 +385,8 @@ int rtmpc_loop_create(const rtmpc_loop_desc* d, int32_t B, rtmpc_loop** out) {
 void rtmpc_loop_destroy(rtmpc_loop* l) {
     if (!l) return;
     for (void* p : l->allocs) cudaFree(p);
+    cudaFree(l->r_warm);
+    if (l->h_npend) cudaFreeHost(l->h_npend);
     delete l;
 }
 
@@ -388,6 +409,7 @@ int rtmpc_loop_reset(rtmpc_loop* l, const double* h_x0) {
     CU(cudaMemcpy(L.alive, ones.data(), B * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(L.last_loss, minus.data(), B * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(L.gamma_last, ones.data(), B * sizeof(int), cudaMemcpyHostToDevice));
+    if (l->r_warm) CU(cudaMemset(l->r_warm, 0xFF, B * (size_t)l->r_warm_stride * sizeof(int)));
     l->t = 0;
     return 0;
 }
@@ -419,6 +441,58 @@ int rtmpc_loop_step(rtmpc_loop* l, const double* d_U_t, const int32_t* d_status,
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     l->t += 1;
+    return 0;
+}
+
+int rtmpc_loop_rollout(rtmpc_loop* l, rtmpc_qp* q, int32_t T, const double* d_ref, int64_t ref_stride_t,
+                       int64_t ref_stride_b, const int32_t* d_theta, const int32_t* d_gamma, const double* d_w,
+                       const double* d_p_loss, uint64_t seed, int64_t id_offset, double* d_traj_x, int64_t traj_stride,
+                       uint64_t* d_stats, void* stream) {
+    if (!l || !q) return fail("rtmpc_loop_rollout: null handle");
+    if (T <= 0) return 0;
+    if ((d_theta == nullptr) != (d_gamma == nullptr)) return fail("rtmpc_loop_rollout: theta and gamma must be given together");
+    const QPDev& P = q->dev;
+    if (P.nx != l->dev.nx || P.nu != l->dev.nu || P.N != l->dev.N) return fail("rtmpc_loop_rollout: QP and loop sizes differ");
+    if (l->dev.actuator == RTMPC_ACT_EXTENDED) return fail("rtmpc_loop_rollout: the extended variant switches between two QPs; use rtmpc_qp_solve + rtmpc_loop_step");
+    if (q->method != RTMPC_METHOD_ACTIVE_SET) return fail("rtmpc_loop_rollout: needs RTMPC_METHOD_ACTIVE_SET");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t B = l->B;
+    if (!l->r_warm || l->r_warm_stride != P.npad + 1) {
+        cudaFree(l->r_warm);
+        l->r_warm = nullptr;
+        l->r_warm_stride = P.npad + 1;
+        CU(cudaMalloc(&l->r_warm, B * (size_t)l->r_warm_stride * sizeof(int)));
+        CU(cudaMemsetAsync(l->r_warm, 0xFF, B * (size_t)l->r_warm_stride * sizeof(int), s));
+    }
+    RolloutArgs a;
+    a.B = l->B; a.t0 = l->t; a.T = l->t + T;
+    a.ref = d_ref; a.ref_stride_t = ref_stride_t; a.ref_stride_b = ref_stride_b;
+    a.theta = d_theta; a.gamma = d_gamma; a.w = d_w; a.p_loss = d_p_loss;
+    a.seed = seed; a.id_offset = id_offset; a.traj = d_traj_x; a.traj_stride = traj_stride;
+    a.warm = l->r_warm; a.U = l->r_U; a.z = nullptr; a.status = l->r_status; a.iters = l->r_iters;
+    a.inst_t = l->r_inst_t; a.pending = l->r_pending; a.ref_pending = l->r_ref; a.n_pending = l->r_npend;
+    a.stats = reinterpret_cast<unsigned long long*>(d_stats);
+    // every instance starts at the loop's common time
+    std::vector<int> t0(B, l->t);
+    CU(cudaMemcpyAsync(l->r_inst_t, t0.data(), B * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(l->r_pending, 0, B * sizeof(int), s));
+    for (int round = 0;; ++round) {
+        CU(cudaMemsetAsync(l->r_npend, 0, sizeof(int), s));
+        CU(rollout_launch(P, l->dev, q->as_wpb, q->as_smem, q->as_g_in_smem, q->num_sms, a, s));
+        g_launches.fetch_add(1);
+        CU(cudaMemcpyAsync(l->h_npend, l->r_npend, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (*l->h_npend == 0) break;
+        if (round > T * 4 + 16) return fail("rtmpc_loop_rollout: parked instances do not make progress");
+        // parked instances: interior-point solve of their current step, then resume
+        QPLaunch f;
+        f.B = l->B; f.x_init = l->dev.x_hat; f.ref = d_ref ? l->r_ref : nullptr; f.sel = l->r_status;
+        f.sel_value = RTMPC_FALLBACK_STATUS; f.z = nullptr; f.U = l->r_U; f.status = l->r_status; f.iters = l->r_iters;
+        f.warm = l->r_warm; f.work = nullptr; f.stream = s;
+        CU(ipm_launch(P, q->ipm_wpb, q->ipm_smem, q->num_sms, f));
+        g_launches.fetch_add(1);
+    }
+    l->t += T;
     return 0;
 }
 

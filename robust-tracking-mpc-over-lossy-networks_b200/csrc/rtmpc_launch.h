@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "rtmpc_ipm.cuh"
+#include "rtmpc_loop.cuh"
 
 namespace rtmpc {
 
@@ -24,5 +25,29 @@ cudaError_t ipm_launch(const QPDev& P, int wpb, size_t smem, int num_sms, const 
 // dual active-set kernel
 bool as_configure(const QPDev& P, int max_smem, int* wpb, size_t* smem, int* g_in_smem, cudaError_t* err);
 cudaError_t as_launch(const QPDev& P, int wpb, size_t smem, int g_in_smem, int num_sms, const QPLaunch& a);
+
+// persistent closed-loop rollout (rtmpc_rollout.cu); uses the active-set kernel's launch shape
+struct RolloutArgs {
+    int B, T, t0;                 // instances; steps t0 .. T-1 are taken
+    const double* ref;            // reference of instance b at step t: ref[(t - t0) * ref_stride_t + b * ref_stride_b + :]
+    long long ref_stride_t, ref_stride_b;
+    const int *theta, *gamma;     // explicit realisations [T - t0][B] (and w [T - t0][B][nx]) or NULL: device RNG
+    const double* w;
+    const double* p_loss;
+    unsigned long long seed;
+    long long id_offset;
+    double* traj;
+    long long traj_stride;
+    int* warm;                    // [B * (npad + 1)] warm-start records
+    double *U, *z;                // [B * (N+1) * nu] packet payloads; [B * nz] or NULL
+    int *status, *iters;          // [B] of the last solve
+    int *inst_t, *pending;        // [B] per-instance time; 1 = current step solved by the interior-point kernel
+    double* ref_pending;          // [B * nx] reference of the step a parked instance waits at
+    int* n_pending;               // instances parked by this launch
+    unsigned long long* stats;    // [8] status counts[4], IPM iterations, active-set steps, rounds, flops (or NULL)
+};
+bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err);
+cudaError_t rollout_launch(const QPDev& P, const LoopDev& L, int wpb, size_t smem, int g_in_smem, int num_sms,
+                           const RolloutArgs& a, cudaStream_t stream);
 
 }  // namespace rtmpc

@@ -47,54 +47,63 @@ __device__ __forceinline__ void cartpole_substeps(double* x, double F, const dou
     x[0] = pos; x[1] = vel; x[2] = phi; x[3] = om;
 }
 
-__global__ void loop_step_kernel(LoopDev L, int B, int t, const double* __restrict__ U_t,
-                                 const int* __restrict__ status, const double* __restrict__ x_nom0,
-                                 long long x_nom0_stride, const double* __restrict__ ref,
-                                 const int* __restrict__ theta_in, const int* __restrict__ gamma_in,
-                                 const double* __restrict__ w_in, const double* __restrict__ p_loss,
-                                 unsigned long long seed, long long id_offset, double* __restrict__ traj,
-                                 long long traj_stride) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+// tube containment statistic  max_i (Hz (x - x_nom) - hz)_i  of instance b, rows i = first, first+stride, ...
+__device__ __forceinline__ double loop_tube_rows(const LoopDev& L, int b, int first, int stride) {
+    const int nx = L.nx;
+    double d[LOOP_MAX_NX];
+    for (int k = 0; k < nx; ++k) d[k] = L.x[(size_t)b * nx + k] - L.x_nom[(size_t)b * nx + k];
+    double worst = -1e300;
+    for (int i = first; i < L.nz_rows; i += stride) {
+        double acc = -L.hz[i];
+        for (int k = 0; k < nx; ++k) acc = fma(L.Hz[i * nx + k], d[k], acc);
+        worst = fmax(worst, acc);
+    }
+    return worst;
+}
+
+// Start of a control step for instance b: records x_0, retires the instance when the controller
+// returned None.  Returns false when the instance takes no step.
+__device__ __forceinline__ bool loop_step_begin(const LoopDev& L, int b, int t, int status_b, double* traj_b) {
+    if (!L.alive[b]) return false;
+    const int nx = L.nx;
+    if (traj_b && t == 0) for (int k = 0; k < nx; ++k) traj_b[k] = L.x[(size_t)b * nx + k];
+    // controller returned None (infeasible): the reference stops this controller's run
+    if (status_b == RTMPC_INFEASIBLE) { L.alive[b] = 0; return false; }
+    return true;
+}
+
+// One closed-loop step of instance b (one thread): statistics, network / disturbance realisation,
+// local side, plant, remote side.  Ub: this step's packet payload [(N+1)*nu]; x_nom0_b: x_nom[:,0]
+// of this step's solve or NULL; theta_in < 0 selects the device RNG.
+// (no __restrict__: inside the rollout kernel these buffers are written by the same warp)
+__device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, const double* Ub, const double* x_nom0_b,
+                                               const double* ref_b, int theta_in, int gamma_in, const double* w_in_b,
+                                               double p, unsigned long long seed, unsigned long long id, double* traj_b,
+                                               double tube_worst) {
     const int nx = L.nx, nu = L.nu, N = L.N;
-    if (!L.alive[b]) return;
     double x[LOOP_MAX_NX], xn[LOOP_MAX_NX], xh[LOOP_MAX_NX], w[LOOP_MAX_NX];
     for (int k = 0; k < nx; ++k) {
         x[k] = L.x[(size_t)b * nx + k];
         xn[k] = L.x_nom[(size_t)b * nx + k];
         xh[k] = L.x_hat[(size_t)b * nx + k];
     }
-    if (traj && t == 0) for (int k = 0; k < nx; ++k) traj[(size_t)b * traj_stride + k] = x[k];
-    // controller returned None (infeasible): the reference stops this controller's run
-    if (status && status[b] == RTMPC_INFEASIBLE) { L.alive[b] = 0; return; }
-
     // statistics on the pre-step state (x_traj[:, t] in the reference's scripts)
-    if (ref) {
+    if (ref_b) {
         double e = 0.0;
-        for (int k = 0; k < nx; ++k) { double d = x[k] - ref[(size_t)b * nx + k]; e = fma(d, d, e); }
+        for (int k = 0; k < nx; ++k) { double d = x[k] - ref_b[k]; e = fma(d, d, e); }
         L.err_acc[b] += e;
     }
-    if (L.nz_rows > 0) {
-        double worst = L.tube_max[b];
-        for (int i = 0; i < L.nz_rows; ++i) {
-            double acc = -L.hz[i];
-            for (int k = 0; k < nx; ++k) acc = fma(L.Hz[i * nx + k], x[k] - xn[k], acc);
-            worst = fmax(worst, acc);
-        }
-        L.tube_max[b] = worst;
-    }
+    if (L.nz_rows > 0) L.tube_max[b] = fmax(L.tube_max[b], tube_worst);
 
     // network and disturbance realisation
     int theta, gamma;
-    if (theta_in) {
-        theta = theta_in[b];
-        gamma = gamma_in[b];
-        for (int k = 0; k < nx; ++k) w[k] = w_in ? w_in[(size_t)b * nx + k] : 0.0;
+    if (theta_in >= 0) {
+        theta = theta_in;
+        gamma = gamma_in;
+        for (int k = 0; k < nx; ++k) w[k] = w_in_b ? w_in_b[k] : 0.0;
     } else {
-        const unsigned long long id = (unsigned long long)(id_offset + b);
         const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
         Philox4 r = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, 0u, k0, k1);
-        const double p = p_loss ? p_loss[b] : 0.0;
         theta = (t == 0) ? 1 : (u01_from_bits(r.x, r.y) < p ? 0 : 1);
         gamma = (t == 0) ? 1 : (u01_from_bits(r.z, r.w) < p ? 0 : 1);
         for (int k = 0; k < nx; k += 2) {
@@ -112,12 +121,11 @@ __global__ void loop_step_kernel(LoopDev L, int B, int t, const double* __restri
     else last_loss = t;
     int s_t = L.s_t[b];
     double* buf = L.buf + (size_t)b * (N + 1) * nu;
-    const double* Ub = U_t + (size_t)b * (N + 1) * nu;
     if (Theta) {
         s_t = t;
         for (int i = 0; i < (N + 1) * nu; ++i) buf[i] = Ub[i];
-        if (L.actuator != RTMPC_ACT_SMART && x_nom0)    // packet carries x_nom_0 (SmartActuator.py:183-187,219-222)
-            for (int k = 0; k < nx; ++k) xn[k] = x_nom0[(size_t)b * x_nom0_stride + k];
+        if (L.actuator != RTMPC_ACT_SMART && x_nom0_b)    // packet carries x_nom_0 (SmartActuator.py:183-187,219-222)
+            for (int k = 0; k < nx; ++k) xn[k] = x_nom0_b[k];
     }
     const int kk = t - s_t;
     const double* xfb = (L.actuator == RTMPC_ACT_SMART) ? x : xn;   // state fed to compute_u_t
@@ -191,8 +199,8 @@ __global__ void loop_step_kernel(LoopDev L, int B, int t, const double* __restri
         xbase = xp;
     } else {
         for (int j = 0; j < nu; ++j) uh[j] = Ub[j];           // first input of the latest sent sequence
-        if (L.actuator == RTMPC_ACT_EXTENDED && x_nom0) {
-            for (int k = 0; k < nx; ++k) xn0[k] = x_nom0[(size_t)b * x_nom0_stride + k];
+        if (L.actuator == RTMPC_ACT_EXTENDED && x_nom0_b) {
+            for (int k = 0; k < nx; ++k) xn0[k] = x_nom0_b[k];
             xbase = xn0;
         } else xbase = xh;
     }
@@ -215,7 +223,27 @@ __global__ void loop_step_kernel(LoopDev L, int B, int t, const double* __restri
     L.Theta[b] = Theta;
     L.last_loss[b] = last_loss;
     L.gamma_last[b] = gamma;
-    if (traj) for (int k = 0; k < nx; ++k) traj[(size_t)b * traj_stride + (size_t)(t + 1) * nx + k] = xnew[k];
+    if (traj_b) for (int k = 0; k < nx; ++k) traj_b[(size_t)(t + 1) * nx + k] = xnew[k];
+}
+
+#ifdef RTMPC_LOOP_KERNELS   // the non-template kernels are compiled in one translation unit (rtmpc_capi.cu)
+__global__ void loop_step_kernel(LoopDev L, int B, int t, const double* __restrict__ U_t,
+                                 const int* __restrict__ status, const double* __restrict__ x_nom0,
+                                 long long x_nom0_stride, const double* __restrict__ ref,
+                                 const int* __restrict__ theta_in, const int* __restrict__ gamma_in,
+                                 const double* __restrict__ w_in, const double* __restrict__ p_loss,
+                                 unsigned long long seed, long long id_offset, double* __restrict__ traj,
+                                 long long traj_stride) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nx = L.nx, nu = L.nu, N = L.N;
+    double* traj_b = traj ? traj + (size_t)b * traj_stride : nullptr;
+    if (!loop_step_begin(L, b, t, status ? status[b] : RTMPC_OPTIMAL, traj_b)) return;
+    const double worst = (L.nz_rows > 0) ? loop_tube_rows(L, b, 0, 1) : 0.0;
+    loop_step_body(L, b, t, U_t + (size_t)b * (N + 1) * nu, x_nom0 ? x_nom0 + (size_t)b * x_nom0_stride : nullptr,
+                   ref ? ref + (size_t)b * nx : nullptr, theta_in ? theta_in[b] : -1, theta_in ? gamma_in[b] : -1,
+                   w_in ? w_in + (size_t)b * nx : nullptr, p_loss ? p_loss[b] : 0.0, seed,
+                   (unsigned long long)(id_offset + b), traj_b, worst);
 }
 
 // out[j] = max_v <dirs[j,:], V[v,:]> ; one thread per direction, vertices staged in shared memory
@@ -358,5 +386,7 @@ __global__ void estimator_update_kernel(EstArgs e, int B) {
     for (int i = 0; i < nx; ++i) e.x_hat[(size_t)b * nx + i] = out[i];
     if (e.gamma[b] == 1) e.q_t[b] = e.t;
 }
+
+#endif  // RTMPC_LOOP_KERNELS
 
 }  // namespace rtmpc

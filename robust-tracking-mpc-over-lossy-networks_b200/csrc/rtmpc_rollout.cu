@@ -1,0 +1,136 @@
+// Persistent closed-loop rollout: one warp owns one instance for all T control steps.
+//
+// Per control step the warp solves the instance's tracking-MPC QP with the dual active-set method
+// (rtmpc_as.cuh, warm-started from its own previous step) and then takes the closed-loop step of
+// rtmpc_loop.cuh (consistent actuator, nominal model, ancillary law, plant, estimator; lane 0, with the
+// tube-containment statistic spread over the lanes).  Instances never exchange data, so a rollout is a
+// single launch: no per-step launch latency and no waiting for the slowest instance of every step.
+// An instance whose solve has to be handed to the interior-point kernel parks itself (inst_t, pending,
+// ref_pending); the host runs that kernel on the parked instances and relaunches, which resumes them.
+#include "rtmpc_as.cuh"
+#include "rtmpc_launch.h"
+#include "rtmpc_loop.cuh"
+
+namespace rtmpc {
+
+template <int R, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1)
+rollout_kernel(QPDev P, LoopDev L, RolloutArgs a, int g_in_smem) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int nx = P.nx;
+    double* wbase;
+    const double* Gs = as_stage(P, smem, g_in_smem, &wbase);
+    ASWarp w = as_carve(wbase + (size_t)warp * as_warp_doubles(P), P);
+    const size_t usz = (size_t)(P.N + 1) * P.nu;
+
+    for (int inst = blockIdx.x * wpb + warp; inst < a.B; inst += gridDim.x * wpb) {
+        int t = a.inst_t[inst];
+        if (t >= a.T) continue;
+        bool have = a.pending[inst] != 0;       // this step was solved by the interior-point kernel
+        unsigned n_status[4] = {0, 0, 0, 0}, n_ipm = 0, n_steps = 0, n_rounds = 0;
+        unsigned long long n_flops = 0;
+        double* U_inst = a.U + inst * usz;
+        double* z_inst = a.z ? a.z + (size_t)inst * P.nz : nullptr;
+        int* warm_inst = a.warm ? a.warm + (size_t)inst * (P.npad + 1) : nullptr;
+        double* traj_b = a.traj ? a.traj + (size_t)inst * a.traj_stride : nullptr;
+        const double p = a.p_loss ? a.p_loss[inst] : 0.0;
+        for (; t < a.T; ++t) {
+            if (!L.alive[inst]) { t = a.T; break; }
+            const int k = t - a.t0;
+            const double* ref_t = a.ref ? a.ref + (size_t)k * a.ref_stride_t + (size_t)inst * a.ref_stride_b : nullptr;
+            int status;
+            if (have) {
+                have = false;
+                status = a.status[inst];
+                const int it = a.iters[inst];
+                n_ipm += it & 0xFFF;
+                n_rounds += (it >> 24) & 0xFF;
+                if (lane == 0) a.pending[inst] = 0;
+            } else {
+                ASCounters cnt;
+                cnt.steps = 0; cnt.rounds = 0; cnt.flops = 0;
+                status = as_solve_instance<R>(P, Gs, w, lane, L.x_hat + (size_t)inst * nx, ref_t, warm_inst, z_inst,
+                                              U_inst, cnt);
+                n_steps += cnt.steps; n_rounds += cnt.rounds; n_flops += cnt.flops;
+                if (status == RTMPC_FALLBACK) {
+                    if (lane == 0) {
+                        a.status[inst] = RTMPC_FALLBACK;
+                        a.pending[inst] = 1;
+                        for (int j = 0; j < nx; ++j) a.ref_pending[(size_t)inst * nx + j] = ref_t ? ref_t[j] : 0.0;
+                        atomicAdd(a.n_pending, 1);
+                    }
+                    break;
+                }
+                if (lane == 0) { a.status[inst] = status; a.iters[inst] = as_pack_iters(cnt); }
+            }
+            if (status >= 0 && status < 4) n_status[status] += 1;
+            __syncwarp();
+            // ---- closed-loop step ------------------------------------------------------------
+            int go = 0;
+            if (lane == 0) go = loop_step_begin(L, inst, t, status, traj_b) ? 1 : 0;
+            go = __shfl_sync(RTMPC_FULL_MASK, go, 0);
+            if (go) {
+                double worst = 0.0;
+                if (L.nz_rows > 0) worst = warp_max(loop_tube_rows(L, inst, lane, 32));
+                if (lane == 0) {
+                    const bool expl = a.theta != nullptr;
+                    loop_step_body(L, inst, t, U_inst, (L.actuator == RTMPC_ACT_EXTENDED) ? z_inst : nullptr, ref_t,
+                                   expl ? a.theta[(size_t)k * a.B + inst] : -1, expl ? a.gamma[(size_t)k * a.B + inst] : -1,
+                                   (expl && a.w) ? a.w + ((size_t)k * a.B + inst) * nx : nullptr, p, a.seed,
+                                   (unsigned long long)(a.id_offset + inst), traj_b, worst);
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            a.inst_t[inst] = t;
+            if (a.stats) {
+                for (int i = 0; i < 4; ++i) if (n_status[i]) atomicAdd(a.stats + i, (unsigned long long)n_status[i]);
+                if (n_ipm) atomicAdd(a.stats + 4, (unsigned long long)n_ipm);
+                if (n_steps) atomicAdd(a.stats + 5, (unsigned long long)n_steps);
+                if (n_rounds) atomicAdd(a.stats + 6, (unsigned long long)n_rounds);
+                if (n_flops) atomicAdd(a.stats + 7, n_flops);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+typedef void (*ro_fn)(QPDev, LoopDev, RolloutArgs, int);
+struct RoChoice { int r, maxw; ro_fn fn; };
+static const RoChoice kRo[] = {
+    {4, 32, rollout_kernel<4, 32>},   {9, 28, rollout_kernel<9, 28>},   {16, 16, rollout_kernel<16, 16>},
+    {24, 12, rollout_kernel<24, 12>}, {32, 8, rollout_kernel<32, 8>},
+};
+static const RoChoice* pick(int mpad) {
+    const int r_need = mpad / 32;
+    for (const auto& c : kRo)
+        if (c.r >= r_need) return &c;
+    return nullptr;
+}
+
+bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err) {
+    const RoChoice* kc = pick(P.mpad);
+    if (!kc) { *err = cudaSuccess; return false; }
+    *err = cudaFuncSetAttribute((const void*)kc->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    return *err == cudaSuccess;
+}
+
+cudaError_t rollout_launch(const QPDev& P, const LoopDev& L, int wpb, size_t smem, int g_in_smem, int num_sms,
+                           const RolloutArgs& a, cudaStream_t stream) {
+    const RoChoice* kc = pick(P.mpad);
+    int per_cta = (a.B + num_sms - 1) / num_sms;
+    int warps = per_cta < wpb ? per_cta : wpb;
+    if (warps < 1) warps = 1;
+    int blocks = (a.B + warps - 1) / warps;
+    if (blocks > num_sms) blocks = num_sms;
+    const size_t per_warp = (size_t)as_warp_doubles(P) * sizeof(double);
+    const size_t bytes = smem - per_warp * (wpb - warps);
+    kc->fn<<<blocks, warps * 32, bytes, stream>>>(P, L, a, g_in_smem);
+    return cudaGetLastError();
+}
+
+}  // namespace rtmpc

@@ -20,7 +20,7 @@ EXPORTS = [
     "rtmpc_loop_create", "rtmpc_loop_destroy", "rtmpc_loop_reset", "rtmpc_loop_x", "rtmpc_loop_x_nom",
     "rtmpc_loop_x_hat", "rtmpc_loop_q_t", "rtmpc_loop_s_t", "rtmpc_loop_Theta", "rtmpc_loop_alive",
     "rtmpc_loop_err_acc", "rtmpc_loop_tube_max", "rtmpc_loop_u", "rtmpc_loop_gamma", "rtmpc_loop_time",
-    "rtmpc_loop_step",
+    "rtmpc_loop_step", "rtmpc_loop_rollout",
     "rtmpc_actuator_process", "rtmpc_estimator_update", "rtmpc_support_sweep", "rtmpc_support_sweep_host",
 ]
 
@@ -96,6 +96,8 @@ def lib():
     L.rtmpc_loop_time.restype = C.c_int32
     L.rtmpc_loop_step.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, C.c_uint64, C.c_int64, vp,
                                   C.c_int64, vp]
+    L.rtmpc_loop_rollout.argtypes = [vp, vp, C.c_int32, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, C.c_uint64, C.c_int64,
+                                     vp, C.c_int64, vp, vp]
     i32 = C.c_int32
     L.rtmpc_actuator_process.argtypes = [i32] * 6 + [vp] * 18
     L.rtmpc_estimator_update.argtypes = [i32] * 7 + [vp] * 13

@@ -94,6 +94,8 @@ class RemoteLoop:
         pr = getattr(mpc, "_prob_packet_received", None)
         self.warm_recv = None if pr is None else torch.full((B_, pr.warm_stride), -1, device=self.dev, dtype=i32)
         self.status_count = torch.zeros(4, device=self.dev, dtype=torch.int64)
+        # rtmpc_loop_rollout's counters: solves by status [4], IPM iterations, active-set steps, rounds, flops
+        self.stats = torch.zeros(8, device=self.dev, dtype=torch.int64)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -108,6 +110,7 @@ class RemoteLoop:
         _lib.check(self.L.rtmpc_loop_reset(self._h, _lib.ptr(x0)), "rtmpc_loop_reset")
         self.iters_total.zero_()
         self.status_count.zero_()
+        self.stats.zero_()
         self.warm.fill_(-1)
         if self.warm_recv is not None:
             self.warm_recv.fill_(-1)
@@ -144,10 +147,19 @@ class RemoteLoop:
         it = self.iters
         self.iters_total += torch.stack(((it & 0xFFF).sum(), ((it >> 12) & 0xFFF).sum(), ((it >> 24) & 0xFF).sum()))
 
-    def run(self, T, ref, p_loss=None, theta=None, gamma=None, w=None, seed=0, id_offset=0, record=False, stats=True):
+    def run(self, T, ref, p_loss=None, theta=None, gamma=None, w=None, seed=0, id_offset=0, record=False, stats=True,
+            fused=None):
         """T steps.  ``ref`` [nx], [T,nx] or [T,B,nx]; explicit arrays theta/gamma [T,B], w [T,B,nx] (host or
-        device) or p_loss [B].  Returns the trajectory tensor [B,T+1,nx] when ``record``."""
+        device) or p_loss [B].  Returns the trajectory tensor [B,T+1,nx] when ``record``.
+
+        ``fused`` (default: whenever the variant has a single QP) runs all T steps in one persistent launch
+        (``rtmpc_loop_rollout``); otherwise one QP launch + one loop-step launch per control step.  Both
+        give identical results."""
         f64 = torch.float64
+        if fused is None:
+            fused = self.kind != "extended"
+        if fused:
+            return self._run_fused(T, ref, p_loss, theta, gamma, w, seed, id_offset, record)
         ref = np.asarray(ref, float)
         if ref.ndim == 1:
             ref = np.broadcast_to(ref, (T, self.nx))
@@ -168,6 +180,42 @@ class RemoteLoop:
                 self.step(ref_d[k], theta[k], gamma[k], None if w is None else w[k], traj=traj, stats=stats)
             else:
                 self.step(ref_d[k], p_loss=p_loss, seed=seed, id_offset=id_offset, traj=traj, stats=stats)
+        return traj
+
+    def _run_fused(self, T, ref, p_loss, theta, gamma, w, seed, id_offset, record):
+        f64 = torch.float64
+        if self.kind == "extended":
+            raise _lib.RtmpcError("the fused rollout has one QP per step; the extended variant needs fused=False")
+        if torch.is_tensor(ref):
+            ref_d = ref.to(self.dev, f64).contiguous()
+        else:
+            ref_d = torch.as_tensor(np.ascontiguousarray(np.asarray(ref, float)), device=self.dev, dtype=f64)
+        nx, B = self.nx, self.B
+        if ref_d.ndim == 1:
+            st, sb = 0, 0
+        elif ref_d.ndim == 2:
+            st, sb = nx, 0
+        else:
+            st, sb = B * nx, nx
+        traj = torch.zeros(B, T + 1, nx, device=self.dev, dtype=f64) if record else None
+        if theta is not None:
+            theta = torch.as_tensor(np.ascontiguousarray(theta), device=self.dev).to(torch.int32).contiguous()
+            gamma = torch.as_tensor(np.ascontiguousarray(gamma), device=self.dev).to(torch.int32).contiguous()
+            w = None if w is None else torch.as_tensor(np.ascontiguousarray(w), device=self.dev, dtype=f64).contiguous()
+            p_loss = None
+        elif p_loss is not None:
+            if not torch.is_tensor(p_loss):
+                p_loss = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(p_loss, (B,))), device=self.dev, dtype=f64)
+        else:
+            p_loss = torch.zeros(B, device=self.dev, dtype=f64)
+        p = _lib.ptr
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.L.rtmpc_loop_rollout(self._h, self.mpc._prob._h, int(T), p(ref_d), st, sb, p(theta), p(gamma), p(w),
+                                             p(p_loss), int(seed), int(id_offset), p(traj),
+                                             0 if traj is None else (T + 1) * nx, p(self.stats), stream),
+                   "rtmpc_loop_rollout")
+        self.status_count = self.stats[:4].clone()
+        self.iters_total = self.stats[4:7].clone()
         return traj
 
     def tracking_error(self, T):

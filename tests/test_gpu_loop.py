@@ -170,3 +170,38 @@ def test_nonlinear_cartpole_plant_config4_slice():
         assert np.abs(loop.x.cpu().numpy() - x).max() <= 1e-10
     assert loop.status_count[2].item() == 0
     assert np.abs(x[:, 0] - 0.5).max() < 0.45          # all carts moved towards the reference
+
+
+def test_fused_rollout_matches_golden_and_stepwise_bit_for_bit():
+    """rtmpc_loop_rollout (one persistent launch for all T steps) against the oracle's golden closed loops
+    and against the step-by-step path (QP launch + loop-step launch per control step)."""
+    from rtmpc_b200.rollout import RemoteLoop
+    s, g = H.load("sets_di.npz"), H.load("loop_di_tube.npz")
+    mpc = H.make_tube_mpc(s)
+    loop = RemoteLoop(mpc, 1, kind="tube", Z=H.poly(s, "Z"))
+    loop.reset(np.array([[1.0, 2.0]]))
+    tr = loop.run(120, g["refs"], theta=g["theta"][:, None], gamma=g["gamma"][:, None], w=g["w"][:, None], record=True,
+                  fused=True).cpu().numpy()
+    assert np.abs(tr[0] - g["x"]).max() <= TOL
+    assert np.abs(loop.x_hat.cpu().numpy()[0] - g["x_hat"][-1]).max() <= TOL
+    assert loop.tube_max.item() < 1e-7
+    assert loop.status_count[0].item() == 120
+
+    s, g = H.load("sets_cp.npz"), H.load("loop_cp_tube.npz")
+    for kind, mk, key in (("tube", H.make_tube_mpc, "tube"), ("track", H.make_track_mpc, "track")):
+        mpc = mk(s)
+        out = {}
+        for fused in (True, False):
+            loop = RemoteLoop(mpc, 4, kind=kind, Z=H.poly(s, "Z") if kind == "tube" else None)
+            loop.reset(np.zeros((4, 4)))
+            tr = loop.run(250, g["refs"], theta=g["theta"].T, gamma=g["gamma"].T, w=np.transpose(g["w"], (1, 0, 2)),
+                          record=True, fused=fused).cpu().numpy()
+            out[fused] = (tr, loop.x_hat.cpu().numpy(), loop.x_nom.cpu().numpy(), loop.s_t.cpu().numpy(),
+                          loop.q_t.cpu().numpy(), loop.Theta.cpu().numpy(), loop.err_acc.cpu().numpy(),
+                          loop.status_count.cpu().numpy())
+        assert np.abs(out[True][0] - g[key + "_x"]).max() <= TOL
+        assert np.abs(out[True][1] - g[key + "_x_hat"][:, -1]).max() <= TOL
+        for a, b in zip(out[True], out[False]):
+            assert np.array_equal(a, b)
+        if kind == "tube":
+            assert out[True][7][0] == 1000
