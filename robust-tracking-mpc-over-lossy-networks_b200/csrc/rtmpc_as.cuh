@@ -6,25 +6,30 @@
 // instances:  Hinv,  Y = G Hinv,  W = G Hinv G'  and the parameter maps
 //     z_u = Zx x_init + Zr ref  (unconstrained minimiser),   G z_u = Tx x_init + Tr ref.
 // With those, a dual active-set step never touches H or G: for the working set A (signed rows n_a)
-//     multipliers  lam_A = S^-1 (N_A' z_u - b_A),  S = N_A' Hinv N_A = signed sub-matrix of W,
-//     adding the violated row p moves every row value by  -step * (s_p W[:,p] - W[:,A] (s_A r)),  r = S^-1 W[A,p].
-// Per lane: the violations  vu = G z - up,  vl = lo - G z  of its R rows (row = slot*32 + lane) live
-// in registers; per warp: the Cholesky factor of S (appended to on every add, rebuilt on a drop),
-// multipliers and the active list live in shared memory.
+//     multipliers  lam_A = M (N_A' z_u - b_A),  M = (N_A' Hinv N_A)^-1 = inverse of a signed sub-matrix of W,
+//     adding the violated row p moves every row value by  -step * (s_p W[:,p] - W[:,A] (s_A r)),  r = M W[A,p].
+// M is kept explicitly and updated by bordering (row added) / a rank-one downdate (row dropped): a step
+// is one small mat-vec, a few warp reductions and one pass over |A|+1 rows of W.  No factorisation.
 //
-// Per instance (mirrored by tools/as_model.py):
-//   0. parameter rows; z_u; violations at z_u; none -> z_u is optimal.
-//   1. warm start: last control step's certified active set moved one stage earlier (QPDev.shift),
-//      equality solve, drop rows with negative multipliers until the set is dual feasible.
+// Data placement.  Per lane, in registers: value t = (G z)_i and bounds up_i, lo_i of its 2*R2 rows
+// (rows r2*64 + 2*lane + {0,1}: every table is read with 16-byte loads), plus the multiplier and row
+// of working-set slot `lane`.  Per warp, in shared memory: M (npad x npad), z_u, z and three scratch
+// vectors.  Shared by all warps, read through L1: W, G', Y and the parameter tables.
+//
+// Per instance (mirrored by tools/as_model.py::solve_as_inv):
+//   0. parameter rows; z_u; row values at z_u; no row violated -> z_u is optimal.
+//   1. warm start: last control step's certified active set moved one stage earlier (QPDev.shift) is
+//      bordered in row by row (dependent rows skipped), multipliers = M rhs, rows with negative
+//      multipliers are dropped one at a time until the set is dual feasible.
 //   2. Goldfarb-Idnani: add the most violated row with primal/dual ratio test (partial steps drop
 //      the blocking row) until no row is violated by more than 1e-11 (scaled).  Strictly increasing
 //      dual objective: no cycling.  Linear dependence without a blocking row = primal infeasible.
-//   3. certification: fresh multiplier solve with two steps of iterative refinement against the
-//      true rows of G, z = z_u - Y_A' (s lam), every row and multiplier re-checked (KKT certificate,
-//      same tolerances as the interior-point kernel's endgame).  A violated row found here sends
-//      the instance back to 2 with exact row values.
-// Anything unexpected (step cap, lost rank, negative multiplier at certification) returns
-// RTMPC_FALLBACK; the C ABI then runs the interior-point kernel on those instances only.
+//   3. certification: multipliers refined against the true rows of G with M as approximate inverse
+//      (three passes), z = z_u - Y_A' (s lam), every row recomputed from G' z and re-checked, every
+//      multiplier re-checked (KKT certificate, same tolerances as the interior-point kernel's
+//      endgame).  A violated row found here sends the instance back to 2 with exact row values.
+// Anything unexpected (step cap, refinement not converging, negative multiplier at certification)
+// returns RTMPC_FALLBACK; the C ABI then runs the interior-point kernel on those instances only.
 #pragma once
 #include "rtmpc_ipm.cuh"
 
@@ -32,316 +37,390 @@ namespace rtmpc {
 
 constexpr int RTMPC_FALLBACK = RTMPC_FALLBACK_STATUS;
 
-// per-warp shared memory, in doubles: S, zu, z, coef, lam, 16 parameters, act lists (2*npad ints)
+// per-warp shared memory, in doubles: M, zu, z, v, coef, rvec, 16 parameters, slot lists (2*npad ints)
+__host__ __device__ inline int as_ms(const QPDev& P) { return P.npad + 2; }
 __host__ __device__ inline int as_warp_doubles(const QPDev& P) {
-    return P.npad * P.ss + 4 * P.npad + 16 + P.npad;
-}
-__host__ __device__ inline int as_block_doubles(const QPDev& P, bool g_in_smem) {
-    return g_in_smem ? P.mpad * P.gs : 0;
+    return P.npad * as_ms(P) + 5 * P.npad + 16 + P.npad;
 }
 
+// (offsets are added to one base pointer where they are used: nine live pointers would not stay in registers)
 struct ASWarp {
-    double *S, *zu, *z, *coef, *lam, *xr;
-    int *act_row, *act_sgn;
+    double* base;
+    int npad, mm;     // mm = npad * ms
+    __device__ __forceinline__ double* M() const { return base; }
+    __device__ __forceinline__ double* zu() const { return base + mm; }
+    __device__ __forceinline__ double* z() const { return base + mm + npad; }
+    __device__ __forceinline__ double* v() const { return base + mm + 2 * npad; }
+    __device__ __forceinline__ double* coef() const { return base + mm + 3 * npad; }
+    __device__ __forceinline__ double* rv() const { return base + mm + 4 * npad; }
+    __device__ __forceinline__ double* xr() const { return base + mm + 5 * npad; }
+    __device__ __forceinline__ int* act_row() const { return reinterpret_cast<int*>(base + mm + 5 * npad + 16); }
+    __device__ __forceinline__ int* act_sgn() const { return act_row() + npad; }
 };
 
 __device__ __forceinline__ ASWarp as_carve(double* base, const QPDev& P) {
     ASWarp w;
-    w.S = base; base += P.npad * P.ss;
-    w.zu = base; base += P.npad;
-    w.z = base; base += P.npad;
-    w.coef = base; base += P.npad;
-    w.lam = base; base += P.npad;
-    w.xr = base; base += 16;
-    w.act_row = reinterpret_cast<int*>(base);
-    w.act_sgn = w.act_row + P.npad;
+    w.base = base; w.npad = P.npad; w.mm = P.npad * as_ms(P);
     return w;
 }
 
-// forward substitution L y = r (inverse diagonal stored); lane k holds r_k / y_k
-__device__ __forceinline__ double tri_fwd(const double* __restrict__ S, int ss, int na, int lane, double r) {
-    for (int k = 0; k < na; ++k) {
-        const double yk = __shfl_sync(RTMPC_FULL_MASK, r, k) * S[k * ss + k];
-        if (lane == k) r = yk;
-        else if (lane > k && lane < na) r = fma(-S[lane * ss + k], yk, r);
-    }
-    return (lane < na) ? r : 0.0;
-}
-// backward substitution L' x = y
-__device__ __forceinline__ double tri_bwd(const double* __restrict__ S, int ss, int na, int lane, double r) {
-    for (int k = na - 1; k >= 0; --k) {
-        const double xk = __shfl_sync(RTMPC_FULL_MASK, r, k) * S[k * ss + k];
-        if (lane == k) r = xk;
-        else if (lane < k) r = fma(-S[k * ss + lane], xk, r);
-    }
-    return (lane < na) ? r : 0.0;
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// steps: rows added + dropped; rounds: certifications; rows: rows of W streamed; sq: sum of na^2 over the
+// small dense operations (mat-vec, bordering, downdate).  Algorithmic flops are derived from these.
+struct ASCounters { int steps, rounds, rows, sq; };
+
+__device__ __forceinline__ unsigned long long as_flops(const QPDev& P, const ASCounters& c, bool with_z) {
+    const unsigned long long n = P.n, m = P.m, nx = P.nx;
+    unsigned long long f = 2ull * n * 2 * nx + 2ull * m * 4 * nx;                 // z_u, row values and bounds
+    f += 2ull * m * (unsigned long long)c.rows + 2ull * (unsigned long long)c.sq; // steps
+    f += (unsigned long long)c.rounds * (2ull * m * n + 12ull * n * n);            // certification: G z + refinement
+    f += 2ull * (with_z ? (unsigned long long)P.nz : (unsigned long long)((P.N + 1) * P.nu)) * (n + nx);
+    return f;
 }
 
-// S = signed sub-matrix of W on the active list (lower triangle), then its Cholesky factor with
-// dependent rows neutralised.  Returns the mask of independent rows.
-__device__ __forceinline__ unsigned as_factor(const QPDev& P, ASWarp& w, int na, int lane) {
-    const int ss = P.ss;
-    double* S = w.S;
-    const bool mine = lane < na;
-    if (mine) {
-        const int ra = w.act_row[lane];
-        const double sa = (double)w.act_sgn[lane];
-        const double* Wa = P.W + (size_t)ra * P.mpad;
-        for (int b = 0; b <= lane; ++b) S[lane * ss + b] = Wa[w.act_row[b]] * sa * (double)w.act_sgn[b];
-    }
-    __syncwarp();
-    const double sdiag = mine ? S[lane * ss + lane] : 0.0;
-    const double dmax = warp_max(sdiag);
-    unsigned keep = 0;
-    for (int k = 0; k < na; ++k) {
-        double s = 0.0;
-        if (lane >= k && mine) {
-            s = S[lane * ss + k];
-            double s2 = 0.0;
-            int j = 0;
-            for (; j + 1 < k; j += 2) {
-                s = fma(-S[lane * ss + j], S[k * ss + j], s);
-                s2 = fma(-S[lane * ss + j + 1], S[k * ss + j + 1], s2);
-            }
-            if (j < k) s = fma(-S[lane * ss + j], S[k * ss + j], s);
-            s += s2;
+// Warp reductions.  Maxima / arg-maxima go through the integer reduction unit (REDUX) on an
+// order-preserving 64-bit key, two 32-bit halves: a handful of instructions instead of five shuffle stages.
+__device__ __forceinline__ unsigned long long as_key(double v) {
+    const long long b = __double_as_longlong(v);
+    return (b < 0) ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double as_unkey(unsigned long long k) {
+    return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+__device__ __forceinline__ double as_wmax(double v) {
+    const unsigned long long k = as_key(v);
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_max_sync(RTMPC_FULL_MASK, hi);
+    const unsigned ml = __reduce_max_sync(RTMPC_FULL_MASK, hi == mh ? lo : 0u);
+    return as_unkey(((unsigned long long)mh << 32) | ml);
+}
+__device__ __forceinline__ double as_wmin(double v) { return -as_wmax(-v); }
+// lane holding the maximum (lowest lane among equals)
+__device__ __forceinline__ int as_lane_max(double v) {
+    const unsigned long long k = as_key(v);
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_max_sync(RTMPC_FULL_MASK, hi);
+    const unsigned ml = __reduce_max_sync(RTMPC_FULL_MASK, hi == mh ? lo : 0u);
+    return __ffs(__ballot_sync(RTMPC_FULL_MASK, hi == mh && lo == ml)) - 1;
+}
+struct ASArg { double v; int idx; };
+__device__ __forceinline__ ASArg as_wargmax(double v, int idx) {
+    const int src = as_lane_max(v);
+    ASArg r;
+    r.v = __shfl_sync(RTMPC_FULL_MASK, v, src);
+    r.idx = __shfl_sync(RTMPC_FULL_MASK, idx, src);
+    return r;
+}
+__device__ __forceinline__ ASArg as_wargmin(double v, int idx) {
+    const int src = as_lane_max(-v);
+    ASArg r;
+    r.v = __shfl_sync(RTMPC_FULL_MASK, v, src);
+    r.idx = __shfl_sync(RTMPC_FULL_MASK, idx, src);
+    return r;
+}
+__device__ __forceinline__ double as_wsum(double v) { return warp_sum(v); }
+
+// slot state of one lane: working-set slot `lane` holds signed row (ra, sa) with multiplier lam
+struct ASSlot { int ra; double sa, lam; };
+
+// out_a = sum_b M[a][b] vec[b] over the slots below hi (free slots hold zeros)
+static __device__ __noinline__ double as_matvec(const double* __restrict__ M, int ms, int hi, int lane, int npad,
+                                         const double* __restrict__ vec) {
+    double s0 = 0.0, s1 = 0.0;
+    if (lane < npad) {
+        const double* row = M + lane * ms;
+#pragma unroll 2
+        for (int b = 0; b < hi; b += 2) {
+            const double2 mm = ld2(row + b), vv = ld2(vec + b);
+            s0 = fma(mm.x, vv.x, s0);
+            s1 = fma(mm.y, vv.y, s1);
         }
-        const double pk = __shfl_sync(RTMPC_FULL_MASK, s, k);
-        const double skk = __shfl_sync(RTMPC_FULL_MASK, sdiag, k);
-        const bool good = (pk > 1e-11 * skk) && (pk > 1e-14 * dmax);
-        if (good) {
-            keep |= (1u << k);
-            const double idk = __drcp_rn(sqrt(pk));
-            if (lane >= k && mine) S[lane * ss + k] = (lane == k) ? idk : s * idk;
+    }
+    return s0 + s1;
+}
+
+// M grows by slot s:  [[M + r r'/kappa, -r/kappa], [-r'/kappa, 1/kappa]]   (r in rv, zero on free slots;
+// hi = even number of slots covering every occupied one and s)
+static __device__ __noinline__ void as_border(double* __restrict__ M, const double* __restrict__ rv, int ms, int hi, int lane,
+                                       int s, double r_own, double kappa) {
+    const double ik = __drcp_rn(kappa);
+    if (lane < hi) {
+        double* row = M + lane * ms;
+        if (lane == s) {
+#pragma unroll 1
+            for (int b = 0; b < hi; b += 2) {
+                const double2 rr = ld2(rv + b);
+                row[b] = -rr.x * ik;
+                row[b + 1] = -rr.y * ik;
+            }
+            row[s] = ik;
         } else {
-            if (lane >= k && mine) S[lane * ss + k] = (lane == k) ? 1.0 : 0.0;
-            if (lane == k) for (int j = 0; j < k; ++j) S[k * ss + j] = 0.0;
+            const double c = r_own * ik;
+            if (c != 0.0) {
+#pragma unroll 1
+                for (int b = 0; b < hi; b += 2) {
+                    const double2 rr = ld2(rv + b);
+                    double2 mm = ld2(row + b);
+                    mm.x = fma(c, rr.x, mm.x);
+                    mm.y = fma(c, rr.y, mm.y);
+                    *reinterpret_cast<double2*>(row + b) = mm;
+                }
+            }
+            row[s] = -c;
         }
-        __syncwarp();
     }
-    return keep;
-}
-
-// bound of the signed row (row, sgn) for this instance:  sgn > 0: up,  sgn < 0: -lo
-__device__ __forceinline__ double as_bound(const QPDev& P, const double* __restrict__ xr, int row, int sgn) {
-    const int nx = P.nx;
-    if (sgn > 0) {
-        double up = P.up0[row];
-        for (int k = 0; k < nx; ++k) up = fma(P.Ux[row * nx + k], xr[k], up);
-        return up;
-    }
-    double lo = P.lo0[row];
-    for (int k = 0; k < nx; ++k) lo = fma(P.Lx[row * nx + k], xr[k], lo);
-    return -lo;
-}
-
-// remove the entries flagged in `bad` from the active list (and lam), keeping the order
-__device__ __forceinline__ int as_compact(ASWarp& w, int na, int lane, bool bad, double lamv) {
-    const bool mine = lane < na;
-    const unsigned good = __ballot_sync(RTMPC_FULL_MASK, mine && !bad);
-    const int pos = __popc(good & ((1u << lane) - 1u));
-    const int rr = mine ? w.act_row[lane] : 0, sg = mine ? w.act_sgn[lane] : 0;
     __syncwarp();
-    if (mine && !bad) { w.act_row[pos] = rr; w.act_sgn[pos] = sg; w.lam[pos] = lamv; }
-    __syncwarp();
-    return __popc(good);
 }
 
-struct ASCounters { int steps, rounds; unsigned long long flops; };
-
-// violations of every row move by  -sum_a coef_a W[row_a][row]  (coef in w.coef[0..na))
-template <int R>
-__device__ __forceinline__ void as_apply_rows(const QPDev& P, const ASWarp& w, int na, int lane, int nslots,
-                                              double (&vu)[R], double (&vl)[R]) {
-    for (int a = 0; a < na; ++a) {
-        const double c = w.coef[a];
-        const double* __restrict__ Wa = P.W + (size_t)w.act_row[a] * P.mpad + lane;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r < nslots) {
-                const double g = Wa[r * 32];
-                vu[r] = fma(-c, g, vu[r]);
-                vl[r] = fma(c, g, vl[r]);
+// slot j leaves:  M <- M - m_j m_j' / M_jj, row and column j cleared (tmp: npad doubles of scratch)
+static __device__ __noinline__ void as_downdate(double* __restrict__ M, double* __restrict__ tmp, int ms, int hi, int lane, int j) {
+    if (lane < hi) tmp[lane] = M[j * ms + lane];
+    __syncwarp();
+    const double ij = __drcp_rn(tmp[j]);
+    if (lane < hi) {
+        double* row = M + lane * ms;
+        const double c = (lane == j) ? -1.0 : -row[j] * ij;      // row j: m_j - m_j = 0
+        if (c != 0.0) {
+#pragma unroll 1
+            for (int b = 0; b < hi; b += 2) {
+                const double2 vv = ld2(tmp + b);
+                double2 mm = ld2(row + b);
+                mm.x = (lane == j) ? 0.0 : fma(c, vv.x, mm.x);
+                mm.y = (lane == j) ? 0.0 : fma(c, vv.y, mm.y);
+                *reinterpret_cast<double2*>(row + b) = mm;
             }
         }
+        row[j] = 0.0;
+    }
+    __syncwarp();
+}
+
+// flag / unflag row `row` as a member of the working set in its owner lane's bit masks
+__device__ __forceinline__ void as_mark(int lane, int row, int sgn, bool on, unsigned& actu, unsigned& actl) {
+    if (lane == ((row & 63) >> 1)) {
+        const unsigned bit = 1u << (((row >> 6) << 1) | (row & 1));
+        if (sgn > 0) actu = on ? (actu | bit) : (actu & ~bit);
+        else actl = on ? (actl | bit) : (actl & ~bit);
     }
 }
 
-// Goldfarb-Idnani iteration.  Returns 0 when no row is violated by more than tolp.
-template <int R>
-__device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, int& na, int lane, int nslots, double (&vu)[R],
-                                     double (&vl)[R], unsigned& actu, unsigned& actl, double tolp, int max_steps,
+__device__ __forceinline__ int as_hi(unsigned amask) { return (33 - __clz(amask | 1u)) & ~1; }   // even, covers amask
+
+// Goldfarb-Idnani iteration.  `apply_only`: the warm start left its multipliers in w.coef(); the first pass
+// only moves the row values (the row streaming code exists once).  Returns 0 when no row is violated by
+// more than tolp.
+template <int R2>
+__device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask, ASSlot& sl, int lane,
+                                     double (&t)[2 * R2], const double (&up)[2 * R2], const double (&lo)[2 * R2],
+                                     unsigned& actu, unsigned& actl, double tolp, int max_steps, bool apply_only,
                                      ASCounters& cnt) {
-    const int ss = P.ss, n = P.n, mpad = P.mpad;
-    double* S = w.S;
+    const int npad = P.npad, n = P.n, mpad = P.mpad, ms = as_ms(P);
+    const unsigned slots = (npad >= 32) ? 0xffffffffu : ((1u << npad) - 1u);
     while (true) {
-        double best = -RTMPC_INF;
-        int code = 0;
+        int p = 0;
+        double sp = 1.0, cp = 0.0, lam_p = 0.0, wpp = 1.0;
+        if (!apply_only) {
+            double best = -RTMPC_INF;
+            int code = 0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r < nslots) {
-                const int row = r * 32 + lane;
-                if (!((actu >> r) & 1u) && vu[r] > best) { best = vu[r]; code = 2 * row; }
-                if (!((actl >> r) & 1u) && vl[r] > best) { best = vl[r]; code = 2 * row + 1; }
+            for (int i = 0; i < 2 * R2; ++i) {
+                const int row = ((i >> 1) << 6) + 2 * lane + (i & 1);
+                const double vu = t[i] - up[i], vl = lo[i] - t[i];
+                if (!((actu >> i) & 1u) && vu > best) { best = vu; code = 2 * row; }
+                if (!((actl >> i) & 1u) && vl > best) { best = vl; code = 2 * row + 1; }
             }
+            const ASArg bm = as_wargmax(best, code);
+            if (bm.v <= tolp) return 0;
+            p = bm.idx >> 1;
+            sp = (bm.idx & 1) ? -1.0 : 1.0;
+            cp = bm.v;
+            wpp = P.W[(size_t)p * mpad + p];
         }
-        best = warp_argmax(best, code);
-        if (best <= tolp) return 0;
-        const int p = code >> 1;
-        const double sp = (code & 1) ? -1.0 : 1.0;
         const double* __restrict__ Wp = P.W + (size_t)p * mpad;
-        const double wpp = Wp[p];
-        double cp = best, lam_p = 0.0;
         while (true) {
-            if (cnt.steps >= max_steps) return RTMPC_FALLBACK;
-            cnt.steps += 1;
-            const bool mine = lane < na;
-            const int ra = mine ? w.act_row[lane] : 0;
-            const double sa = mine ? (double)w.act_sgn[lane] : 0.0;
-            const double v = mine ? sa * sp * Wp[ra] : 0.0;
-            const double l = tri_fwd(S, ss, na, lane, v);
-            const double kappa = wpp - warp_sum(l * l);
-            const double rr = tri_bwd(S, ss, na, lane, l);
-            const bool dependent = !(kappa > 1e-11 * wpp);
-            const double lam_a = mine ? w.lam[lane] : 0.0;
-            const double rmax = warp_max(fabs(rr));
-            double ratio = (mine && rr > 1e-13 * (1.0 + rmax)) ? lam_a / rr : RTMPC_INF;
-            int j1 = lane;
-            const double t1 = warp_argmin(ratio, j1);
-            const bool has_j = t1 < 0.5 * RTMPC_INF;
-            double step;
-            bool full;
-            if (dependent) {
-                // n_p is a combination of the active rows: without a blocking multiplier the
-                // constraints contradict each other (Farkas: y = (-r, 1) >= 0, N y = 0, b'y = -c_p < 0)
-                if (!has_j) return (cp > 1e-6 * P.sc_b) ? RTMPC_INFEASIBLE : RTMPC_FALLBACK;
-                step = t1;
-                full = false;
-            } else {
-                const double t2 = cp / kappa;
-                full = !(has_j && t1 < t2);
-                step = full ? t2 : t1;
-            }
-            if (mine) w.lam[lane] = (!full && lane == j1) ? 0.0 : fma(-step, rr, lam_a);
-            lam_p += step;
-            cnt.flops += 4ull * na * na + 2ull * na;
-            if (!dependent) {
-                if (lane < P.npad) w.coef[lane] = mine ? -step * sa * rr : 0.0;
+            const bool occ = (amask >> lane) & 1u;
+            const int na = __popc(amask);
+            const int hi = as_hi(amask);
+            double c = 0.0, rr = 0.0, kappa = 1.0, step = 0.0;
+            bool full = false, dependent = false;
+            int j1 = 0;
+            if (!apply_only) {
+                if (cnt.steps >= max_steps) return RTMPC_FALLBACK;
+                cnt.steps += 1;
+                const double v = occ ? sl.sa * sp * Wp[sl.ra] : 0.0;
+                if (lane < npad) w.v()[lane] = v;
                 __syncwarp();
-                const double c = step * sp;
+                rr = occ ? as_matvec(w.M(), ms, hi, lane, npad, w.v()) : 0.0;
+                kappa = wpp - as_wsum(v * rr);
+                dependent = !(kappa > 1e-11 * wpp);
+                const double rmax = as_wmax(fabs(rr));
+                const double ratio = (occ && rr > 1e-13 * (1.0 + rmax)) ? sl.lam * __drcp_rn(rr) : RTMPC_INF;
+                const ASArg rm = as_wargmin(ratio, lane);
+                const double t1 = rm.v;
+                j1 = rm.idx;
+                const bool has_j = t1 < 0.5 * RTMPC_INF;
+                if (dependent) {
+                    // n_p is a combination of the active rows: without a blocking multiplier the
+                    // constraints contradict each other (Farkas: y = (-r, 1) >= 0, N y = 0, b'y = -c_p < 0)
+                    if (!has_j) return (cp > 1e-6 * P.sc_b) ? RTMPC_INFEASIBLE : RTMPC_FALLBACK;
+                    step = t1;
+                } else {
+                    const double t2 = cp * __drcp_rn(kappa);
+                    full = !(has_j && t1 < t2);
+                    step = full ? t2 : t1;
+                }
+                if (occ) sl.lam = (!full && lane == j1) ? 0.0 : fma(-step, rr, sl.lam);
+                lam_p += step;
+                cnt.sq += na * na;
+                if (lane < npad) w.coef()[lane] = occ ? step * sl.sa * rr : 0.0;
+                __syncwarp();
+                c = -step * sp;
+            }
+            if (!dependent) {
+                // row values move by  c W[p][:] + sum_a coef_a W[row_a][:]
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (r < nslots) {
-                        const double g = Wp[r * 32 + lane];
-                        vu[r] = fma(-c, g, vu[r]);
-                        vl[r] = fma(c, g, vl[r]);
+                for (int r2 = 0; r2 < R2; ++r2) {
+                    const double2 g = ld2(Wp + r2 * 64 + 2 * lane);
+                    t[2 * r2] = fma(c, g.x, t[2 * r2]);
+                    t[2 * r2 + 1] = fma(c, g.y, t[2 * r2 + 1]);
+                }
+#pragma unroll 1
+                for (unsigned mk = amask; mk;) {
+                    // two rows per pass: twice the loads in flight
+                    const int a = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    const int a2 = mk ? __ffs(mk) - 1 : a;
+                    const double ca = w.coef()[a], cb = mk ? w.coef()[a2] : 0.0;
+                    mk &= mk - 1;
+                    const double* __restrict__ Wa = P.W + (size_t)w.act_row()[a] * mpad + 2 * lane;
+                    const double* __restrict__ Wb = P.W + (size_t)w.act_row()[a2] * mpad + 2 * lane;
+#pragma unroll
+                    for (int r2 = 0; r2 < R2; ++r2) {
+                        const double2 g = ld2(Wa + r2 * 64), h = ld2(Wb + r2 * 64);
+                        t[2 * r2] = fma(cb, h.x, fma(ca, g.x, t[2 * r2]));
+                        t[2 * r2 + 1] = fma(cb, h.y, fma(ca, g.y, t[2 * r2 + 1]));
                     }
                 }
-                as_apply_rows<R>(P, w, na, lane, nslots, vu, vl);
                 cp = fma(-step, kappa, cp);
-                cnt.flops += 2ull * P.m * (na + 1);
-                __syncwarp();
+                cnt.rows += na + 1;
             }
+            if (apply_only) { apply_only = false; break; }
             if (full) {
-                if (na >= n) return RTMPC_FALLBACK;
-                // the factor grows by one row: [l', sqrt(kappa)]
-                if (mine) S[na * ss + lane] = l;
-                if (lane == 0) {
-                    S[na * ss + na] = __drcp_rn(sqrt(kappa));
-                    w.act_row[na] = p;
-                    w.act_sgn[na] = (int)sp;
-                    w.lam[na] = lam_p;
-                }
-                if (lane == (p & 31)) {
-                    if (sp > 0) actu |= 1u << (p >> 5); else actl |= 1u << (p >> 5);
-                }
-                na += 1;
+                const unsigned freem = ~amask & slots;
+                if (na >= n || !freem) return RTMPC_FALLBACK;
+                const int s = __ffs(freem) - 1;
+                if (lane < npad) w.rv()[lane] = rr;
+                __syncwarp();
+                as_border(w.M(), w.rv(), ms, as_hi(amask | (1u << s)), lane, s, rr, kappa);
+                if (lane == s) { sl.ra = p; sl.sa = sp; sl.lam = lam_p; w.act_row()[s] = p; w.act_sgn()[s] = (int)sp; }
+                as_mark(lane, p, (int)sp, true, actu, actl);
+                amask |= 1u << s;
+                cnt.sq += na * na;
                 __syncwarp();
                 break;
             }
             // partial step: the blocking row leaves the working set
-            {
-                const int rowj = w.act_row[j1], sgj = w.act_sgn[j1];
-                if (lane == (rowj & 31)) {
-                    if (sgj > 0) actu &= ~(1u << (rowj >> 5)); else actl &= ~(1u << (rowj >> 5));
-                }
-                const double lamv = mine ? w.lam[lane] : 0.0;
-                na = as_compact(w, na, lane, lane == j1, lamv);
-                const unsigned keep = as_factor(P, w, na, lane);
-                cnt.flops += (unsigned long long)na * na * na / 3;
-                if (keep != ((na >= 32) ? 0xffffffffu : ((1u << na) - 1u))) return RTMPC_FALLBACK;
-            }
+            as_mark(lane, w.act_row()[j1], w.act_sgn()[j1], false, actu, actl);
+            as_downdate(w.M(), w.v(), ms, hi, lane, j1);
+            amask &= ~(1u << j1);
+            cnt.sq += na * na;
         }
     }
 }
 
-// Certification on the working set: refined multipliers, z, exact row values.  Returns 0 when the
-// KKT conditions hold, 1 when a row is still violated (vu/vl hold exact values: go back to as_gi),
-// 2 on a negative multiplier.
-template <int R>
-__device__ __forceinline__ int as_certify(const QPDev& P, const double* __restrict__ Gs, ASWarp& w, int na, int lane,
-                                          int nslots, double (&vu)[R], double (&vl)[R], unsigned actu, unsigned actl,
-                                          double tolp, ASCounters& cnt) {
-    const int n = P.n, npad = P.npad, gs = P.gs, ss = P.ss, nx = P.nx;
-    const bool mine = lane < na;
-    const int ra = mine ? w.act_row[lane] : 0;
-    const int sgi = mine ? w.act_sgn[lane] : 1;
-    const double sa = mine ? (double)sgi : 0.0;
-    const double ba = mine ? as_bound(P, w.xr, ra, sgi) : 0.0;
-    const double* __restrict__ Ga = Gs + (size_t)ra * gs;
-    double resid = 0.0;
-    if (mine) {
-        double acc = 0.0;
-        for (int k = 0; k < n; ++k) acc = fma(Ga[k], w.zu[k], acc);
-        resid = sa * acc - ba;
+// Certification on the working set.  Returns 0 when the KKT conditions hold, 1 when a row is still
+// violated (t holds exact values: go back to as_gi), 2 on a negative multiplier / no convergence.
+template <int R2>
+__device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned amask, ASSlot& sl, int lane,
+                                          double (&t)[2 * R2], const double (&up)[2 * R2], const double (&lo)[2 * R2],
+                                          unsigned actu, unsigned actl, double tolp, ASCounters& cnt) {
+    const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ms = as_ms(P);
+    const bool occ = (amask >> lane) & 1u;
+    const int hi = as_hi(amask);
+    double ba = 0.0;
+    if (occ) {
+        // bound of the signed row:  s > 0: up,  s < 0: -lo
+        const double* tab = (sl.sa > 0) ? P.UxT : P.LxT;
+        double b = (sl.sa > 0) ? P.upI[sl.ra] : P.loI[sl.ra];
+#pragma unroll 1
+        for (int k = 0; k < nx; ++k) b = fma(tab[(size_t)k * mpad + sl.ra], w.xr()[k], b);
+        ba = (sl.sa > 0) ? b : -b;
     }
-    double lam = 0.0;
-    double zj = (lane < n) ? w.zu[lane] : 0.0;
-    for (int pass = 0; pass < 3; ++pass) {
-        const double dl = tri_bwd(w.S, ss, na, lane, tri_fwd(w.S, ss, na, lane, resid));
-        lam += dl;
-        if (lane < npad) w.coef[lane] = dl * sa;
-        __syncwarp();
-        if (lane < n) {
-            for (int a = 0; a < na; ++a) zj = fma(-w.coef[a], P.Y[(size_t)w.act_row[a] * npad + lane], zj);
-        }
-        if (lane < npad) w.z[lane] = zj;
-        __syncwarp();
-        if (pass < 2) {
-            resid = 0.0;
-            if (mine) {
-                double acc = 0.0;
-                for (int k = 0; k < n; ++k) acc = fma(Ga[k], w.z[k], acc);
-                resid = sa * acc - ba;
+    const double* __restrict__ Ga = P.G + (size_t)(occ ? sl.ra : 0) * npad;
+    double lam = 0.0, resid = 0.0;
+    double zj = (lane < n) ? w.zu()[lane] : 0.0;
+    if (lane < npad) w.z()[lane] = zj;
+    __syncwarp();
+    // pass 0 evaluates the residual at z_u, passes 1..3 refine
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+        if (pass > 0) {
+            if (lane < npad) w.v()[lane] = resid;
+            __syncwarp();
+            const double dl = occ ? as_matvec(w.M(), ms, hi, lane, npad, w.v()) : 0.0;
+            lam += dl;
+            if (lane < npad) w.coef()[lane] = dl * sl.sa;
+            __syncwarp();
+            if (lane < n) {
+                double z2 = 0.0;
+#pragma unroll 1
+                for (unsigned mk = amask; mk;) {
+                    const int a = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    const int a2 = mk ? __ffs(mk) - 1 : a;
+                    const double cb = mk ? w.coef()[a2] : 0.0;
+                    mk &= mk - 1;
+                    zj = fma(-w.coef()[a], P.Y[(size_t)w.act_row()[a] * npad + lane], zj);
+                    z2 = fma(-cb, P.Y[(size_t)w.act_row()[a2] * npad + lane], z2);
+                }
+                zj += z2;
             }
+            if (lane < npad) w.z()[lane] = zj;
+            __syncwarp();
+        }
+        resid = 0.0;
+        if (occ) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll 2
+            for (int k = 0; k < npad; k += 2) {
+                const double2 g = ld2(Ga + k), zz = ld2(w.z() + k);
+                a0 = fma(g.x, zz.x, a0);
+                a1 = fma(g.y, zz.y, a1);
+            }
+            resid = sl.sa * (a0 + a1) - ba;
         }
     }
-    cnt.flops += 3ull * (4ull * na * na + 4ull * na * n) + 2ull * P.m * n;
     cnt.rounds += 1;
-    // exact row values at z
-    double t[R];
-    gemv_rows<R>(Gs, gs, npad, nslots, w.z, lane, t);
+    // exact row values at z:  t = G z through the transposed copy (coalesced 16-byte loads)
+#pragma unroll
+    for (int i = 0; i < 2 * R2; ++i) t[i] = 0.0;
+    // (z is zero beyond n, G' is zero-padded: three columns per pass keep 3*R2 loads in flight)
+#pragma unroll 1
+    for (int k = 0; k < npad; k += 3) {
+        const int k1 = (k + 1 < npad) ? k + 1 : k, k2 = (k + 2 < npad) ? k + 2 : k;
+        const double z0 = w.z()[k], z1 = (k + 1 < npad) ? w.z()[k1] : 0.0, z2 = (k + 2 < npad) ? w.z()[k2] : 0.0;
+        const double* __restrict__ g0 = P.GT + (size_t)k * mpad + 2 * lane;
+        const double* __restrict__ g1 = P.GT + (size_t)k1 * mpad + 2 * lane;
+        const double* __restrict__ g2 = P.GT + (size_t)k2 * mpad + 2 * lane;
+#pragma unroll
+        for (int r2 = 0; r2 < R2; ++r2) {
+            const double2 a = ld2(g0 + r2 * 64), b = ld2(g1 + r2 * 64), c = ld2(g2 + r2 * 64);
+            t[2 * r2] = fma(c.x, z2, fma(b.x, z1, fma(a.x, z0, t[2 * r2])));
+            t[2 * r2 + 1] = fma(c.y, z2, fma(b.y, z1, fma(a.y, z0, t[2 * r2 + 1])));
+        }
+    }
     double worst = -RTMPC_INF;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (r < nslots) {
-            const int row = r * 32 + lane;
-            double lo = P.lo0[row], up = P.up0[row];
-            for (int k = 0; k < nx; ++k) {
-                lo = fma(P.Lx[row * nx + k], w.xr[k], lo);
-                up = fma(P.Ux[row * nx + k], w.xr[k], up);
-            }
-            vu[r] = P.has_up[row] ? t[r] - up : -RTMPC_INF;
-            vl[r] = P.has_lo[row] ? lo - t[r] : -RTMPC_INF;
-            if (!((actu >> r) & 1u)) worst = fmax(worst, vu[r]);
-            if (!((actl >> r) & 1u)) worst = fmax(worst, vl[r]);
-        }
+    for (int i = 0; i < 2 * R2; ++i) {
+        if (!((actu >> i) & 1u)) worst = fmax(worst, t[i] - up[i]);
+        if (!((actl >> i) & 1u)) worst = fmax(worst, lo[i] - t[i]);
     }
-    worst = warp_max(worst);
-    const double lmin = warp_min(mine ? lam : RTMPC_INF);
-    const double lmaxabs = warp_max(mine ? fabs(lam) : 0.0);
-    if (mine) w.lam[lane] = fmax(lam, 0.0);
-    __syncwarp();
+    worst = as_wmax(worst);
+    const double lmin = as_wmin(occ ? lam : RTMPC_INF), lmaxabs = as_wmax(occ ? fabs(lam) : 0.0);
+    const double rmax = as_wmax(fabs(resid));
+    if (occ) sl.lam = fmax(lam, 0.0);
+    if (rmax > tolp) return 2;                                   // refinement did not converge
     if (lmin < -1e-9 * (1.0 + lmaxabs)) return 2;
     return (worst > tolp) ? 1 : 0;
 }
@@ -349,127 +428,173 @@ __device__ __forceinline__ int as_certify(const QPDev& P, const double* __restri
 // One instance, one warp.  x_init / ref: this instance's parameters (ref may be NULL); warm_inst: this
 // instance's warm-start record (npad + 1 ints) or NULL; z_out_inst / U_out_inst: this instance's
 // outputs or NULL.  Returns the status; on RTMPC_FALLBACK nothing has been written.
-template <int R>
-__device__ __forceinline__ int as_solve_instance(const QPDev& P, const double* __restrict__ Gs, ASWarp& w, int lane,
-                                                 const double* x_init, const double* ref, int* warm_inst,
-                                                 double* z_out_inst, double* U_out_inst, ASCounters& cnt) {
-    const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ss = P.ss;
-    const int nslots = mpad >> 5;
+// (no __restrict__ on the instance pointers: the rollout kernel writes them from the same warp)
+template <int R2>
+__device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int lane, const double* x_init,
+                                                 const double* ref, int* warm_inst, double* z_out_inst,
+                                                 double* U_out_inst, ASCounters& cnt) {
+    const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ms = as_ms(P);
     const double tolp = 1e-11 * P.sc_b;
     if (lane < nx) {
-        w.xr[lane] = x_init[lane];
-        w.xr[8 + lane] = ref ? ref[lane] : 0.0;
+        w.xr()[lane] = x_init[lane];
+        w.xr()[8 + lane] = ref ? ref[lane] : 0.0;
     }
     __syncwarp();
     bool par_bad = false;
+#pragma unroll 1
     for (int i = lane; i < P.np; i += 32) {
         double acc = -P.parh[i];
-        for (int k = 0; k < nx; ++k) acc = fma(P.parC[i * nx + k], w.xr[k], acc);
+#pragma unroll 1
+        for (int k = 0; k < nx; ++k) acc = fma(P.parC[i * nx + k], w.xr()[k], acc);
         if (acc > 1e-9 * (1.0 + fabs(P.parh[i]))) par_bad = true;
     }
     par_bad = __any_sync(RTMPC_FULL_MASK, par_bad);
     double zuj = 0.0;
     if (lane < n) {
+#pragma unroll 1
         for (int k = 0; k < nx; ++k) {
-            zuj = fma(P.Zx[lane * nx + k], w.xr[k], zuj);
-            zuj = fma(P.Zr[lane * nx + k], w.xr[8 + k], zuj);
+            zuj = fma(P.Zx[lane * nx + k], w.xr()[k], zuj);
+            zuj = fma(P.Zr[lane * nx + k], w.xr()[8 + k], zuj);
         }
     }
-    if (lane < npad) { w.zu[lane] = zuj; w.z[lane] = zuj; }
-    // row values and violations at z_u
-    double vu[R], vl[R];
+    if (lane < npad) { w.zu()[lane] = zuj; w.z()[lane] = zuj; }
+    // row values and bounds at z_u (rows without a bound carry +-1e30)
+    double t[2 * R2], up[2 * R2], lo[2 * R2];
+#pragma unroll
+    for (int r2 = 0; r2 < R2; ++r2) {
+        const int base = r2 * 64 + 2 * lane;
+        const double2 uu = ld2(P.upI + base), ll = ld2(P.loI + base);
+        t[2 * r2] = 0.0; t[2 * r2 + 1] = 0.0;
+        up[2 * r2] = uu.x; up[2 * r2 + 1] = uu.y;
+        lo[2 * r2] = ll.x; lo[2 * r2 + 1] = ll.y;
+    }
+#pragma unroll 1
+    for (int k = 0; k < nx; ++k) {
+        const double xk = w.xr()[k], rk = w.xr()[8 + k];
+        const size_t o = (size_t)k * mpad + 2 * lane;
+#pragma unroll
+        for (int r2 = 0; r2 < R2; ++r2) {
+            const double2 a = ld2(P.TxT + o + r2 * 64), b = ld2(P.TrT + o + r2 * 64);
+            const double2 c = ld2(P.UxT + o + r2 * 64), d = ld2(P.LxT + o + r2 * 64);
+            t[2 * r2] = fma(b.x, rk, fma(a.x, xk, t[2 * r2]));
+            t[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, t[2 * r2 + 1]));
+            up[2 * r2] = fma(c.x, xk, up[2 * r2]);
+            up[2 * r2 + 1] = fma(c.y, xk, up[2 * r2 + 1]);
+            lo[2 * r2] = fma(d.x, xk, lo[2 * r2]);
+            lo[2 * r2 + 1] = fma(d.y, xk, lo[2 * r2 + 1]);
+        }
+    }
     double vmax = -RTMPC_INF;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        vu[r] = -RTMPC_INF; vl[r] = -RTMPC_INF;
-        if (r < nslots) {
-            const int row = r * 32 + lane;
-            double t = 0.0, lo = P.lo0[row], up = P.up0[row];
-            for (int k = 0; k < nx; ++k) {
-                t = fma(P.Tx[row * nx + k], w.xr[k], t);
-                t = fma(P.Tr[row * nx + k], w.xr[8 + k], t);
-                lo = fma(P.Lx[row * nx + k], w.xr[k], lo);
-                up = fma(P.Ux[row * nx + k], w.xr[k], up);
-            }
-            if (P.has_up[row]) vu[r] = t - up;
-            if (P.has_lo[row]) vl[r] = lo - t;
-            vmax = fmax(vmax, fmax(vu[r], vl[r]));
-        }
-    }
-    vmax = warp_max(vmax);
-    cnt.flops += 2ull * n * 2 * nx + 2ull * P.m * 4 * nx;
+    for (int i = 0; i < 2 * R2; ++i) vmax = fmax(vmax, fmax(t[i] - up[i], lo[i] - t[i]));
+    vmax = as_wmax(vmax);
     __syncwarp();
 
-    int status = RTMPC_OPTIMAL, na = 0;
-    unsigned actu = 0, actl = 0;
+    int status = RTMPC_OPTIMAL;
+    unsigned amask = 0, actu = 0, actl = 0;
+    ASSlot sl;
+    sl.ra = 0; sl.sa = 0.0; sl.lam = 0.0;
     if (par_bad) status = RTMPC_INFEASIBLE;
     else if (vmax < 0.0) status = RTMPC_OPTIMAL;      // the unconstrained minimiser is feasible
     else {
+        // M starts empty
+        if (lane < npad) {
+            double* row = w.M() + lane * ms;
+#pragma unroll 1
+            for (int b = 0; b < npad; b += 2) *reinterpret_cast<double2*>(row + b) = make_double2(0.0, 0.0);
+            w.act_row()[lane] = 0;
+            w.act_sgn()[lane] = 0;
+        }
+        __syncwarp();
         // ---- 1. warm start ------------------------------------------------------------------
-        if (warm_inst && P.shift) {
-            const int wn = warm_inst[0];
-            if (wn > 0) {
-                int srow = -1, ssg = 1;
-                if (lane < wn && lane < npad) {
-                    const int code = warm_inst[1 + lane];
-                    const int row = code >> 1;
-                    ssg = (code & 1) ? -1 : 1;
-                    srow = (row >= 0 && row < mpad) ? P.shift[row] : -1;
-                    if (srow >= 0 && !(ssg > 0 ? P.has_up[srow] : P.has_lo[srow])) srow = -1;
-                }
-                const unsigned okm = __ballot_sync(RTMPC_FULL_MASK, srow >= 0);
-                const int pos = __popc(okm & ((1u << lane) - 1u));
-                if (srow >= 0) { w.act_row[pos] = srow; w.act_sgn[pos] = ssg; }
-                na = __popc(okm);
+        const int wn = (warm_inst && P.shift) ? warm_inst[0] : 0;
+        bool apply = false;
+        if (wn > 0) {
+            const unsigned slots = (npad >= 32) ? 0xffffffffu : ((1u << npad) - 1u);
+#pragma unroll 1
+            for (int c = 0; c < wn && c < npad; ++c) {
+                const int code = warm_inst[1 + c];
+                const int row0 = code >> 1;
+                const double sp = (code & 1) ? -1.0 : 1.0;
+                if (row0 < 0 || row0 >= mpad) continue;
+                const int p = P.shift[row0];
+                if (p < 0) continue;
+                if ((sp > 0) ? !(P.upI[p] < 0.5 * RTMPC_INF) : !(P.loI[p] > -0.5 * RTMPC_INF)) continue;
+                const unsigned freem = ~amask & slots;
+                if (!freem || __popc(amask) >= n) break;
+                const bool occ = (amask >> lane) & 1u;
+                const int na = __popc(amask);
+                const double* __restrict__ Wp = P.W + (size_t)p * mpad;
+                const double wpp = Wp[p];
+                const double v = occ ? sl.sa * sp * Wp[sl.ra] : 0.0;
+                if (lane < npad) w.v()[lane] = v;
                 __syncwarp();
-                while (na > 0) {
-                    const unsigned keep = as_factor(P, w, na, lane);
-                    const bool mine = lane < na;
-                    const bool kept = mine && ((keep >> lane) & 1u);
-                    double rhs = 0.0;
-                    if (kept) {
-                        const int ra = w.act_row[lane], sg = w.act_sgn[lane];
-                        double t = 0.0;
-                        for (int k = 0; k < nx; ++k) {
-                            t = fma(P.Tx[ra * nx + k], w.xr[k], t);
-                            t = fma(P.Tr[ra * nx + k], w.xr[8 + k], t);
-                        }
-                        rhs = (double)sg * t - as_bound(P, w.xr, ra, sg);
-                    }
-                    double lamv = tri_bwd(w.S, ss, na, lane, tri_fwd(w.S, ss, na, lane, rhs));
-                    if (!kept) lamv = 0.0;
-                    const double lmaxabs = warp_max(fabs(lamv));
-                    const bool bad = mine && (!kept || lamv < -1e-9 * (1.0 + lmaxabs));
-                    cnt.flops += (unsigned long long)na * na * na / 3 + 4ull * na * na;
-                    cnt.steps += 1;
-                    if (!__any_sync(RTMPC_FULL_MASK, bad)) {
-                        if (mine) w.lam[lane] = fmax(lamv, 0.0);
-                        __syncwarp();
-                        break;
-                    }
-                    na = as_compact(w, na, lane, bad, lamv);
+                const double rr = occ ? as_matvec(w.M(), ms, as_hi(amask), lane, npad, w.v()) : 0.0;
+                const double kappa = wpp - as_wsum(v * rr);
+                cnt.sq += 2 * na * na;
+                if (!(kappa > 1e-11 * wpp)) continue;           // depends on the rows taken so far
+                const int s = __ffs(freem) - 1;
+                if (lane < npad) w.rv()[lane] = rr;
+                __syncwarp();
+                as_border(w.M(), w.rv(), ms, as_hi(amask | (1u << s)), lane, s, rr, kappa);
+                if (lane == s) { sl.ra = p; sl.sa = sp; w.act_row()[s] = p; w.act_sgn()[s] = (int)sp; }
+                amask |= 1u << s;
+                __syncwarp();
+            }
+            // multipliers of the equality-constrained problem; drop negative ones, most negative first
+            double rhs = 0.0;
+            if ((amask >> lane) & 1u) {
+                double tv = 0.0;
+                const double* tab = (sl.sa > 0) ? P.UxT : P.LxT;
+                double b = (sl.sa > 0) ? P.upI[sl.ra] : P.loI[sl.ra];
+#pragma unroll 1
+                for (int k = 0; k < nx; ++k) {
+                    tv = fma(P.TxT[(size_t)k * mpad + sl.ra], w.xr()[k], tv);
+                    tv = fma(P.TrT[(size_t)k * mpad + sl.ra], w.xr()[8 + k], tv);
+                    b = fma(tab[(size_t)k * mpad + sl.ra], w.xr()[k], b);
                 }
-                if (na > 0) {
-                    if (lane < npad) w.coef[lane] = (lane < na) ? (double)w.act_sgn[lane] * w.lam[lane] : 0.0;
-                    __syncwarp();
-                    as_apply_rows<R>(P, w, na, lane, nslots, vu, vl);
-                    cnt.flops += 2ull * P.m * na;
-                    for (int a = 0; a < na; ++a) {
-                        const int row = w.act_row[a];
-                        if (lane == (row & 31)) {
-                            if (w.act_sgn[a] > 0) actu |= 1u << (row >> 5); else actl |= 1u << (row >> 5);
-                        }
-                    }
-                    __syncwarp();
+                rhs = sl.sa * (tv - b);                          // s (t_u - up)  or  -(t_u - lo)
+            }
+#pragma unroll 1
+            while (amask) {
+                const bool occ = (amask >> lane) & 1u;
+                const int na = __popc(amask);
+                const int hi = as_hi(amask);
+                if (lane < npad) w.v()[lane] = occ ? rhs : 0.0;
+                __syncwarp();
+                const double lamv = occ ? as_matvec(w.M(), ms, hi, lane, npad, w.v()) : 0.0;
+                const ASArg lm = as_wargmin(occ ? lamv : RTMPC_INF, lane);
+                const double lmaxabs = as_wmax(fabs(lamv));
+                cnt.sq += na * na;
+                cnt.steps += 1;
+                if (!(lm.v < -1e-9 * (1.0 + lmaxabs))) {
+                    sl.lam = occ ? fmax(lamv, 0.0) : 0.0;
+                    break;
                 }
+                as_downdate(w.M(), w.v(), ms, hi, lane, lm.idx);
+                amask &= ~(1u << lm.idx);
+                cnt.sq += na * na;
+            }
+            if (amask) {
+                const bool occ = (amask >> lane) & 1u;
+                if (lane < npad) w.coef()[lane] = occ ? -sl.sa * sl.lam : 0.0;
+                __syncwarp();
+#pragma unroll 1
+                for (unsigned mk = amask; mk; mk &= mk - 1) {
+                    const int a = __ffs(mk) - 1;
+                    as_mark(lane, w.act_row()[a], w.act_sgn()[a], true, actu, actl);
+                }
+                apply = true;         // as_gi moves the row values first
             }
         }
         // ---- 2./3. Goldfarb-Idnani, then certification -----------------------------------------
         const int max_steps = 8 * npad + 32;
+#pragma unroll 1
         for (int refresh = 0;; ++refresh) {
-            status = as_gi<R>(P, w, na, lane, nslots, vu, vl, actu, actl, tolp, max_steps, cnt);
+            status = as_gi<R2>(P, w, amask, sl, lane, t, up, lo, actu, actl, tolp, max_steps, apply, cnt);
+            apply = false;
             if (status != 0) break;
-            const int c = as_certify<R>(P, Gs, w, na, lane, nslots, vu, vl, actu, actl, tolp, cnt);
+            const int c = as_certify<R2>(P, w, amask, sl, lane, t, up, lo, actu, actl, tolp, cnt);
             if (c == 0) { status = RTMPC_OPTIMAL; break; }
             if (c == 2 || refresh >= 3) { status = RTMPC_FALLBACK; break; }
         }
@@ -479,91 +604,81 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, const double* _
     if (status != RTMPC_FALLBACK) {
         const bool has_sol = (status == RTMPC_OPTIMAL);
         const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-        if (lane < npad) w.coef[lane] = (lane < n) ? w.z[lane] * P.D[lane] : 0.0;   // unscaled decision
-        __syncwarp();
         const int nu = P.nu, N = P.N;
-        const int ou = nx * (N + 1);
-        const int first = z_out_inst ? 0 : ou;              // only the input rows are needed for the packet
-        for (int i = first + lane; i < P.nz; i += 32) {
-            double acc = 0.0;
-            for (int k = 0; k < n; ++k) acc = fma(P.Phi[(size_t)i * npad + k], w.coef[k], acc);
-            for (int k = 0; k < nx; ++k) acc = fma(P.Psi[(size_t)i * nx + k], w.xr[k], acc);
-            if (!has_sol) acc = nanv;
-            if (z_out_inst) z_out_inst[i] = acc;
-            if (U_out_inst && i >= ou && i < ou + N * nu) U_out_inst[i - ou] = acc;
-        }
-        if (U_out_inst && P.nss > 0) {
-            // last column of the packet: u_bar + K x_bar
-            const int oxb = ou + N * nu;
-            double val = 0.0;
-            if (lane < nx + nu) {
-                const int i = oxb + lane;
-                for (int k = 0; k < n; ++k) val = fma(P.Phi[(size_t)i * npad + k], w.coef[k], val);
-                for (int k = 0; k < nx; ++k) val = fma(P.Psi[(size_t)i * nx + k], w.xr[k], val);
-            }
-            for (int j = 0; j < nu; ++j) {
-                double acc = __shfl_sync(RTMPC_FULL_MASK, val, nx + j);
-                for (int k = 0; k < nx; ++k) acc = fma(P.Kss[j * nx + k], __shfl_sync(RTMPC_FULL_MASK, val, k), acc);
-                if (lane == 0) U_out_inst[N * nu + j] = has_sol ? acc : nanv;
+        const int nrow = (N + 1) * nu;
+        if (U_out_inst) {
+            // packet payload straight from the scaled decision: U = UPhi z + UPsi x_init, last column u_bar + K x_bar
+#pragma unroll 1
+            for (int i = lane; i < nrow; i += 32) {
+                if (i >= N * nu && P.nss == 0) continue;
+                double acc = 0.0, acc2 = 0.0;
+#pragma unroll 2
+                for (int k = 0; k < npad; k += 2) {          // UPhiT is zero-padded to npad columns
+                    acc = fma(P.UPhiT[(size_t)k * nrow + i], w.z()[k], acc);
+                    acc2 = fma(P.UPhiT[(size_t)(k + 1) * nrow + i], w.z()[k + 1], acc2);
+                }
+#pragma unroll 1
+                for (int k = 0; k < nx; ++k) acc = fma(P.UPsiT[(size_t)k * nrow + i], w.xr()[k], acc);
+                U_out_inst[i] = has_sol ? acc + acc2 : nanv;
             }
         }
-        cnt.flops += 2ull * (P.nz - first) * (n + nx);
+        if (z_out_inst) {
+            if (lane < npad) w.coef()[lane] = (lane < n) ? w.z()[lane] * P.D[lane] : 0.0;   // unscaled decision
+            __syncwarp();
+#pragma unroll 1
+            for (int i = lane; i < P.nz; i += 32) {
+                double acc = 0.0;
+#pragma unroll 1
+                for (int k = 0; k < n; ++k) acc = fma(P.Phi[(size_t)i * npad + k], w.coef()[k], acc);
+#pragma unroll 1
+                for (int k = 0; k < nx; ++k) acc = fma(P.Psi[(size_t)i * nx + k], w.xr()[k], acc);
+                z_out_inst[i] = has_sol ? acc : nanv;
+            }
+        }
     }
     if (warm_inst) {
-        const int nw = (status == RTMPC_OPTIMAL) ? na : -1;
-        if (lane == 0) warm_inst[0] = nw;
-        if (lane < nw) warm_inst[1 + lane] = 2 * w.act_row[lane] + (w.act_sgn[lane] < 0 ? 1 : 0);
+        // certified working set, compacted (the slots are sparse)
+        const bool occ = (status == RTMPC_OPTIMAL) && ((amask >> lane) & 1u);
+        const unsigned om = __ballot_sync(RTMPC_FULL_MASK, occ);
+        const int pos = __popc(om & ((1u << lane) - 1u));
+        if (lane == 0) warm_inst[0] = (status == RTMPC_OPTIMAL) ? __popc(om) : -1;
+        if (occ) warm_inst[1 + pos] = 2 * sl.ra + (sl.sa < 0 ? 1 : 0);
     }
     __syncwarp();
     return status;
-}
-
-// G staged on chip (or the padded global copy), and the per-warp scratch
-__device__ __forceinline__ const double* as_stage(const QPDev& P, double* smem, int g_in_smem, double** wbase) {
-    if (!g_in_smem) { *wbase = smem; return P.Gpad; }
-    const int npad = P.npad, mpad = P.mpad;
-    for (int idx = threadIdx.x; idx < mpad * npad; idx += blockDim.x) {
-        int i = idx / npad, j = idx - i * npad;
-        smem[i * P.gs + j] = P.G[idx];
-    }
-    for (int idx = threadIdx.x; idx < mpad * 2; idx += blockDim.x) smem[(size_t)(idx >> 1) * P.gs + npad + (idx & 1)] = 0.0;
-    __syncthreads();
-    *wbase = smem + (size_t)mpad * P.gs;
-    return smem;
 }
 
 __device__ __forceinline__ int as_pack_iters(const ASCounters& cnt) {
     return ((cnt.steps > 4095 ? 4095 : cnt.steps) << 12) | ((cnt.rounds > 255 ? 255 : cnt.rounds) << 24);
 }
 
-template <int R, int MAXW>
+template <int R2, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 as_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double* __restrict__ ref,
                 const int* __restrict__ sel, int sel_value, double* __restrict__ z_out, double* __restrict__ U_out,
                 int* __restrict__ status_out, int* __restrict__ iters_out, int* __restrict__ warm,
-                unsigned long long* __restrict__ work, int g_in_smem) {
+                unsigned long long* __restrict__ work) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
     const int nx = P.nx;
-    double* wbase;
-    const double* Gs = as_stage(P, smem, g_in_smem, &wbase);
-    ASWarp w = as_carve(wbase + (size_t)warp * as_warp_doubles(P), P);
+    ASWarp w = as_carve(smem + (size_t)warp * as_warp_doubles(P), P);
     const size_t usz = (size_t)(P.N + 1) * P.nu;
+#pragma unroll 1
     for (int inst = blockIdx.x * wpb + warp; inst < B; inst += gridDim.x * wpb) {
         if (sel && sel[inst] != sel_value) continue;
         ASCounters cnt;
-        cnt.steps = 0; cnt.rounds = 0; cnt.flops = 0;
-        const int status = as_solve_instance<R>(P, Gs, w, lane, x_init + (size_t)inst * nx,
-                                                ref ? ref + (size_t)inst * nx : nullptr,
-                                                warm ? warm + (size_t)inst * (P.npad + 1) : nullptr,
-                                                z_out ? z_out + (size_t)inst * P.nz : nullptr,
-                                                U_out ? U_out + inst * usz : nullptr, cnt);
+        cnt.steps = 0; cnt.rounds = 0; cnt.rows = 0; cnt.sq = 0;
+        const int status = as_solve_instance<R2>(P, w, lane, x_init + (size_t)inst * nx,
+                                                 ref ? ref + (size_t)inst * nx : nullptr,
+                                                 warm ? warm + (size_t)inst * (P.npad + 1) : nullptr,
+                                                 z_out ? z_out + (size_t)inst * P.nz : nullptr,
+                                                 U_out ? U_out + inst * usz : nullptr, cnt);
         if (lane == 0) {
             if (status_out) status_out[inst] = status;
             if (iters_out) iters_out[inst] = as_pack_iters(cnt);
-            if (work) atomicAdd(work, cnt.flops);
+            if (work) atomicAdd(work, as_flops(P, cnt, z_out != nullptr));
         }
         __syncwarp();
     }

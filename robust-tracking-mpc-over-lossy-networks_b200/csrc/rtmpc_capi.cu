@@ -30,7 +30,7 @@ struct rtmpc_qp {
     QPDev dev;
     std::vector<void*> allocs;
     int device = 0, num_sms = 0;
-    int ipm_wpb = 8, as_wpb = 0, as_g_in_smem = 0;
+    int ipm_wpb = 8, as_wpb = 0;
     size_t ipm_smem = 0, as_smem = 0;
     int method = RTMPC_METHOD_ACTIVE_SET;
     unsigned long long* d_work = nullptr;   // algorithmic flop counter of the active-set kernel
@@ -79,33 +79,52 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
     if (d->nx < 1 || d->nx > 8 || d->nu < 1 || d->nu > 4) return fail("rtmpc_qp_create: need nx <= 8, nu <= 4");
     if (d->mpad < 32 || (d->mpad & 31) || d->m > d->mpad || d->mpad > 1024)
         return fail("rtmpc_qp_create: mpad must be a multiple of 32 with m <= mpad <= 1024");
+    if (d->n > 30) return fail("rtmpc_qp_create: the active-set kernel keeps one working-set slot per lane: n <= 30");
     if (!d->Hs || !d->Hinv || !d->G || !d->Y || !d->Fx || !d->Fr || !d->lo0 || !d->up0 || !d->Lx || !d->Ux ||
         !d->has_lo || !d->has_up || !d->Dscale || !d->Phi || !d->Psi)
         return fail("rtmpc_qp_create: null matrix in the description");
+    // rows are padded to what the active-set kernel's instantiation works on (a multiple of 64)
+    const int mpad = as_padded_rows(d->mpad);
+    if (mpad < 0) return fail("rtmpc_qp_create: too many rows for the compiled kernel set (mpad <= 1024)");
+    if (d->nss > 0 && !d->Kss) return fail("rtmpc_qp_create: Kss required when nss > 0");
     rtmpc_qp* q = new rtmpc_qp();
     CU(cudaGetDevice(&q->device));
     CU(cudaDeviceGetAttribute(&q->num_sms, cudaDevAttrMultiProcessorCount, q->device));
     QPDev& P = q->dev;
     std::memset(&P, 0, sizeof(P));
-    P.nx = d->nx; P.nu = d->nu; P.N = d->N; P.n = d->n; P.npad = d->npad; P.m = d->m; P.mpad = d->mpad;
+    P.nx = d->nx; P.nu = d->nu; P.N = d->N; P.n = d->n; P.npad = d->npad; P.m = d->m; P.mpad = mpad;
     P.np = d->np; P.nz = d->nz; P.nss = d->nss;
     P.gs = d->npad + 2;
     P.ss = d->npad + 1;
-    P.va_len = ((d->mpad > d->nz ? d->mpad : d->nz) + 1) & ~1;
+    P.va_len = ((mpad > d->nz ? mpad : d->nz) + 1) & ~1;
     P.s_floor = d->s_floor; P.sc_b = d->sc_b; P.max_iter = d->max_iter > 0 ? d->max_iter : 60;
     int mtot = 0;
     for (int i = 0; i < d->mpad; ++i) mtot += (d->has_lo[i] ? 1 : 0) + (d->has_up[i] ? 1 : 0);
     P.mtot = mtot > 0 ? mtot : 1;
-    const int npad = d->npad, mpad = d->mpad, nx = d->nx, gs = P.gs;
+    const int npad = d->npad, nx = d->nx, m0 = d->mpad;
     const size_t nn = (size_t)npad * npad, mn = (size_t)mpad * npad;
-    // operators derived once on the host from the description (shared by every instance):
-    //   W = G Hinv G' (= G Y'), Zx = -Hinv Fx, Zr = -Hinv Fr, Tx = -Y Fx, Tr = -Y Fr, G with the on-chip row stride
-    std::vector<double> W((size_t)mpad * mpad), Zx((size_t)npad * nx), Zr((size_t)npad * nx), Tx((size_t)mpad * nx),
-        Tr((size_t)mpad * nx), Gpad((size_t)mpad * gs, 0.0);
+    // row-indexed inputs, zero-padded to mpad rows (padding rows carry no bound)
+    std::vector<double> G(mn, 0.0), Y(mn, 0.0), lo0(mpad, 0.0), up0(mpad, 0.0), Lx((size_t)mpad * nx, 0.0),
+        Ux((size_t)mpad * nx, 0.0);
+    std::vector<unsigned char> has_lo(mpad, 0), has_up(mpad, 0);
+    std::vector<int> shift(mpad, -1);
+    std::memcpy(G.data(), d->G, (size_t)m0 * npad * sizeof(double));
+    std::memcpy(Y.data(), d->Y, (size_t)m0 * npad * sizeof(double));
+    std::memcpy(lo0.data(), d->lo0, (size_t)m0 * sizeof(double));
+    std::memcpy(up0.data(), d->up0, (size_t)m0 * sizeof(double));
+    std::memcpy(Lx.data(), d->Lx, (size_t)m0 * nx * sizeof(double));
+    std::memcpy(Ux.data(), d->Ux, (size_t)m0 * nx * sizeof(double));
+    std::memcpy(has_lo.data(), d->has_lo, (size_t)m0);
+    std::memcpy(has_up.data(), d->has_up, (size_t)m0);
+    if (d->shift) std::memcpy(shift.data(), d->shift, (size_t)m0 * sizeof(int));
+    // operators derived once on the host (shared by every instance):
+    //   W = G Hinv G' (= G Y'), Zx = -Hinv Fx, Zr = -Hinv Fr, Tx = -Y Fx, Tr = -Y Fr; G, Tx, Tr, Ux, Lx transposed
+    std::vector<double> W((size_t)mpad * mpad), Zx((size_t)npad * nx), Zr((size_t)npad * nx), TxT((size_t)mpad * nx),
+        TrT((size_t)mpad * nx), UxT((size_t)mpad * nx), LxT((size_t)mpad * nx), GT(mn), upI(mpad), loI(mpad);
     for (int a = 0; a < mpad; ++a)
         for (int b = a; b < mpad; ++b) {
             double acc = 0.0;
-            for (int k = 0; k < npad; ++k) acc += d->G[(size_t)a * npad + k] * d->Y[(size_t)b * npad + k];
+            for (int k = 0; k < npad; ++k) acc += G[(size_t)a * npad + k] * Y[(size_t)b * npad + k];
             W[(size_t)a * mpad + b] = acc;
             W[(size_t)b * mpad + a] = acc;
         }
@@ -123,40 +142,68 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
         for (int k = 0; k < nx; ++k) {
             double ax = 0.0, ar = 0.0;
             for (int i = 0; i < npad; ++i) {
-                ax -= d->Y[(size_t)r * npad + i] * d->Fx[(size_t)i * nx + k];
-                ar -= d->Y[(size_t)r * npad + i] * d->Fr[(size_t)i * nx + k];
+                ax -= Y[(size_t)r * npad + i] * d->Fx[(size_t)i * nx + k];
+                ar -= Y[(size_t)r * npad + i] * d->Fr[(size_t)i * nx + k];
             }
-            Tx[(size_t)r * nx + k] = ax;
-            Tr[(size_t)r * nx + k] = ar;
+            TxT[(size_t)k * mpad + r] = ax;
+            TrT[(size_t)k * mpad + r] = ar;
+            UxT[(size_t)k * mpad + r] = Ux[(size_t)r * nx + k];
+            LxT[(size_t)k * mpad + r] = Lx[(size_t)r * nx + k];
         }
-        for (int k = 0; k < npad; ++k) Gpad[(size_t)r * gs + k] = d->G[(size_t)r * npad + k];
+        for (int k = 0; k < npad; ++k) GT[(size_t)k * mpad + r] = G[(size_t)r * npad + k];
+        upI[r] = has_up[r] ? up0[r] : RTMPC_INF;
+        loI[r] = has_lo[r] ? lo0[r] : -RTMPC_INF;
+    }
+    // packet payload map from the scaled decision (unscaling and the steady-state gain folded in)
+    const int nrow = (d->N + 1) * d->nu, ou = nx * (d->N + 1), oxb = ou + d->N * d->nu, oub = oxb + nx;
+    std::vector<double> UPhiT((size_t)npad * nrow, 0.0), UPsiT((size_t)nx * nrow, 0.0);
+    for (int i = 0; i < nrow; ++i) {
+        const bool last = i >= d->N * d->nu;
+        if (last && d->nss == 0) continue;
+        const int j = i - d->N * d->nu;
+        for (int k = 0; k < npad; ++k) {
+            double v = last ? d->Phi[(size_t)(oub + j) * npad + k] : d->Phi[(size_t)(ou + i) * npad + k];
+            if (last) for (int c = 0; c < nx; ++c) v += d->Kss[(size_t)j * nx + c] * d->Phi[(size_t)(oxb + c) * npad + k];
+            UPhiT[(size_t)k * nrow + i] = v * d->Dscale[k];
+        }
+        for (int k = 0; k < nx; ++k) {
+            double v = last ? d->Psi[(size_t)(oub + j) * nx + k] : d->Psi[(size_t)(ou + i) * nx + k];
+            if (last) for (int c = 0; c < nx; ++c) v += d->Kss[(size_t)j * nx + c] * d->Psi[(size_t)(oxb + c) * nx + k];
+            UPsiT[(size_t)k * nrow + i] = v;
+        }
     }
     int rc = 0;
     rc |= upload(q, d->Hs, nn, &P.Hs);
     rc |= upload(q, d->Hinv, nn, &P.Hinv);
-    rc |= upload(q, d->G, mn, &P.G);
-    rc |= upload(q, d->Y, mn, &P.Y);
+    rc |= upload(q, G.data(), mn, &P.G);
+    rc |= upload(q, Y.data(), mn, &P.Y);
     rc |= upload(q, d->Fx, (size_t)npad * nx, &P.Fx);
     rc |= upload(q, d->Fr, (size_t)npad * nx, &P.Fr);
-    rc |= upload(q, d->lo0, (size_t)mpad, &P.lo0);
-    rc |= upload(q, d->up0, (size_t)mpad, &P.up0);
-    rc |= upload(q, d->Lx, (size_t)mpad * nx, &P.Lx);
-    rc |= upload(q, d->Ux, (size_t)mpad * nx, &P.Ux);
-    rc |= upload(q, d->has_lo, (size_t)mpad, &P.has_lo);
-    rc |= upload(q, d->has_up, (size_t)mpad, &P.has_up);
+    rc |= upload(q, lo0.data(), (size_t)mpad, &P.lo0);
+    rc |= upload(q, up0.data(), (size_t)mpad, &P.up0);
+    rc |= upload(q, Lx.data(), (size_t)mpad * nx, &P.Lx);
+    rc |= upload(q, Ux.data(), (size_t)mpad * nx, &P.Ux);
+    rc |= upload(q, has_lo.data(), (size_t)mpad, &P.has_lo);
+    rc |= upload(q, has_up.data(), (size_t)mpad, &P.has_up);
     rc |= upload(q, d->parC, (size_t)d->np * nx, &P.parC);
     rc |= upload(q, d->parh, (size_t)d->np, &P.parh);
     rc |= upload(q, d->Dscale, (size_t)npad, &P.D);
     rc |= upload(q, d->Phi, (size_t)d->nz * npad, &P.Phi);
     rc |= upload(q, d->Psi, (size_t)d->nz * nx, &P.Psi);
     rc |= upload(q, d->Kss, (size_t)d->nu * nx, &P.Kss);
-    rc |= upload(q, d->shift, (size_t)mpad, &P.shift);
+    if (d->shift) rc |= upload(q, shift.data(), (size_t)mpad, &P.shift);
     rc |= upload(q, W.data(), W.size(), &P.W);
-    rc |= upload(q, Gpad.data(), Gpad.size(), &P.Gpad);
+    rc |= upload(q, GT.data(), GT.size(), &P.GT);
     rc |= upload(q, Zx.data(), Zx.size(), &P.Zx);
     rc |= upload(q, Zr.data(), Zr.size(), &P.Zr);
-    rc |= upload(q, Tx.data(), Tx.size(), &P.Tx);
-    rc |= upload(q, Tr.data(), Tr.size(), &P.Tr);
+    rc |= upload(q, TxT.data(), TxT.size(), &P.TxT);
+    rc |= upload(q, TrT.data(), TrT.size(), &P.TrT);
+    rc |= upload(q, UxT.data(), UxT.size(), &P.UxT);
+    rc |= upload(q, LxT.data(), LxT.size(), &P.LxT);
+    rc |= upload(q, upI.data(), upI.size(), &P.upI);
+    rc |= upload(q, loI.data(), loI.size(), &P.loI);
+    rc |= upload(q, UPhiT.data(), UPhiT.size(), &P.UPhiT);
+    rc |= upload(q, UPsiT.data(), UPsiT.size(), &P.UPsiT);
     if (rc) { rtmpc_qp_destroy(q); return -1; }
     if (P.nss > 0 && !P.Kss) { rtmpc_qp_destroy(q); return fail("rtmpc_qp_create: Kss required when nss > 0"); }
 
@@ -167,7 +214,7 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
         rtmpc_qp_destroy(q);
         return fail("rtmpc_qp_create: problem does not fit the interior-point kernel (shared memory / mpad <= 1024)", e);
     }
-    if (!as_configure(P, max_smem, &q->as_wpb, &q->as_smem, &q->as_g_in_smem, &e)) {
+    if (!as_configure(P, max_smem, &q->as_wpb, &q->as_smem, &e)) {
         rtmpc_qp_destroy(q);
         return fail("rtmpc_qp_create: problem does not fit the active-set kernel", e);
     }
@@ -229,7 +276,7 @@ int rtmpc_qp_solve(rtmpc_qp* q, int32_t B, const double* d_x_init, const double*
         }
         a.status = q->s_tmp_status;
     }
-    CU(as_launch(q->dev, q->as_wpb, q->as_smem, q->as_g_in_smem, q->num_sms, a));
+    CU(as_launch(q->dev, q->as_wpb, q->as_smem, q->num_sms, a));
     // instances the active-set kernel handed over (status RTMPC_FALLBACK); exits at once when there are none
     QPLaunch f = a;
     f.sel = a.status; f.sel_value = RTMPC_FALLBACK_STATUS; f.work = nullptr;
@@ -478,7 +525,7 @@ int rtmpc_loop_rollout(rtmpc_loop* l, rtmpc_qp* q, int32_t T, const double* d_re
     CU(cudaMemsetAsync(l->r_pending, 0, B * sizeof(int), s));
     for (int round = 0;; ++round) {
         CU(cudaMemsetAsync(l->r_npend, 0, sizeof(int), s));
-        CU(rollout_launch(P, l->dev, q->as_wpb, q->as_smem, q->as_g_in_smem, q->num_sms, a, s));
+        CU(rollout_launch(P, l->dev, q->as_wpb, q->num_sms, a, s));
         g_launches.fetch_add(1);
         CU(cudaMemcpyAsync(l->h_npend, l->r_npend, sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));

@@ -34,11 +34,16 @@ struct QPDev {
     const double *Hs, *Hinv, *G, *Y, *Fx, *Fr, *lo0, *up0, *Lx, *Ux;
     const unsigned char *has_lo, *has_up;
     const double *parC, *parh, *D, *Phi, *Psi, *Kss;
-    const double* W;      // [mpad*mpad]  G Hinv G'  (Schur entries of the active-set steps are look-ups)
-    const double* Gpad;   // [mpad*gs]    G with the shared-memory row stride (used when G does not fit on chip)
-    const double *Zx, *Zr;   // [npad*nx]  z_u = Zx x_init + Zr ref    (= -Hinv Fx, -Hinv Fr)
-    const double *Tx, *Tr;   // [mpad*nx]  G z_u = Tx x_init + Tr ref
-    const int* shift;     // [mpad] warm-start map: same constraint one stage earlier, -1 = none
+    // operators of the active-set kernel (rtmpc_as.cuh), derived once per problem in rtmpc_qp_create
+    const double* W;         // [mpad*mpad]  G Hinv G'
+    const double* GT;        // [npad*mpad]  G transposed (coalesced row-value recomputation)
+    const double *Zx, *Zr;   // [npad*nx]    z_u = Zx x_init + Zr ref    (= -Hinv Fx, -Hinv Fr)
+    const double *TxT, *TrT; // [nx*mpad]    G z_u = Tx x_init + Tr ref, transposed
+    const double *UxT, *LxT; // [nx*mpad]    Ux, Lx transposed
+    const double *upI, *loI; // [mpad]       up0 / lo0 with +-1e30 where the row has no such bound
+    const double *UPhiT, *UPsiT;   // [npad*(N+1)nu], [nx*(N+1)nu]  packet payload from the scaled decision:
+                                   // U_t = UPhi z + UPsi x_init, last column u_bar + K x_bar folded in
+    const int* shift;        // [mpad] warm-start map: same constraint one stage earlier, -1 = none
     double s_floor, sc_b;
     int max_iter;
 };

@@ -23,8 +23,9 @@ bool ipm_configure(const QPDev& P, int max_smem, int* wpb, size_t* smem, cudaErr
 cudaError_t ipm_launch(const QPDev& P, int wpb, size_t smem, int num_sms, const QPLaunch& a);
 
 // dual active-set kernel
-bool as_configure(const QPDev& P, int max_smem, int* wpb, size_t* smem, int* g_in_smem, cudaError_t* err);
-cudaError_t as_launch(const QPDev& P, int wpb, size_t smem, int g_in_smem, int num_sms, const QPLaunch& a);
+int as_padded_rows(int mpad);    // rows the active-set kernel's instantiation for mpad works on (multiple of 64), -1: none
+bool as_configure(const QPDev& P, int max_smem, int* wpb, size_t* smem, cudaError_t* err);
+cudaError_t as_launch(const QPDev& P, int wpb, size_t smem, int num_sms, const QPLaunch& a);
 
 // persistent closed-loop rollout (rtmpc_rollout.cu); uses the active-set kernel's launch shape
 struct RolloutArgs {
@@ -47,7 +48,7 @@ struct RolloutArgs {
     unsigned long long* stats;    // [8] status counts[4], IPM iterations, active-set steps, rounds, flops (or NULL)
 };
 bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err);
-cudaError_t rollout_launch(const QPDev& P, const LoopDev& L, int wpb, size_t smem, int g_in_smem, int num_sms,
-                           const RolloutArgs& a, cudaStream_t stream);
+cudaError_t rollout_launch(const QPDev& P, const LoopDev& L, int wpb, int num_sms, const RolloutArgs& a,
+                           cudaStream_t stream);
 
 }  // namespace rtmpc

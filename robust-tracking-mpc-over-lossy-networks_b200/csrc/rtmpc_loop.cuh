@@ -28,7 +28,7 @@ struct LoopDev {
     int *q_t, *s_t, *Theta, *alive, *last_loss, *gamma_last;
 };
 
-__device__ __forceinline__ void cartpole_substeps(double* x, double F, const double* c) {
+static __device__ __noinline__ void cartpole_substeps(double* x, double F, const double* c) {
     const double M = c[0], m = c[1], I = c[2], g = c[3], l = c[4], dt = c[5];
     const int nsub = (int)c[6];
     double pos = x[0], vel = x[1], phi = x[2], om = x[3];
@@ -48,17 +48,27 @@ __device__ __forceinline__ void cartpole_substeps(double* x, double F, const dou
 }
 
 // tube containment statistic  max_i (Hz (x - x_nom) - hz)_i  of instance b, rows i = first, first+stride, ...
-__device__ __forceinline__ double loop_tube_rows(const LoopDev& L, int b, int first, int stride) {
-    const int nx = L.nx;
-    double d[LOOP_MAX_NX];
-    for (int k = 0; k < nx; ++k) d[k] = L.x[(size_t)b * nx + k] - L.x_nom[(size_t)b * nx + k];
+template <int NX>
+__device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, int b, int first, int stride) {
+    const int nx = NX ? NX : L.nx;
+    constexpr int AX = NX ? NX : LOOP_MAX_NX;
+    double d[AX];
+#pragma unroll
+    for (int k = 0; k < AX; ++k) d[k] = (k < nx) ? L.x[(size_t)b * nx + k] - L.x_nom[(size_t)b * nx + k] : 0.0;
     double worst = -1e300;
+#pragma unroll 4
     for (int i = first; i < L.nz_rows; i += stride) {
         double acc = -L.hz[i];
-        for (int k = 0; k < nx; ++k) acc = fma(L.Hz[i * nx + k], d[k], acc);
+#pragma unroll
+        for (int k = 0; k < AX; ++k) if (k < nx) acc = fma(L.Hz[i * nx + k], d[k], acc);
         worst = fmax(worst, acc);
     }
     return worst;
+}
+__device__ __forceinline__ double loop_tube_rows(const LoopDev& L, int b, int first, int stride) {
+    if (L.nx == 4) return loop_tube_rows_t<4>(L, b, first, stride);
+    if (L.nx == 2) return loop_tube_rows_t<2>(L, b, first, stride);
+    return loop_tube_rows_t<0>(L, b, first, stride);
 }
 
 // Start of a control step for instance b: records x_0, retires the instance when the controller
@@ -76,12 +86,20 @@ __device__ __forceinline__ bool loop_step_begin(const LoopDev& L, int b, int t, 
 // local side, plant, remote side.  Ub: this step's packet payload [(N+1)*nu]; x_nom0_b: x_nom[:,0]
 // of this step's solve or NULL; theta_in < 0 selects the device RNG.
 // (no __restrict__: inside the rollout kernel these buffers are written by the same warp)
-__device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, const double* Ub, const double* x_nom0_b,
-                                               const double* ref_b, int theta_in, int gamma_in, const double* w_in_b,
-                                               double p, unsigned long long seed, unsigned long long id, double* traj_b,
-                                               double tube_worst) {
-    const int nx = L.nx, nu = L.nu, N = L.N;
-    double x[LOOP_MAX_NX], xn[LOOP_MAX_NX], xh[LOOP_MAX_NX], w[LOOP_MAX_NX];
+// NX, NU > 0: sizes known at compile time (state in registers, loops unrolled); 0: taken from L.
+static __device__ __noinline__ Philox4 loop_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32_10(c0, c1, c2, c3, k0, k1);
+}
+
+template <int NX, int NU>
+static __device__ __noinline__ void loop_step_body_t(const LoopDev& L, int b, int t, const double* Ub,
+                                                     const double* x_nom0_b, const double* ref_b, int theta_in,
+                                                     int gamma_in, const double* w_in_b, double p,
+                                                     unsigned long long seed, unsigned long long id, double* traj_b,
+                                                     double tube_worst) {
+    const int nx = NX ? NX : L.nx, nu = NU ? NU : L.nu, N = L.N;
+    constexpr int AX = NX ? NX : LOOP_MAX_NX, AU = NU ? NU : LOOP_MAX_NU;
+    double x[AX], xn[AX], xh[AX], w[AX];
     for (int k = 0; k < nx; ++k) {
         x[k] = L.x[(size_t)b * nx + k];
         xn[k] = L.x_nom[(size_t)b * nx + k];
@@ -103,11 +121,11 @@ __device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, c
         for (int k = 0; k < nx; ++k) w[k] = w_in_b ? w_in_b[k] : 0.0;
     } else {
         const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-        Philox4 r = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, 0u, k0, k1);
+        Philox4 r = loop_philox((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, 0u, k0, k1);
         theta = (t == 0) ? 1 : (u01_from_bits(r.x, r.y) < p ? 0 : 1);
         gamma = (t == 0) ? 1 : (u01_from_bits(r.z, r.w) < p ? 0 : 1);
         for (int k = 0; k < nx; k += 2) {
-            Philox4 q = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, 1u + (uint32_t)(k >> 1), k0, k1);
+            Philox4 q = loop_philox((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, 1u + (uint32_t)(k >> 1), k0, k1);
             w[k] = L.w_half[k] * (2.0 * u01_from_bits(q.x, q.y) - 1.0);
             if (k + 1 < nx) w[k + 1] = L.w_half[k + 1] * (2.0 * u01_from_bits(q.z, q.w) - 1.0);
         }
@@ -129,7 +147,7 @@ __device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, c
     }
     const int kk = t - s_t;
     const double* xfb = (L.actuator == RTMPC_ACT_SMART) ? x : xn;   // state fed to compute_u_t
-    double u_nom[LOOP_MAX_NU], u[LOOP_MAX_NU];
+    double u_nom[AU], u[AU];
     for (int j = 0; j < nu; ++j) {
         if (kk < N) u_nom[j] = buf[kk * nu + j];
         else {
@@ -145,14 +163,14 @@ __device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, c
         }
     }
     // plant packet content (pre-update values)
-    double xp[LOOP_MAX_NX], xnp[LOOP_MAX_NX];
+    double xp[AX], xnp[AX];
     for (int k = 0; k < nx; ++k) {
         xnp[k] = xn[k];
         xp[k] = (L.actuator == RTMPC_ACT_CONSISTENT) ? xn[k] : x[k];
     }
     // nominal model
     if (L.actuator != RTMPC_ACT_SMART) {
-        double nxt[LOOP_MAX_NX];
+        double nxt[AX];
         for (int i = 0; i < nx; ++i) {
             double acc = 0.0;
             for (int k = 0; k < nx; ++k) acc = fma(L.A[i * nx + k], xnp[k], acc);
@@ -162,7 +180,7 @@ __device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, c
         for (int i = 0; i < nx; ++i) xn[i] = nxt[i];
     }
     // ---- plant ----------------------------------------------------------------------------
-    double xnew[LOOP_MAX_NX];
+    double xnew[AX];
     if (L.plant == RTMPC_PLANT_CARTPOLE) {
         for (int k = 0; k < nx; ++k) xnew[k] = x[k];
         cartpole_substeps(xnew, u[0], L.cart);
@@ -175,9 +193,9 @@ __device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, c
         }
     }
     // ---- remote side ----------------------------------------------------------------------
-    double uh[LOOP_MAX_NU];
+    double uh[AU];
     const double* xbase;
-    double xn0[LOOP_MAX_NX];
+    double xn0[AX];
     if (gamma == 1) {
         // \hat u(k|k) from the sequence the plant is using (== buf) and the packet's state
         for (int j = 0; j < nu; ++j) {
@@ -204,7 +222,7 @@ __device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, c
             xbase = xn0;
         } else xbase = xh;
     }
-    double xhn[LOOP_MAX_NX];
+    double xhn[AX];
     for (int i = 0; i < nx; ++i) {
         double acc = 0.0;
         for (int k = 0; k < nx; ++k) acc = fma(L.A[i * nx + k], xbase[k], acc);
@@ -224,6 +242,19 @@ __device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, c
     L.last_loss[b] = last_loss;
     L.gamma_last[b] = gamma;
     if (traj_b) for (int k = 0; k < nx; ++k) traj_b[(size_t)(t + 1) * nx + k] = xnew[k];
+}
+
+// sizes known at compile time for the reference's two systems (double integrator, cartpole), generic otherwise
+__device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, const double* Ub, const double* x_nom0_b,
+                                               const double* ref_b, int theta_in, int gamma_in, const double* w_in_b,
+                                               double p, unsigned long long seed, unsigned long long id, double* traj_b,
+                                               double tube_worst) {
+    if (L.nx == 4 && L.nu == 1)
+        loop_step_body_t<4, 1>(L, b, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
+    else if (L.nx == 2 && L.nu == 1)
+        loop_step_body_t<2, 1>(L, b, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
+    else
+        loop_step_body_t<0, 0>(L, b, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
 }
 
 #ifdef RTMPC_LOOP_KERNELS   // the non-template kernels are compiled in one translation unit (rtmpc_capi.cu)

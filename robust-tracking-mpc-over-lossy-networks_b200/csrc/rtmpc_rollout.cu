@@ -13,17 +13,15 @@
 
 namespace rtmpc {
 
-template <int R, int MAXW>
+template <int R2, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
-rollout_kernel(QPDev P, LoopDev L, RolloutArgs a, int g_in_smem) {
+rollout_kernel(QPDev P, LoopDev L, RolloutArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
     const int nx = P.nx;
-    double* wbase;
-    const double* Gs = as_stage(P, smem, g_in_smem, &wbase);
-    ASWarp w = as_carve(wbase + (size_t)warp * as_warp_doubles(P), P);
+    ASWarp w = as_carve(smem + (size_t)warp * as_warp_doubles(P), P);
     const size_t usz = (size_t)(P.N + 1) * P.nu;
 
     for (int inst = blockIdx.x * wpb + warp; inst < a.B; inst += gridDim.x * wpb) {
@@ -51,10 +49,10 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a, int g_in_smem) {
                 if (lane == 0) a.pending[inst] = 0;
             } else {
                 ASCounters cnt;
-                cnt.steps = 0; cnt.rounds = 0; cnt.flops = 0;
-                status = as_solve_instance<R>(P, Gs, w, lane, L.x_hat + (size_t)inst * nx, ref_t, warm_inst, z_inst,
-                                              U_inst, cnt);
-                n_steps += cnt.steps; n_rounds += cnt.rounds; n_flops += cnt.flops;
+                cnt.steps = 0; cnt.rounds = 0; cnt.rows = 0; cnt.sq = 0;
+                status = as_solve_instance<R2>(P, w, lane, L.x_hat + (size_t)inst * nx, ref_t, warm_inst, z_inst,
+                                               U_inst, cnt);
+                n_steps += cnt.steps; n_rounds += cnt.rounds; n_flops += as_flops(P, cnt, z_inst != nullptr);
                 if (status == RTMPC_FALLBACK) {
                     if (lane == 0) {
                         a.status[inst] = RTMPC_FALLBACK;
@@ -74,7 +72,7 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a, int g_in_smem) {
             go = __shfl_sync(RTMPC_FULL_MASK, go, 0);
             if (go) {
                 double worst = 0.0;
-                if (L.nz_rows > 0) worst = warp_max(loop_tube_rows(L, inst, lane, 32));
+                if (L.nz_rows > 0) worst = as_wmax(loop_tube_rows(L, inst, lane, 32));
                 if (lane == 0) {
                     const bool expl = a.theta != nullptr;
                     loop_step_body(L, inst, t, U_inst, (L.actuator == RTMPC_ACT_EXTENDED) ? z_inst : nullptr, ref_t,
@@ -99,16 +97,16 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a, int g_in_smem) {
     }
 }
 
-typedef void (*ro_fn)(QPDev, LoopDev, RolloutArgs, int);
-struct RoChoice { int r, maxw; ro_fn fn; };
+typedef void (*ro_fn)(QPDev, LoopDev, RolloutArgs);
+struct RoChoice { int r2, maxw; ro_fn fn; };
 static const RoChoice kRo[] = {
-    {4, 32, rollout_kernel<4, 32>},   {9, 28, rollout_kernel<9, 28>},   {16, 16, rollout_kernel<16, 16>},
-    {24, 12, rollout_kernel<24, 12>}, {32, 8, rollout_kernel<32, 8>},
+    {2, 24, rollout_kernel<2, 24>},  {5, 16, rollout_kernel<5, 16>},  {9, 12, rollout_kernel<9, 12>},
+    {12, 10, rollout_kernel<12, 10>}, {16, 8, rollout_kernel<16, 8>},
 };
 static const RoChoice* pick(int mpad) {
-    const int r_need = mpad / 32;
+    const int r_need = (mpad + 63) / 64;
     for (const auto& c : kRo)
-        if (c.r >= r_need) return &c;
+        if (c.r2 >= r_need) return &c;
     return nullptr;
 }
 
@@ -119,17 +117,17 @@ bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err) {
     return *err == cudaSuccess;
 }
 
-cudaError_t rollout_launch(const QPDev& P, const LoopDev& L, int wpb, size_t smem, int g_in_smem, int num_sms,
-                           const RolloutArgs& a, cudaStream_t stream) {
+cudaError_t rollout_launch(const QPDev& P, const LoopDev& L, int wpb, int num_sms, const RolloutArgs& a,
+                           cudaStream_t stream) {
     const RoChoice* kc = pick(P.mpad);
+    if (wpb > kc->maxw) wpb = kc->maxw;
     int per_cta = (a.B + num_sms - 1) / num_sms;
     int warps = per_cta < wpb ? per_cta : wpb;
     if (warps < 1) warps = 1;
     int blocks = (a.B + warps - 1) / warps;
     if (blocks > num_sms) blocks = num_sms;
     const size_t per_warp = (size_t)as_warp_doubles(P) * sizeof(double);
-    const size_t bytes = smem - per_warp * (wpb - warps);
-    kc->fn<<<blocks, warps * 32, bytes, stream>>>(P, L, a, g_in_smem);
+    kc->fn<<<blocks, warps * 32, per_warp * warps, stream>>>(P, L, a);
     return cudaGetLastError();
 }
 

@@ -182,3 +182,176 @@ def solve_as(d, W, x_init, ref, warm=None, shift=None, max_iter=96, tol_p=1e-11,
         return None, FALLBACK, info
     info["active"] = fin
     return z, OPTIMAL, info
+
+
+# ------------------------------------------------------------------------------------------------------
+# Version 2 of the kernel: the explicit inverse M = S^-1 of the working set's Schur complement is kept up to
+# date by bordering (add) / rank-one downdates (drop); no factorisation anywhere.  Certification = iterative
+# refinement of the multipliers against the true rows of G with M as the approximate inverse.
+# ------------------------------------------------------------------------------------------------------
+def solve_as_inv(d, W, x_init, ref, warm=None, shift=None, max_iter=224, tol_p=1e-11, kappa_eps=1e-11, passes=3):
+    n, m, G, q, lo, up, hl, hu = _problem(d, x_init, ref)
+    info = dict(path="as", iters=0, drops=0, rounds=0, active=None, why=None)
+    if np.any(d.par_C @ x_init - d.par_h > 1e-9 * (1.0 + np.abs(d.par_h))):
+        return np.full(n, np.nan), INFEASIBLE, dict(info, path="param_rows")
+    Hinv = d.Hinv[:n, :n]
+    Y = d.Y[:m, :n]
+    zu = -(Hinv @ q)
+    tu = G @ zu
+    tolp = tol_p * d.sc_b
+    upi = np.where(hu, up, 1e30)
+    loi = np.where(hl, lo, -1e30)
+    if max((tu - upi).max(), (loi - tu).max()) < 0:
+        return zu, OPTIMAL, dict(info, path="unconstrained", active=[])
+
+    act = []                 # [(row, sign)]
+    M = np.zeros((0, 0))
+    lam = np.zeros(0)
+
+    def border(M, r, kappa):
+        na = M.shape[0]
+        ik = 1.0 / kappa
+        Mn = np.zeros((na + 1, na + 1))
+        Mn[:na, :na] = M + np.outer(r, r) * ik
+        Mn[:na, na] = -r * ik
+        Mn[na, :na] = -r * ik
+        Mn[na, na] = ik
+        return Mn
+
+    def downdate(M, j):
+        Mn = M - np.outer(M[:, j], M[j, :]) / M[j, j]
+        keep = [i for i in range(M.shape[0]) if i != j]
+        return Mn[np.ix_(keep, keep)]
+
+    def sv(act):
+        rows = np.array([a[0] for a in act], int)
+        sg = np.array([a[1] for a in act], float)
+        return rows, sg
+
+    if warm:
+        cand = [(int(shift[r]), s) for r, s in warm if shift[r] >= 0] if shift is not None else list(warm)
+        cand = [(r, s) for r, s in cand if (hu[r] if s > 0 else hl[r])]
+        for (p, sp) in cand:
+            rows, sg = sv(act)
+            v = sg * W[rows, p] * sp if act else np.zeros(0)
+            r = M @ v
+            kappa = W[p, p] - v @ r
+            if kappa > kappa_eps * W[p, p]:
+                M = border(M, r, kappa)
+                act.append((p, sp))
+        while act:
+            rows, sg = sv(act)
+            rhs = sg * tu[rows] - np.where(sg > 0, up[rows], -lo[rows])
+            lam = M @ rhs
+            j = int(np.argmin(lam))
+            if lam[j] >= -1e-9 * (1.0 + np.abs(lam).max()):
+                break
+            M = downdate(M, j)
+            act.pop(j)
+            info["drops"] += 1
+        lam = np.maximum(lam, 0.0) if act else np.zeros(0)
+    rows, sg = sv(act)
+    t = tu - W[:m, rows] @ (sg * lam) if act else tu.copy()
+
+    it = 0
+    for refresh in range(4):
+        status = None
+        while True:
+            vu = t - upi
+            vl = loi - t
+            for (r_, s_) in act:
+                if s_ > 0:
+                    vu[r_] = -np.inf
+                else:
+                    vl[r_] = -np.inf
+            iu, il = int(np.argmax(vu)), int(np.argmax(vl))
+            vmax, p, sp = (vu[iu], iu, 1) if vu[iu] >= vl[il] else (vl[il], il, -1)
+            if vmax <= tolp:
+                break
+            cp = vmax
+            lam_p = 0.0
+            while True:
+                it += 1
+                if it > max_iter:
+                    status = FALLBACK
+                    break
+                na = len(act)
+                rows, sg = sv(act)
+                v = sg * W[rows, p] * sp if na else np.zeros(0)
+                r = M @ v
+                kappa = W[p, p] - v @ r
+                dependent = not (kappa > kappa_eps * W[p, p])
+                t1, j1 = np.inf, -1
+                rmax = np.abs(r).max(initial=0.0)
+                for j in range(na):
+                    if r[j] > 1e-13 * (1.0 + rmax) and lam[j] / r[j] < t1:
+                        t1, j1 = lam[j] / r[j], j
+                if dependent:
+                    if j1 < 0:
+                        status = INFEASIBLE if cp > 1e-6 * d.sc_b else FALLBACK
+                        break
+                    step, full = t1, False
+                else:
+                    t2 = cp / kappa
+                    full = not (j1 >= 0 and t1 < t2)
+                    step = t2 if full else t1
+                lam = lam - step * r
+                lam_p += step
+                if not dependent:
+                    t = t - step * (sp * W[:m, p] - (W[:m, rows] @ (sg * r) if na else 0.0))
+                    cp -= step * kappa
+                if full:
+                    if na >= n:
+                        status = FALLBACK
+                        break
+                    M = border(M, r, kappa)
+                    act.append((p, sp))
+                    lam = np.r_[lam, lam_p]
+                    break
+                M = downdate(M, j1)
+                act.pop(j1)
+                lam = np.delete(lam, j1)
+                info["drops"] += 1
+            if status is not None:
+                break
+        info["iters"] = it
+        if status == INFEASIBLE:
+            return np.full(n, np.nan), INFEASIBLE, info
+        if status == FALLBACK:
+            info["why"] = "gi"
+            return None, FALLBACK, info
+        # certification: refinement against the true rows with M as approximate inverse
+        info["rounds"] += 1
+        rows, sg = sv(act)
+        na = len(act)
+        b = np.where(sg > 0, up[rows], -lo[rows]) if na else np.zeros(0)
+        Gt = sg[:, None] * G[rows] if na else np.zeros((0, n))
+        Yt = sg[:, None] * Y[rows] if na else np.zeros((0, n))
+        z = zu.copy()
+        lam_acc = np.zeros(na)
+        resid = Gt @ z - b
+        for _ in range(passes):
+            dl = M @ resid
+            lam_acc += dl
+            z = z - Yt.T @ dl
+            resid = Gt @ z - b
+        if na and np.abs(resid).max() > tolp:
+            info["why"] = "refine %.2e" % np.abs(resid).max()
+            return None, FALLBACK, info
+        t = G @ z
+        if na and lam_acc.min() < -1e-9 * (1.0 + np.abs(lam_acc).max()):
+            info["why"] = "neg"
+            return None, FALLBACK, info
+        lam = np.maximum(lam_acc, 0.0)
+        vu = t - upi
+        vl = loi - t
+        for (r_, s_) in act:
+            if s_ > 0:
+                vu[r_] = -np.inf
+            else:
+                vl[r_] = -np.inf
+        if max(vu.max(), vl.max()) <= tolp:
+            info["active"] = list(act)
+            return z, OPTIMAL, info
+    info["why"] = "refresh"
+    return None, FALLBACK, info
