@@ -210,11 +210,11 @@ __device__ __forceinline__ int as_hi(unsigned amask) { return (33 - __clz(amask 
 // Goldfarb-Idnani iteration.  `apply_only`: the warm start left its multipliers in w.coef(); the first pass
 // only moves the row values (the row streaming code exists once).  Returns 0 when no row is violated by
 // more than tolp.
-template <int R2>
+// ILP = 2: two rows of W / three columns of G' per pass (more loads in flight, more registers)
+template <int R2, int ILP>
 __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask, ASSlot& sl, int lane,
-                                     double (&t)[2 * R2], const double (&up)[2 * R2], const double (&lo)[2 * R2],
-                                     unsigned& actu, unsigned& actl, double tolp, int max_steps, bool apply_only,
-                                     ASCounters& cnt) {
+                                     double (&e)[2 * R2], unsigned& actu, unsigned& actl, double tolp, int max_steps,
+                                     bool apply_only, ASCounters& cnt) {
     const int npad = P.npad, n = P.n, mpad = P.mpad, ms = as_ms(P);
     const unsigned slots = (npad >= 32) ? 0xffffffffu : ((1u << npad) - 1u);
     while (true) {
@@ -224,11 +224,14 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
             double best = -RTMPC_INF;
             int code = 0;
 #pragma unroll
-            for (int i = 0; i < 2 * R2; ++i) {
-                const int row = ((i >> 1) << 6) + 2 * lane + (i & 1);
-                const double vu = t[i] - up[i], vl = lo[i] - t[i];
-                if (!((actu >> i) & 1u) && vu > best) { best = vu; code = 2 * row; }
-                if (!((actl >> i) & 1u) && vl > best) { best = vl; code = 2 * row + 1; }
+            for (int r2 = 0; r2 < R2; ++r2) {
+                const int row = (r2 << 6) + 2 * lane;
+                const double2 wd = ld2(P.wid + row);
+                const double vu0 = e[2 * r2], vl0 = -e[2 * r2] - wd.x, vu1 = e[2 * r2 + 1], vl1 = -e[2 * r2 + 1] - wd.y;
+                if (!((actu >> (2 * r2)) & 1u) && vu0 > best) { best = vu0; code = 2 * row; }
+                if (!((actl >> (2 * r2)) & 1u) && vl0 > best) { best = vl0; code = 2 * row + 1; }
+                if (!((actu >> (2 * r2 + 1)) & 1u) && vu1 > best) { best = vu1; code = 2 * row + 2; }
+                if (!((actl >> (2 * r2 + 1)) & 1u) && vl1 > best) { best = vl1; code = 2 * row + 3; }
             }
             const ASArg bm = as_wargmax(best, code);
             if (bm.v <= tolp) return 0;
@@ -282,24 +285,34 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
 #pragma unroll
                 for (int r2 = 0; r2 < R2; ++r2) {
                     const double2 g = ld2(Wp + r2 * 64 + 2 * lane);
-                    t[2 * r2] = fma(c, g.x, t[2 * r2]);
-                    t[2 * r2 + 1] = fma(c, g.y, t[2 * r2 + 1]);
+                    e[2 * r2] = fma(c, g.x, e[2 * r2]);
+                    e[2 * r2 + 1] = fma(c, g.y, e[2 * r2 + 1]);
                 }
 #pragma unroll 1
                 for (unsigned mk = amask; mk;) {
                     // two rows per pass: twice the loads in flight
                     const int a = __ffs(mk) - 1;
                     mk &= mk - 1;
-                    const int a2 = mk ? __ffs(mk) - 1 : a;
-                    const double ca = w.coef()[a], cb = mk ? w.coef()[a2] : 0.0;
-                    mk &= mk - 1;
+                    const double ca = w.coef()[a];
                     const double* __restrict__ Wa = P.W + (size_t)w.act_row()[a] * mpad + 2 * lane;
-                    const double* __restrict__ Wb = P.W + (size_t)w.act_row()[a2] * mpad + 2 * lane;
+                    if (ILP >= 2) {
+                        const int a2 = mk ? __ffs(mk) - 1 : a;
+                        const double cb = mk ? w.coef()[a2] : 0.0;
+                        mk &= mk - 1;
+                        const double* __restrict__ Wb = P.W + (size_t)w.act_row()[a2] * mpad + 2 * lane;
 #pragma unroll
-                    for (int r2 = 0; r2 < R2; ++r2) {
-                        const double2 g = ld2(Wa + r2 * 64), h = ld2(Wb + r2 * 64);
-                        t[2 * r2] = fma(cb, h.x, fma(ca, g.x, t[2 * r2]));
-                        t[2 * r2 + 1] = fma(cb, h.y, fma(ca, g.y, t[2 * r2 + 1]));
+                        for (int r2 = 0; r2 < R2; ++r2) {
+                            const double2 g = ld2(Wa + r2 * 64), h = ld2(Wb + r2 * 64);
+                            e[2 * r2] = fma(cb, h.x, fma(ca, g.x, e[2 * r2]));
+                            e[2 * r2 + 1] = fma(cb, h.y, fma(ca, g.y, e[2 * r2 + 1]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int r2 = 0; r2 < R2; ++r2) {
+                            const double2 g = ld2(Wa + r2 * 64);
+                            e[2 * r2] = fma(ca, g.x, e[2 * r2]);
+                            e[2 * r2 + 1] = fma(ca, g.y, e[2 * r2 + 1]);
+                        }
                     }
                 }
                 cp = fma(-step, kappa, cp);
@@ -331,10 +344,10 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
 
 // Certification on the working set.  Returns 0 when the KKT conditions hold, 1 when a row is still
 // violated (t holds exact values: go back to as_gi), 2 on a negative multiplier / no convergence.
-template <int R2>
+template <int R2, int ILP>
 __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned amask, ASSlot& sl, int lane,
-                                          double (&t)[2 * R2], const double (&up)[2 * R2], const double (&lo)[2 * R2],
-                                          unsigned actu, unsigned actl, double tolp, ASCounters& cnt) {
+                                          double (&e)[2 * R2], unsigned actu, unsigned actl, double tolp,
+                                          ASCounters& cnt) {
     const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ms = as_ms(P);
     const bool occ = (amask >> lane) & 1u;
     const int hi = as_hi(amask);
@@ -392,29 +405,62 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
         }
     }
     cnt.rounds += 1;
-    // exact row values at z:  t = G z through the transposed copy (coalesced 16-byte loads)
+    // exact row values at z:  e = G z - up through the transposed copies (coalesced 16-byte loads)
 #pragma unroll
-    for (int i = 0; i < 2 * R2; ++i) t[i] = 0.0;
-    // (z is zero beyond n, G' is zero-padded: three columns per pass keep 3*R2 loads in flight)
+    for (int r2 = 0; r2 < R2; ++r2) {
+        const double2 uu = ld2(P.upI + r2 * 64 + 2 * lane);
+        e[2 * r2] = -uu.x;
+        e[2 * r2 + 1] = -uu.y;
+    }
 #pragma unroll 1
-    for (int k = 0; k < npad; k += 3) {
-        const int k1 = (k + 1 < npad) ? k + 1 : k, k2 = (k + 2 < npad) ? k + 2 : k;
-        const double z0 = w.z()[k], z1 = (k + 1 < npad) ? w.z()[k1] : 0.0, z2 = (k + 2 < npad) ? w.z()[k2] : 0.0;
-        const double* __restrict__ g0 = P.GT + (size_t)k * mpad + 2 * lane;
-        const double* __restrict__ g1 = P.GT + (size_t)k1 * mpad + 2 * lane;
-        const double* __restrict__ g2 = P.GT + (size_t)k2 * mpad + 2 * lane;
+    for (int k = 0; k < nx; ++k) {
+        const double xk = w.xr()[k];
+        const double* __restrict__ u = P.UxT + (size_t)k * mpad + 2 * lane;
 #pragma unroll
         for (int r2 = 0; r2 < R2; ++r2) {
-            const double2 a = ld2(g0 + r2 * 64), b = ld2(g1 + r2 * 64), c = ld2(g2 + r2 * 64);
-            t[2 * r2] = fma(c.x, z2, fma(b.x, z1, fma(a.x, z0, t[2 * r2])));
-            t[2 * r2 + 1] = fma(c.y, z2, fma(b.y, z1, fma(a.y, z0, t[2 * r2 + 1])));
+            const double2 c = ld2(u + r2 * 64);
+            e[2 * r2] = fma(-c.x, xk, e[2 * r2]);
+            e[2 * r2 + 1] = fma(-c.y, xk, e[2 * r2 + 1]);
+        }
+    }
+    // (z is zero beyond n, G' is zero-padded)
+    if (ILP >= 2) {
+        // three columns per pass keep 3*R2 loads in flight
+#pragma unroll 1
+        for (int k = 0; k < npad; k += 3) {
+            const int k1 = (k + 1 < npad) ? k + 1 : k, k2 = (k + 2 < npad) ? k + 2 : k;
+            const double z0 = w.z()[k], z1 = (k + 1 < npad) ? w.z()[k1] : 0.0, z2 = (k + 2 < npad) ? w.z()[k2] : 0.0;
+            const double* __restrict__ g0 = P.GT + (size_t)k * mpad + 2 * lane;
+            const double* __restrict__ g1 = P.GT + (size_t)k1 * mpad + 2 * lane;
+            const double* __restrict__ g2 = P.GT + (size_t)k2 * mpad + 2 * lane;
+#pragma unroll
+            for (int r2 = 0; r2 < R2; ++r2) {
+                const double2 a = ld2(g0 + r2 * 64), b = ld2(g1 + r2 * 64), c = ld2(g2 + r2 * 64);
+                e[2 * r2] = fma(c.x, z2, fma(b.x, z1, fma(a.x, z0, e[2 * r2])));
+                e[2 * r2 + 1] = fma(c.y, z2, fma(b.y, z1, fma(a.y, z0, e[2 * r2 + 1])));
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < n; ++k) {
+            const double z0 = w.z()[k];
+            const double* __restrict__ g0 = P.GT + (size_t)k * mpad + 2 * lane;
+#pragma unroll
+            for (int r2 = 0; r2 < R2; ++r2) {
+                const double2 a = ld2(g0 + r2 * 64);
+                e[2 * r2] = fma(a.x, z0, e[2 * r2]);
+                e[2 * r2 + 1] = fma(a.y, z0, e[2 * r2 + 1]);
+            }
         }
     }
     double worst = -RTMPC_INF;
 #pragma unroll
-    for (int i = 0; i < 2 * R2; ++i) {
-        if (!((actu >> i) & 1u)) worst = fmax(worst, t[i] - up[i]);
-        if (!((actl >> i) & 1u)) worst = fmax(worst, lo[i] - t[i]);
+    for (int r2 = 0; r2 < R2; ++r2) {
+        const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane);
+        if (!((actu >> (2 * r2)) & 1u)) worst = fmax(worst, e[2 * r2]);
+        if (!((actl >> (2 * r2)) & 1u)) worst = fmax(worst, -e[2 * r2] - wd.x);
+        if (!((actu >> (2 * r2 + 1)) & 1u)) worst = fmax(worst, e[2 * r2 + 1]);
+        if (!((actl >> (2 * r2 + 1)) & 1u)) worst = fmax(worst, -e[2 * r2 + 1] - wd.y);
     }
     worst = as_wmax(worst);
     const double lmin = as_wmin(occ ? lam : RTMPC_INF), lmaxabs = as_wmax(occ ? fabs(lam) : 0.0);
@@ -429,7 +475,7 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
 // instance's warm-start record (npad + 1 ints) or NULL; z_out_inst / U_out_inst: this instance's
 // outputs or NULL.  Returns the status; on RTMPC_FALLBACK nothing has been written.
 // (no __restrict__ on the instance pointers: the rollout kernel writes them from the same warp)
-template <int R2>
+template <int R2, int ILP>
 __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int lane, const double* x_init,
                                                  const double* ref, int* warm_inst, double* z_out_inst,
                                                  double* U_out_inst, ASCounters& cnt) {
@@ -458,15 +504,13 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
         }
     }
     if (lane < npad) { w.zu()[lane] = zuj; w.z()[lane] = zuj; }
-    // row values and bounds at z_u (rows without a bound carry +-1e30)
-    double t[2 * R2], up[2 * R2], lo[2 * R2];
+    // e = G z_u - up for every row (rows are measured from their upper bound; the lower side is e + wid >= 0)
+    double e[2 * R2];
 #pragma unroll
     for (int r2 = 0; r2 < R2; ++r2) {
-        const int base = r2 * 64 + 2 * lane;
-        const double2 uu = ld2(P.upI + base), ll = ld2(P.loI + base);
-        t[2 * r2] = 0.0; t[2 * r2 + 1] = 0.0;
-        up[2 * r2] = uu.x; up[2 * r2 + 1] = uu.y;
-        lo[2 * r2] = ll.x; lo[2 * r2 + 1] = ll.y;
+        const double2 uu = ld2(P.upI + r2 * 64 + 2 * lane);
+        e[2 * r2] = -uu.x;
+        e[2 * r2 + 1] = -uu.y;
     }
 #pragma unroll 1
     for (int k = 0; k < nx; ++k) {
@@ -474,19 +518,17 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
         const size_t o = (size_t)k * mpad + 2 * lane;
 #pragma unroll
         for (int r2 = 0; r2 < R2; ++r2) {
-            const double2 a = ld2(P.TxT + o + r2 * 64), b = ld2(P.TrT + o + r2 * 64);
-            const double2 c = ld2(P.UxT + o + r2 * 64), d = ld2(P.LxT + o + r2 * 64);
-            t[2 * r2] = fma(b.x, rk, fma(a.x, xk, t[2 * r2]));
-            t[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, t[2 * r2 + 1]));
-            up[2 * r2] = fma(c.x, xk, up[2 * r2]);
-            up[2 * r2 + 1] = fma(c.y, xk, up[2 * r2 + 1]);
-            lo[2 * r2] = fma(d.x, xk, lo[2 * r2]);
-            lo[2 * r2 + 1] = fma(d.y, xk, lo[2 * r2 + 1]);
+            const double2 a = ld2(P.ExT + o + r2 * 64), b = ld2(P.TrT + o + r2 * 64);
+            e[2 * r2] = fma(b.x, rk, fma(a.x, xk, e[2 * r2]));
+            e[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, e[2 * r2 + 1]));
         }
     }
     double vmax = -RTMPC_INF;
 #pragma unroll
-    for (int i = 0; i < 2 * R2; ++i) vmax = fmax(vmax, fmax(t[i] - up[i], lo[i] - t[i]));
+    for (int r2 = 0; r2 < R2; ++r2) {
+        const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane);
+        vmax = fmax(vmax, fmax(fmax(e[2 * r2], -e[2 * r2] - wd.x), fmax(e[2 * r2 + 1], -e[2 * r2 + 1] - wd.y)));
+    }
     vmax = as_wmax(vmax);
     __syncwarp();
 
@@ -544,16 +586,13 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             // multipliers of the equality-constrained problem; drop negative ones, most negative first
             double rhs = 0.0;
             if ((amask >> lane) & 1u) {
-                double tv = 0.0;
-                const double* tab = (sl.sa > 0) ? P.UxT : P.LxT;
-                double b = (sl.sa > 0) ? P.upI[sl.ra] : P.loI[sl.ra];
+                double ev = -P.upI[sl.ra];
 #pragma unroll 1
                 for (int k = 0; k < nx; ++k) {
-                    tv = fma(P.TxT[(size_t)k * mpad + sl.ra], w.xr()[k], tv);
-                    tv = fma(P.TrT[(size_t)k * mpad + sl.ra], w.xr()[8 + k], tv);
-                    b = fma(tab[(size_t)k * mpad + sl.ra], w.xr()[k], b);
+                    ev = fma(P.ExT[(size_t)k * mpad + sl.ra], w.xr()[k], ev);
+                    ev = fma(P.TrT[(size_t)k * mpad + sl.ra], w.xr()[8 + k], ev);
                 }
-                rhs = sl.sa * (tv - b);                          // s (t_u - up)  or  -(t_u - lo)
+                rhs = (sl.sa > 0) ? ev : -(ev + P.wid[sl.ra]);   // s (t_u - up)  or  -(t_u - lo)
             }
 #pragma unroll 1
             while (amask) {
@@ -591,10 +630,10 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
         const int max_steps = 8 * npad + 32;
 #pragma unroll 1
         for (int refresh = 0;; ++refresh) {
-            status = as_gi<R2>(P, w, amask, sl, lane, t, up, lo, actu, actl, tolp, max_steps, apply, cnt);
+            status = as_gi<R2, ILP>(P, w, amask, sl, lane, e, actu, actl, tolp, max_steps, apply, cnt);
             apply = false;
             if (status != 0) break;
-            const int c = as_certify<R2>(P, w, amask, sl, lane, t, up, lo, actu, actl, tolp, cnt);
+            const int c = as_certify<R2, ILP>(P, w, amask, sl, lane, e, actu, actl, tolp, cnt);
             if (c == 0) { status = RTMPC_OPTIMAL; break; }
             if (c == 2 || refresh >= 3) { status = RTMPC_FALLBACK; break; }
         }
@@ -670,7 +709,7 @@ as_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double*
         if (sel && sel[inst] != sel_value) continue;
         ASCounters cnt;
         cnt.steps = 0; cnt.rounds = 0; cnt.rows = 0; cnt.sq = 0;
-        const int status = as_solve_instance<R2>(P, w, lane, x_init + (size_t)inst * nx,
+        const int status = as_solve_instance<R2, (MAXW * R2 <= 100) ? 2 : 1>(P, w, lane, x_init + (size_t)inst * nx,
                                                  ref ? ref + (size_t)inst * nx : nullptr,
                                                  warm ? warm + (size_t)inst * (P.npad + 1) : nullptr,
                                                  z_out ? z_out + (size_t)inst * P.nz : nullptr,

@@ -119,8 +119,9 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
     if (d->shift) std::memcpy(shift.data(), d->shift, (size_t)m0 * sizeof(int));
     // operators derived once on the host (shared by every instance):
     //   W = G Hinv G' (= G Y'), Zx = -Hinv Fx, Zr = -Hinv Fr, Tx = -Y Fx, Tr = -Y Fr; G, Tx, Tr, Ux, Lx transposed
-    std::vector<double> W((size_t)mpad * mpad), Zx((size_t)npad * nx), Zr((size_t)npad * nx), TxT((size_t)mpad * nx),
-        TrT((size_t)mpad * nx), UxT((size_t)mpad * nx), LxT((size_t)mpad * nx), GT(mn), upI(mpad), loI(mpad);
+    std::vector<double> W((size_t)mpad * mpad), Zx((size_t)npad * nx), Zr((size_t)npad * nx), ExT((size_t)mpad * nx),
+        TrT((size_t)mpad * nx), UxT((size_t)mpad * nx), LxT((size_t)mpad * nx), GT(mn), upI(mpad), loI(mpad), wid(mpad);
+    bool as_ok = true;
     for (int a = 0; a < mpad; ++a)
         for (int b = a; b < mpad; ++b) {
             double acc = 0.0;
@@ -145,7 +146,7 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
                 ax -= Y[(size_t)r * npad + i] * d->Fx[(size_t)i * nx + k];
                 ar -= Y[(size_t)r * npad + i] * d->Fr[(size_t)i * nx + k];
             }
-            TxT[(size_t)k * mpad + r] = ax;
+            ExT[(size_t)k * mpad + r] = ax - Ux[(size_t)r * nx + k];
             TrT[(size_t)k * mpad + r] = ar;
             UxT[(size_t)k * mpad + r] = Ux[(size_t)r * nx + k];
             LxT[(size_t)k * mpad + r] = Lx[(size_t)r * nx + k];
@@ -153,6 +154,16 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
         for (int k = 0; k < npad; ++k) GT[(size_t)k * mpad + r] = G[(size_t)r * npad + k];
         upI[r] = has_up[r] ? up0[r] : RTMPC_INF;
         loI[r] = has_lo[r] ? lo0[r] : -RTMPC_INF;
+        wid[r] = (has_up[r] && has_lo[r]) ? up0[r] - lo0[r] : 3.0 * RTMPC_INF;   // -e - wid < 0 even for e = -1e30
+        if (r < d->m && !has_up[r]) as_ok = false;                  // the active-set kernel measures every row from its upper bound
+        if (has_up[r] && has_lo[r])
+            for (int k = 0; k < nx; ++k)
+                if (Lx[(size_t)r * nx + k] != Ux[(size_t)r * nx + k]) as_ok = false;   // ... and needs a constant width
+    }
+    if (!as_ok) {
+        delete q;
+        return fail("rtmpc_qp_create: every row needs an upper bound and two-sided rows the same x_init dependence on "
+                    "both sides (Lx == Ux), as produced by rtmpc_b200.condense");
     }
     // packet payload map from the scaled decision (unscaling and the steady-state gain folded in)
     const int nrow = (d->N + 1) * d->nu, ou = nx * (d->N + 1), oxb = ou + d->N * d->nu, oub = oxb + nx;
@@ -196,12 +207,13 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
     rc |= upload(q, GT.data(), GT.size(), &P.GT);
     rc |= upload(q, Zx.data(), Zx.size(), &P.Zx);
     rc |= upload(q, Zr.data(), Zr.size(), &P.Zr);
-    rc |= upload(q, TxT.data(), TxT.size(), &P.TxT);
+    rc |= upload(q, ExT.data(), ExT.size(), &P.ExT);
     rc |= upload(q, TrT.data(), TrT.size(), &P.TrT);
     rc |= upload(q, UxT.data(), UxT.size(), &P.UxT);
     rc |= upload(q, LxT.data(), LxT.size(), &P.LxT);
     rc |= upload(q, upI.data(), upI.size(), &P.upI);
     rc |= upload(q, loI.data(), loI.size(), &P.loI);
+    rc |= upload(q, wid.data(), wid.size(), &P.wid);
     rc |= upload(q, UPhiT.data(), UPhiT.size(), &P.UPhiT);
     rc |= upload(q, UPsiT.data(), UPsiT.size(), &P.UPsiT);
     if (rc) { rtmpc_qp_destroy(q); return -1; }

@@ -38,9 +38,10 @@ struct QPDev {
     const double* W;         // [mpad*mpad]  G Hinv G'
     const double* GT;        // [npad*mpad]  G transposed (coalesced row-value recomputation)
     const double *Zx, *Zr;   // [npad*nx]    z_u = Zx x_init + Zr ref    (= -Hinv Fx, -Hinv Fr)
-    const double *TxT, *TrT; // [nx*mpad]    G z_u = Tx x_init + Tr ref, transposed
+    const double *ExT, *TrT; // [nx*mpad]    G z_u - up = Ex x_init + Tr ref - up0  (Ex = Tx - Ux), transposed
     const double *UxT, *LxT; // [nx*mpad]    Ux, Lx transposed
     const double *upI, *loI; // [mpad]       up0 / lo0 with +-1e30 where the row has no such bound
+    const double* wid;       // [mpad]       up - lo (independent of x_init), 3e30 where the row has no lower bound
     const double *UPhiT, *UPsiT;   // [npad*(N+1)nu], [nx*(N+1)nu]  packet payload from the scaled decision:
                                    // U_t = UPhi z + UPsi x_init, last column u_bar + K x_bar folded in
     const int* shift;        // [mpad] warm-start map: same constraint one stage earlier, -1 = none

@@ -7,6 +7,8 @@
 // single launch: no per-step launch latency and no waiting for the slowest instance of every step.
 // An instance whose solve has to be handed to the interior-point kernel parks itself (inst_t, pending,
 // ref_pending); the host runs that kernel on the parked instances and relaunches, which resumes them.
+#include <cstdlib>
+
 #include "rtmpc_as.cuh"
 #include "rtmpc_launch.h"
 #include "rtmpc_loop.cuh"
@@ -50,7 +52,7 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a) {
             } else {
                 ASCounters cnt;
                 cnt.steps = 0; cnt.rounds = 0; cnt.rows = 0; cnt.sq = 0;
-                status = as_solve_instance<R2>(P, w, lane, L.x_hat + (size_t)inst * nx, ref_t, warm_inst, z_inst,
+                status = as_solve_instance<R2, (MAXW * R2 <= 100) ? 2 : 1>(P, w, lane, L.x_hat + (size_t)inst * nx, ref_t, warm_inst, z_inst,
                                                U_inst, cnt);
                 n_steps += cnt.steps; n_rounds += cnt.rounds; n_flops += as_flops(P, cnt, z_inst != nullptr);
                 if (status == RTMPC_FALLBACK) {
@@ -100,11 +102,17 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a) {
 typedef void (*ro_fn)(QPDev, LoopDev, RolloutArgs);
 struct RoChoice { int r2, maxw; ro_fn fn; };
 static const RoChoice kRo[] = {
-    {2, 24, rollout_kernel<2, 24>},  {5, 16, rollout_kernel<5, 16>},  {9, 12, rollout_kernel<9, 12>},
-    {12, 10, rollout_kernel<12, 10>}, {16, 8, rollout_kernel<16, 8>},
+    {2, 32, rollout_kernel<2, 32>},  {5, 28, rollout_kernel<5, 28>},  {9, 20, rollout_kernel<9, 20>},
+    {12, 16, rollout_kernel<12, 16>}, {16, 12, rollout_kernel<16, 12>},
 };
+static const RoChoice kRoExp[] = {{5, 20, rollout_kernel<5, 20>}, {5, 16, rollout_kernel<5, 16>}};
 static const RoChoice* pick(int mpad) {
     const int r_need = (mpad + 63) / 64;
+    const char* v = getenv("RTMPC_RO_MAXW");       // experiment knob
+    const int want = v ? atoi(v) : 0;
+    if (want && r_need == 5)
+        for (const auto& c : kRoExp)
+            if (c.maxw == want) return &c;
     for (const auto& c : kRo)
         if (c.r2 >= r_need) return &c;
     return nullptr;

@@ -269,7 +269,10 @@ def _merge_two_sided(Gi, h0, hx):
         used[i] = True
         mate = None
         for j in groups[key[i].tobytes()]:
-            if not used[j] and sign[j] == -sign[i] and abs(nrm[j] - nrm[i]) <= 1e-9 * nrm[i]:
+            # (the x_init dependence has to be opposite as well: a merged row then has a constant width
+            #  up - lo, which the active-set kernel relies on)
+            if not used[j] and sign[j] == -sign[i] and abs(nrm[j] - nrm[i]) <= 1e-9 * nrm[i] and \
+                    np.abs(hx[j] + hx[i]).max(initial=0.0) <= 1e-12 * (1.0 + np.abs(hx[i]).max(initial=0.0)):
                 mate = j
                 break
         if mate is not None:
@@ -287,7 +290,7 @@ def _merge_two_sided(Gi, h0, hx):
         Ux[r] = hx[i]
         if j is not None:
             lo0[r] = -h0[j]
-            Lx[r] = -hx[j]
+            Lx[r] = hx[i]
     return G, lo0, up0, Lx, Ux, [i for i, _ in out_rows]
 
 
