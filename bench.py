@@ -325,7 +325,7 @@ def run_gpu_arm(args):
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": "rollout_kernel<9,28> (active-set QP + closed-loop step per control step; ipm_solve_kernel<3,9> on handed-over instances)",
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": "rollout_kernel<5,16> (dual active-set QP + closed-loop step, one warp per instance for all T steps; ipm_solve_kernel on handed-over instances)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure; "

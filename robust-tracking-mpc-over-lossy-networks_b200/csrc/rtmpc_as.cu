@@ -11,10 +11,10 @@ typedef void (*as_fn)(QPDev, int, const double*, const double*, const int*, int,
 struct AsChoice { int r2, maxw; as_fn fn; };
 // R2 pairs of rows per lane (mpad = 64 R2); MAXW = resident warps per SM the register budget is sized for
 static const AsChoice kAs[] = {
-    {2, 32, as_solve_kernel<2, 32>},  {5, 28, as_solve_kernel<5, 28>},  {9, 20, as_solve_kernel<9, 20>},
-    {12, 16, as_solve_kernel<12, 16>}, {16, 12, as_solve_kernel<16, 12>},
+    {2, 24, as_solve_kernel<2, 24>},  {5, 20, as_solve_kernel<5, 20>},  {9, 16, as_solve_kernel<9, 16>},
+    {12, 16, as_solve_kernel<12, 16>}, {16, 16, as_solve_kernel<16, 16>},
 };
-static const AsChoice kAsExp[] = {{5, 16, as_solve_kernel<5, 16>}, {5, 20, as_solve_kernel<5, 20>}, {5, 24, as_solve_kernel<5, 24>}};
+static const AsChoice kAsExp[] = {{5, 16, as_solve_kernel<5, 16>}, {5, 24, as_solve_kernel<5, 24>}};
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);

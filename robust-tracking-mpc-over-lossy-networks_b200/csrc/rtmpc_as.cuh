@@ -403,6 +403,8 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
             }
             resid = sl.sa * (a0 + a1) - ba;
         }
+        // converged (every active row on its bound to well below the certificate's tolerance): stop refining
+        if (pass >= 1 && !(as_wmax(fabs(resid)) > 1e-3 * tolp)) break;
     }
     cnt.rounds += 1;
     // exact row values at z:  e = G z - up through the transposed copies (coalesced 16-byte loads)

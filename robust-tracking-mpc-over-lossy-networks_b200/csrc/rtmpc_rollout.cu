@@ -102,10 +102,10 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a) {
 typedef void (*ro_fn)(QPDev, LoopDev, RolloutArgs);
 struct RoChoice { int r2, maxw; ro_fn fn; };
 static const RoChoice kRo[] = {
-    {2, 32, rollout_kernel<2, 32>},  {5, 28, rollout_kernel<5, 28>},  {9, 20, rollout_kernel<9, 20>},
-    {12, 16, rollout_kernel<12, 16>}, {16, 12, rollout_kernel<16, 12>},
+    {2, 24, rollout_kernel<2, 24>},  {5, 16, rollout_kernel<5, 16>},  {9, 16, rollout_kernel<9, 16>},
+    {12, 16, rollout_kernel<12, 16>}, {16, 16, rollout_kernel<16, 16>},
 };
-static const RoChoice kRoExp[] = {{5, 20, rollout_kernel<5, 20>}, {5, 16, rollout_kernel<5, 16>}};
+static const RoChoice kRoExp[] = {{5, 20, rollout_kernel<5, 20>}, {5, 28, rollout_kernel<5, 28>}};
 static const RoChoice* pick(int mpad) {
     const int r_need = (mpad + 63) / 64;
     const char* v = getenv("RTMPC_RO_MAXW");       // experiment knob
