@@ -188,6 +188,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from rtmpc_b200 import _lib
+    from rtmpc_b200 import distributed as D
     from rtmpc_b200.rollout import RemoteLoop
 
     rank = int(os.environ.get("RANK", "0"))
@@ -201,9 +202,9 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     mpc, Z = build_controller()
-    B, T = B_PER_GPU, T_STEPS
+    B, T = args.instances, T_STEPS
     loop = RemoteLoop(mpc, B, kind="tube", w_half=HW, Z=Z)
-    ids0 = rank * B
+    ids0, _ = D.shard(B * world, rank, world)          # weak scaling: B instances per rank, global ids
     p_loss = torch.as_tensor(np.array([0.1 * ((ids0 + i) % 10) for i in range(B)]), device=dev)
     ref_d = torch.as_tensor(np.tile(REF, (B, 1)), device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)    # > 126 MB L2
@@ -253,17 +254,12 @@ def run_gpu_arm(args):
     launches = L.rtmpc_launch_count() - launches0
     err = loop.tracking_error(T)
     tube_max = float(loop.tube_max.max().item())
-    t_ms = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        gathered = [torch.empty_like(err) for _ in range(world)]
-        g0 = time.perf_counter()
-        dist.all_gather(gathered, err)              # the only collective: statistics after the timed region
-        torch.cuda.synchronize()
-        gather_ms = (time.perf_counter() - g0) * 1e3
-        err_all = torch.cat(gathered)
-    else:
-        gather_ms, err_all = 0.0, err
+    t_ms = D.all_reduce_max(torch.tensor([total_ms], device=dev, dtype=torch.float64))
+    g0 = time.perf_counter()
+    err_all = D.all_gather_instances(err, B * world)     # the only collectives: statistics after the timed region
+    status_all = D.all_reduce_sum(torch.as_tensor(status_sum, device=dev)).cpu().numpy()
+    torch.cuda.synchronize()
+    gather_ms = (time.perf_counter() - g0) * 1e3 if world > 1 else 0.0
     total_ms_max = float(t_ms.item())
     solves = B * T * args.steps
     value = solves * world / (total_ms_max * 1e-3)
@@ -295,9 +291,7 @@ def run_gpu_arm(args):
         for k in range(ksteps):
             rollout_host(SEED + k)
         barrier()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = D.all_reduce_max(torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64))
         e2e = {"value": B * T * ksteps * world / float(dt.item()), "unit": "solves/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "api": "RemoteLoop.reset(host x0) + RemoteLoop.run(T, host ref, host loss rates, record=True) -> "
@@ -305,9 +299,15 @@ def run_gpu_arm(args):
                       "back to pinned host memory, wall clock"}
 
     if rank == 0:
-        peaks = {}
+        peaks, traffic = {}, None
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        try:
+            # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of this workload, from the
+            # committed `ncu --set full` capture (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "rollout_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
         flops = as_flops + f_it * int(iters_sum[0])      # rank 0's timed region: active-set kernel + IPM fallback
@@ -327,7 +327,7 @@ def run_gpu_arm(args):
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": "rollout_kernel<5,16> (dual active-set QP + closed-loop step, one warp per instance for all T steps; ipm_solve_kernel on handed-over instances)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure; "
                                         f"its hbm_gbs={peaks.get('hbm_gbs')}, bf16_tflops={peaks.get('bf16_tflops')})",
                          "algorithmic_flops_active_set": as_flops, "flops_per_ipm_iteration": f_it,
@@ -339,7 +339,7 @@ def run_gpu_arm(args):
             "cpu_baseline": {"value": cpu_value, "unit": "solves/s", "cores": cores, "kind": "port",
                              "sample": f"{cpu_n} QP solves of the same workload (states of the golden closed-loop runs at "
                                        "loss 0/0.3/0.6/0.9), oracle IPM + certified polish, one process per core"},
-            "checks": {"status_counts[optimal,max_iter,infeasible,inaccurate]": status_sum.tolist(),
+            "checks": {"status_counts[optimal,max_iter,infeasible,inaccurate]": status_all.tolist(),
                        "max_tube_violation": tube_max, "mean_tracking_error": float(err_all.mean().item()),
                        "stats_all_gather_ms": gather_ms},
         }
@@ -377,6 +377,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-solves", type=int, default=1024, dest="cpu_solves")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
+    ap.add_argument("--instances", type=int, default=B_PER_GPU, help="closed-loop instances per GPU (BASELINE configs[1]: 4096)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -128,6 +128,9 @@ int rtmpc_qp_warm_reset(rtmpc_qp* qp);
 
 /* RTMPC_METHOD_*: which kernel rtmpc_qp_solve runs (default: active set + interior-point fallback) */
 int rtmpc_qp_set_method(rtmpc_qp* qp, int32_t method);
+/* active-set steps (rows added + dropped) after which an instance is handed to the interior-point kernel;
+ * <= 0 restores the default 8*npad + 32.  The result does not depend on it, only which kernel produces it. */
+int rtmpc_qp_set_step_cap(rtmpc_qp* qp, int32_t max_steps);
 /* device counter (or NULL) to which the active-set kernel adds the algorithmic FP64 flops it executes
  * (bench.py's roofline numerator) */
 int rtmpc_qp_set_work_counter(rtmpc_qp* qp, uint64_t* d_counter);

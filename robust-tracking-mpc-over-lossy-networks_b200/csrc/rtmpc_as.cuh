@@ -629,7 +629,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             }
         }
         // ---- 2./3. Goldfarb-Idnani, then certification -----------------------------------------
-        const int max_steps = 8 * npad + 32;
+        const int max_steps = P.as_max_steps;
 #pragma unroll 1
         for (int refresh = 0;; ++refresh) {
             status = as_gi<R2, ILP>(P, w, amask, sl, lane, e, actu, actl, tolp, max_steps, apply, cnt);

@@ -47,6 +47,7 @@ struct QPDev {
     const int* shift;        // [mpad] warm-start map: same constraint one stage earlier, -1 = none
     double s_floor, sc_b;
     int max_iter;
+    int as_max_steps;     // active-set steps (rows added + dropped) before an instance is handed to the interior-point kernel
 };
 
 // per-warp shared memory, in doubles

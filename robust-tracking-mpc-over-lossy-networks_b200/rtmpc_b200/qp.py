@@ -65,6 +65,10 @@ class BatchedQP:
         m = {"active_set": _lib.METHOD_ACTIVE_SET, "interior_point": _lib.METHOD_INTERIOR_POINT}[method]
         _lib.check(self._L.rtmpc_qp_set_method(self._h, m), "rtmpc_qp_set_method")
 
+    def set_step_cap(self, max_steps):
+        """Active-set steps after which an instance goes to the interior-point kernel (<= 0: default)."""
+        _lib.check(self._L.rtmpc_qp_set_step_cap(self._h, int(max_steps)), "rtmpc_qp_set_step_cap")
+
     def set_work_counter(self, counter):
         """uint64 device tensor (1 element) accumulating the active-set kernel's algorithmic flops, or None."""
         _lib.check(self._L.rtmpc_qp_set_work_counter(self._h, _lib.ptr(counter)), "rtmpc_qp_set_work_counter")

@@ -205,3 +205,25 @@ def test_fused_rollout_matches_golden_and_stepwise_bit_for_bit():
             assert np.array_equal(a, b)
         if kind == "tube":
             assert out[True][7][0] == 1000
+
+
+def test_fused_rollout_with_instances_handed_to_the_interior_point_kernel():
+    """A tiny active-set step cap forces most constrained solves through the hand-over path (instance parks,
+    interior-point kernel solves its step, rollout resumes): same closed loop within the parity tolerance."""
+    from rtmpc_b200.rollout import RemoteLoop
+    s, g = H.load("sets_cp.npz"), H.load("loop_cp_tube.npz")
+    mpc = H.make_tube_mpc(s)
+    mpc._prob.set_step_cap(2)
+    try:
+        for fused in (True, False):
+            loop = RemoteLoop(mpc, 4, kind="tube", Z=H.poly(s, "Z"))
+            loop.reset(np.zeros((4, 4)))
+            tr = loop.run(250, g["refs"], theta=g["theta"].T, gamma=g["gamma"].T, w=np.transpose(g["w"], (1, 0, 2)),
+                          record=True, fused=fused).cpu().numpy()
+            assert np.abs(tr - g["tube_x"]).max() <= TOL
+            assert np.abs(loop.x_hat.cpu().numpy() - g["tube_x_hat"][:, -1]).max() <= TOL
+            assert loop.status_count[0].item() == 1000
+            assert loop.iters_total[0].item() > 1000          # interior-point iterations were needed
+            assert loop.tube_max.max().item() < 1e-7
+    finally:
+        mpc._prob.set_step_cap(0)
