@@ -707,7 +707,8 @@ as_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double*
     ASWarp w = as_carve(smem + (size_t)warp * as_warp_doubles(P), P);
     const size_t usz = (size_t)(P.N + 1) * P.nu;
 #pragma unroll 1
-    for (int inst = blockIdx.x * wpb + warp; inst < B; inst += gridDim.x * wpb) {
+    // consecutive instances go to different SMs, so a last partial round is spread over all of them
+    for (int inst = warp * gridDim.x + blockIdx.x; inst < B; inst += gridDim.x * wpb) {
         if (sel && sel[inst] != sel_value) continue;
         ASCounters cnt;
         cnt.steps = 0; cnt.rounds = 0; cnt.rows = 0; cnt.sq = 0;

@@ -28,6 +28,46 @@ struct LoopDev {
     int *q_t, *s_t, *Theta, *alive, *last_loss, *gamma_last;
 };
 
+// Where the per-instance state lives: the step-by-step kernels keep it in global memory (LoopDev's arrays,
+// instance b); the rollout kernel keeps it in a per-warp block of shared memory for all T steps.
+struct LoopGlobalState {
+    const LoopDev* L;
+    int b;
+    __device__ __forceinline__ double& x(int k) const { return L->x[(size_t)b * L->nx + k]; }
+    __device__ __forceinline__ double& x_nom(int k) const { return L->x_nom[(size_t)b * L->nx + k]; }
+    __device__ __forceinline__ double& x_hat(int k) const { return L->x_hat[(size_t)b * L->nx + k]; }
+    __device__ __forceinline__ double& u_last(int j) const { return L->u_last[(size_t)b * L->nu + j]; }
+    __device__ __forceinline__ double* buf() const { return L->buf + (size_t)b * (L->N + 1) * L->nu; }
+    __device__ __forceinline__ double& err_acc() const { return L->err_acc[b]; }
+    __device__ __forceinline__ double& tube_max() const { return L->tube_max[b]; }
+    __device__ __forceinline__ int& q_t() const { return L->q_t[b]; }
+    __device__ __forceinline__ int& s_t() const { return L->s_t[b]; }
+    __device__ __forceinline__ int& Theta() const { return L->Theta[b]; }
+    __device__ __forceinline__ int& alive() const { return L->alive[b]; }
+    __device__ __forceinline__ int& last_loss() const { return L->last_loss[b]; }
+    __device__ __forceinline__ int& gamma_last() const { return L->gamma_last[b]; }
+};
+// shared-memory block: x[8] x_nom[8] x_hat[8] u_last[4] err_acc tube_max | 6 ints (+2 pad) | buf[(N+1) nu]
+constexpr int LOOP_SMEM_FIXED = 3 * LOOP_MAX_NX + LOOP_MAX_NU + 2 + 4;
+__host__ __device__ inline int loop_smem_doubles(int N, int nu) { return LOOP_SMEM_FIXED + (((N + 1) * nu + 1) & ~1); }
+struct LoopSmemState {
+    double* base;
+    __device__ __forceinline__ double& x(int k) const { return base[k]; }
+    __device__ __forceinline__ double& x_nom(int k) const { return base[LOOP_MAX_NX + k]; }
+    __device__ __forceinline__ double& x_hat(int k) const { return base[2 * LOOP_MAX_NX + k]; }
+    __device__ __forceinline__ double& u_last(int j) const { return base[3 * LOOP_MAX_NX + j]; }
+    __device__ __forceinline__ double& err_acc() const { return base[3 * LOOP_MAX_NX + LOOP_MAX_NU]; }
+    __device__ __forceinline__ double& tube_max() const { return base[3 * LOOP_MAX_NX + LOOP_MAX_NU + 1]; }
+    __device__ __forceinline__ int* ints() const { return reinterpret_cast<int*>(base + 3 * LOOP_MAX_NX + LOOP_MAX_NU + 2); }
+    __device__ __forceinline__ int& q_t() const { return ints()[0]; }
+    __device__ __forceinline__ int& s_t() const { return ints()[1]; }
+    __device__ __forceinline__ int& Theta() const { return ints()[2]; }
+    __device__ __forceinline__ int& alive() const { return ints()[3]; }
+    __device__ __forceinline__ int& last_loss() const { return ints()[4]; }
+    __device__ __forceinline__ int& gamma_last() const { return ints()[5]; }
+    __device__ __forceinline__ double* buf() const { return base + LOOP_SMEM_FIXED; }
+};
+
 static __device__ __noinline__ void cartpole_substeps(double* x, double F, const double* c) {
     const double M = c[0], m = c[1], I = c[2], g = c[3], l = c[4], dt = c[5];
     const int nsub = (int)c[6];
@@ -48,13 +88,13 @@ static __device__ __noinline__ void cartpole_substeps(double* x, double F, const
 }
 
 // tube containment statistic  max_i (Hz (x - x_nom) - hz)_i  of instance b, rows i = first, first+stride, ...
-template <int NX>
-__device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, int b, int first, int stride) {
+template <int NX, class State>
+__device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, const State S, int first, int stride) {
     const int nx = NX ? NX : L.nx;
     constexpr int AX = NX ? NX : LOOP_MAX_NX;
     double d[AX];
 #pragma unroll
-    for (int k = 0; k < AX; ++k) d[k] = (k < nx) ? L.x[(size_t)b * nx + k] - L.x_nom[(size_t)b * nx + k] : 0.0;
+    for (int k = 0; k < AX; ++k) d[k] = (k < nx) ? S.x(k) - S.x_nom(k) : 0.0;
     double worst = -1e300;
 #pragma unroll 4
     for (int i = first; i < L.nz_rows; i += stride) {
@@ -65,20 +105,22 @@ __device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, int b, int 
     }
     return worst;
 }
-__device__ __forceinline__ double loop_tube_rows(const LoopDev& L, int b, int first, int stride) {
-    if (L.nx == 4) return loop_tube_rows_t<4>(L, b, first, stride);
-    if (L.nx == 2) return loop_tube_rows_t<2>(L, b, first, stride);
-    return loop_tube_rows_t<0>(L, b, first, stride);
+template <class State>
+__device__ __forceinline__ double loop_tube_rows(const LoopDev& L, const State S, int first, int stride) {
+    if (L.nx == 4) return loop_tube_rows_t<4>(L, S, first, stride);
+    if (L.nx == 2) return loop_tube_rows_t<2>(L, S, first, stride);
+    return loop_tube_rows_t<0>(L, S, first, stride);
 }
 
 // Start of a control step for instance b: records x_0, retires the instance when the controller
 // returned None.  Returns false when the instance takes no step.
-__device__ __forceinline__ bool loop_step_begin(const LoopDev& L, int b, int t, int status_b, double* traj_b) {
-    if (!L.alive[b]) return false;
+template <class State>
+__device__ __forceinline__ bool loop_step_begin(const LoopDev& L, const State S, int t, int status_b, double* traj_b) {
+    if (!S.alive()) return false;
     const int nx = L.nx;
-    if (traj_b && t == 0) for (int k = 0; k < nx; ++k) traj_b[k] = L.x[(size_t)b * nx + k];
+    if (traj_b && t == 0) for (int k = 0; k < nx; ++k) traj_b[k] = S.x(k);
     // controller returned None (infeasible): the reference stops this controller's run
-    if (status_b == RTMPC_INFEASIBLE) { L.alive[b] = 0; return false; }
+    if (status_b == RTMPC_INFEASIBLE) { S.alive() = 0; return false; }
     return true;
 }
 
@@ -91,8 +133,8 @@ static __device__ __noinline__ Philox4 loop_philox(uint32_t c0, uint32_t c1, uin
     return philox4x32_10(c0, c1, c2, c3, k0, k1);
 }
 
-template <int NX, int NU>
-static __device__ __noinline__ void loop_step_body_t(const LoopDev& L, int b, int t, const double* Ub,
+template <int NX, int NU, class State>
+static __device__ __noinline__ void loop_step_body_t(const LoopDev& L, const State S, int t, const double* Ub,
                                                      const double* x_nom0_b, const double* ref_b, int theta_in,
                                                      int gamma_in, const double* w_in_b, double p,
                                                      unsigned long long seed, unsigned long long id, double* traj_b,
@@ -101,17 +143,17 @@ static __device__ __noinline__ void loop_step_body_t(const LoopDev& L, int b, in
     constexpr int AX = NX ? NX : LOOP_MAX_NX, AU = NU ? NU : LOOP_MAX_NU;
     double x[AX], xn[AX], xh[AX], w[AX];
     for (int k = 0; k < nx; ++k) {
-        x[k] = L.x[(size_t)b * nx + k];
-        xn[k] = L.x_nom[(size_t)b * nx + k];
-        xh[k] = L.x_hat[(size_t)b * nx + k];
+        x[k] = S.x(k);
+        xn[k] = S.x_nom(k);
+        xh[k] = S.x_hat(k);
     }
     // statistics on the pre-step state (x_traj[:, t] in the reference's scripts)
     if (ref_b) {
         double e = 0.0;
         for (int k = 0; k < nx; ++k) { double d = x[k] - ref_b[k]; e = fma(d, d, e); }
-        L.err_acc[b] += e;
+        S.err_acc() += e;
     }
-    if (L.nz_rows > 0) L.tube_max[b] = fmax(L.tube_max[b], tube_worst);
+    if (L.nz_rows > 0) S.tube_max() = fmax(S.tube_max(), tube_worst);
 
     // network and disturbance realisation
     int theta, gamma;
@@ -132,13 +174,13 @@ static __device__ __noinline__ void loop_step_body_t(const LoopDev& L, int b, in
     }
 
     // ---- local side ---------------------------------------------------------------------
-    const int q_pkt = L.q_t[b];                 // q_t carried by the controller packet
-    int last_loss = L.last_loss[b];
+    const int q_pkt = S.q_t();                 // q_t carried by the controller packet
+    int last_loss = S.last_loss();
     int Theta = 0;
     if (theta == 1) Theta = (last_loss <= q_pkt) ? 1 : 0;
     else last_loss = t;
-    int s_t = L.s_t[b];
-    double* buf = L.buf + (size_t)b * (N + 1) * nu;
+    int s_t = S.s_t();
+    double* buf = S.buf();
     if (Theta) {
         s_t = t;
         for (int i = 0; i < (N + 1) * nu; ++i) buf[i] = Ub[i];
@@ -231,30 +273,31 @@ static __device__ __noinline__ void loop_step_body_t(const LoopDev& L, int b, in
     }
     // ---- write back -----------------------------------------------------------------------
     for (int k = 0; k < nx; ++k) {
-        L.x[(size_t)b * nx + k] = xnew[k];
-        L.x_nom[(size_t)b * nx + k] = xn[k];
-        L.x_hat[(size_t)b * nx + k] = xhn[k];
+        S.x(k) = xnew[k];
+        S.x_nom(k) = xn[k];
+        S.x_hat(k) = xhn[k];
     }
-    for (int j = 0; j < nu; ++j) L.u_last[(size_t)b * nu + j] = u[j];
-    if (gamma == 1) L.q_t[b] = t;
-    L.s_t[b] = s_t;
-    L.Theta[b] = Theta;
-    L.last_loss[b] = last_loss;
-    L.gamma_last[b] = gamma;
+    for (int j = 0; j < nu; ++j) S.u_last(j) = u[j];
+    if (gamma == 1) S.q_t() = t;
+    S.s_t() = s_t;
+    S.Theta() = Theta;
+    S.last_loss() = last_loss;
+    S.gamma_last() = gamma;
     if (traj_b) for (int k = 0; k < nx; ++k) traj_b[(size_t)(t + 1) * nx + k] = xnew[k];
 }
 
 // sizes known at compile time for the reference's two systems (double integrator, cartpole), generic otherwise
-__device__ __forceinline__ void loop_step_body(const LoopDev& L, int b, int t, const double* Ub, const double* x_nom0_b,
+template <class State>
+__device__ __forceinline__ void loop_step_body(const LoopDev& L, const State S, int t, const double* Ub, const double* x_nom0_b,
                                                const double* ref_b, int theta_in, int gamma_in, const double* w_in_b,
                                                double p, unsigned long long seed, unsigned long long id, double* traj_b,
                                                double tube_worst) {
     if (L.nx == 4 && L.nu == 1)
-        loop_step_body_t<4, 1>(L, b, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
+        loop_step_body_t<4, 1>(L, S, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
     else if (L.nx == 2 && L.nu == 1)
-        loop_step_body_t<2, 1>(L, b, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
+        loop_step_body_t<2, 1>(L, S, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
     else
-        loop_step_body_t<0, 0>(L, b, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
+        loop_step_body_t<0, 0>(L, S, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
 }
 
 #ifdef RTMPC_LOOP_KERNELS   // the non-template kernels are compiled in one translation unit (rtmpc_capi.cu)
@@ -269,9 +312,11 @@ __global__ void loop_step_kernel(LoopDev L, int B, int t, const double* __restri
     if (b >= B) return;
     const int nx = L.nx, nu = L.nu, N = L.N;
     double* traj_b = traj ? traj + (size_t)b * traj_stride : nullptr;
-    if (!loop_step_begin(L, b, t, status ? status[b] : RTMPC_OPTIMAL, traj_b)) return;
-    const double worst = (L.nz_rows > 0) ? loop_tube_rows(L, b, 0, 1) : 0.0;
-    loop_step_body(L, b, t, U_t + (size_t)b * (N + 1) * nu, x_nom0 ? x_nom0 + (size_t)b * x_nom0_stride : nullptr,
+    LoopGlobalState S;
+    S.L = &L; S.b = b;
+    if (!loop_step_begin(L, S, t, status ? status[b] : RTMPC_OPTIMAL, traj_b)) return;
+    const double worst = (L.nz_rows > 0) ? loop_tube_rows(L, S, 0, 1) : 0.0;
+    loop_step_body(L, S, t, U_t + (size_t)b * (N + 1) * nu, x_nom0 ? x_nom0 + (size_t)b * x_nom0_stride : nullptr,
                    ref ? ref + (size_t)b * nx : nullptr, theta_in ? theta_in[b] : -1, theta_in ? gamma_in[b] : -1,
                    w_in ? w_in + (size_t)b * nx : nullptr, p_loss ? p_loss[b] : 0.0, seed,
                    (unsigned long long)(id_offset + b), traj_b, worst);
