@@ -149,3 +149,33 @@ def test_full_size_properties_4096():
     assert np.array_equal(U[:1000][:96], U[1000:2000][:96])             # determinism across warps / CTAs
     x = z[:, :84].reshape(-1, 21, 4)[:, :20]
     assert (x.reshape(-1, 4) @ s["Xc_A"].T - s["Xc_b"]).max() <= 1e-8
+
+
+def test_active_set_kernel_against_interior_point_kernel_on_random_instances():
+    """Two independent GPU implementations (dual active set with KKT certificate; Mehrotra interior point with
+    active-set endgame) on random parameters, including infeasible ones: same classification, same minimiser."""
+    from rtmpc_b200.qp import BatchedQP
+    sd, sc = H.load("sets_di.npz"), H.load("sets_cp.npz")
+    cases = [("di_tube", H.spec_tube_tracking(sd), sd["K"], np.array([9.0, 3.0]), 9.0, 4000),
+             ("cp_tube_near", H.spec_tube_tracking(sc), sc["K"], np.array([1.0, 1.0, 0.05, 0.3]), 1.0, 4000),
+             ("cp_tube_far", H.spec_tube_tracking(sc), sc["K"], np.array([5.0, 4.0, 0.1, 1.2]), 5.0, 2000),
+             ("cp_ext_recv", H.spec_ext_received(sc), sc["K"], np.array([1.0, 1.0, 0.05, 0.3]), 1.0, 2000)]
+    for name, spec, K, box, rbox, B in cases:
+        rng = np.random.default_rng(11)
+        nx = len(box)
+        X = rng.uniform(-1, 1, (B, nx)) * box
+        R = np.zeros((B, nx))
+        R[:, 0] = rng.uniform(-rbox, rbox, B)
+        qp = BatchedQP(spec, Kss=K)
+        z1, U1, s1, i1 = qp.solve_host(X, R)
+        qp.set_method("interior_point")
+        z2, U2, s2, i2 = qp.solve_host(X, R)
+        assert not np.any((s1 == 2) & np.isin(s2, (0, 3))), name          # never "infeasible" where the other solves
+        assert not np.any((s1 == 0) & (s2 == 2)), name
+        both = (s1 == 0) & (s2 == 0)
+        assert both.sum() > B // 10, name
+        err = np.abs(U1[both] - U2[both]).reshape(both.sum(), -1).max(1)
+        scale = np.maximum(1.0, np.abs(U2[both]).reshape(both.sum(), -1).max(1))
+        assert (err / scale).max() <= TOL_TIGHT, (name, (err / scale).max())
+        # the active-set path certifies at least as many instances as the interior-point path
+        assert np.count_nonzero(s1 == 0) >= np.count_nonzero(s2 == 0), name
