@@ -76,7 +76,8 @@ typedef struct rtmpc_qp_desc {
     double s_floor;         /* smallest initial slack (scaled units)                             */
     double sc_b;            /* 1 + typical |bound| (scaled units)                                */
     int32_t max_iter;       /* interior-point iteration cap (Clarabel default 200; we use 60)    */
-    int32_t reserved;
+    int32_t min_rows;       /* pad the rows at least to this count (0: as few as possible); two problems
+                               that one rollout switches between need the same count, see rtmpc_qp_rows */
     const int32_t* shift;   /* [mpad] row holding the same constraint one stage earlier (-1: none),
                                used to move a warm-start active set one control step on; or NULL    */
 } rtmpc_qp_desc;
@@ -116,6 +117,7 @@ int rtmpc_qp_solve(rtmpc_qp* qp, int32_t B, const double* d_x_init, const double
                    const int32_t* d_sel, int32_t sel_value, int32_t* d_warm, double* d_z, double* d_U_t,
                    int32_t* d_status, int32_t* d_iters, void* stream);
 int32_t rtmpc_qp_warm_stride(rtmpc_qp* qp);     /* int32 entries per instance of d_warm (npad + 1) */
+int32_t rtmpc_qp_rows(rtmpc_qp* qp);            /* rows the kernels work on (m padded to a multiple of 64) */
 
 /* Same call with HOST buffers: copies in, solves, copies out, synchronises.  This is the
  * reference-facing plugin call (numpy arrays in, numpy arrays out).  warm != 0 keeps the
@@ -211,6 +213,10 @@ int rtmpc_loop_step(rtmpc_loop* loop, const double* d_U_t, const int32_t* d_stat
  * smart actuator) followed by the step of rtmpc_loop_step.  One warp owns one instance for all T
  * steps; x_hat feeds the next solve on chip and each solve is warm-started from the previous one.
  *   qp       the controller's problem (default method RTMPC_METHOD_ACTIVE_SET); sizes must match
+ *   qp_received  NULL, or for RTMPC_ACT_EXTENDED the "packet received" problem of ExtendedTubeTrackingMPC
+ *            (TubeTrackingMPC.py:253-299): each step solves it instead of qp where gamma_{t-1} = 1 (:307-349) and
+ *            the packet's x_nom_0 resets the local nominal state (SmartActuator.py:219-222); both problems must be
+ *            padded to the same row count (rtmpc_qp_desc.min_rows)
  *   d_ref    reference of instance b at step k (0-based within this call) at
  *            d_ref[k*ref_stride_t + b*ref_stride_b + 0..nx)  (strides in doubles; 0 = shared)
  *   d_theta, d_gamma [T*B], d_w [T*B*nx]: explicit realisations, or NULL for the device RNG of
@@ -219,10 +225,9 @@ int rtmpc_loop_step(rtmpc_loop* loop, const double* d_U_t, const int32_t* d_stat
  *   d_stats  [8] uint64 or NULL, accumulated: solves by status [4], interior-point iterations,
  *            active-set steps, certification rounds, algorithmic flops of the active-set method
  * Instances the active-set method hands over are solved by the interior-point kernel between
- * relaunches; the call synchronises `stream` before it returns.  Not available for
- * RTMPC_ACT_EXTENDED (two QPs per step): use rtmpc_qp_solve + rtmpc_loop_step there.
+ * relaunches; the call synchronises `stream` before it returns.
  */
-int rtmpc_loop_rollout(rtmpc_loop* loop, rtmpc_qp* qp, int32_t T, const double* d_ref, int64_t ref_stride_t,
+int rtmpc_loop_rollout(rtmpc_loop* loop, rtmpc_qp* qp, rtmpc_qp* qp_received, int32_t T, const double* d_ref, int64_t ref_stride_t,
                        int64_t ref_stride_b, const int32_t* d_theta, const int32_t* d_gamma, const double* d_w,
                        const double* d_p_loss, uint64_t seed, int64_t id_offset, double* d_traj_x,
                        int64_t traj_stride, uint64_t* d_stats, void* stream);

@@ -474,12 +474,12 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
 }
 
 // One instance, one warp.  x_init / ref: this instance's parameters (ref may be NULL); warm_inst: this
-// instance's warm-start record (npad + 1 ints) or NULL; z_out_inst / U_out_inst: this instance's
-// outputs or NULL.  Returns the status; on RTMPC_FALLBACK nothing has been written.
+// instance's warm-start record (npad + 1 ints) or NULL; z_out_inst (its first z_rows entries are written) /
+// U_out_inst: this instance's outputs or NULL.  Returns the status; on RTMPC_FALLBACK nothing has been written.
 // (no __restrict__ on the instance pointers: the rollout kernel writes them from the same warp)
 template <int R2, int ILP>
 __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int lane, const double* x_init,
-                                                 const double* ref, int* warm_inst, double* z_out_inst,
+                                                 const double* ref, int* warm_inst, double* z_out_inst, int z_rows,
                                                  double* U_out_inst, ASCounters& cnt) {
     const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ms = as_ms(P);
     const double tolp = 1e-11 * P.sc_b;
@@ -667,7 +667,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             if (lane < npad) w.coef()[lane] = (lane < n) ? w.z()[lane] * P.D[lane] : 0.0;   // unscaled decision
             __syncwarp();
 #pragma unroll 1
-            for (int i = lane; i < P.nz; i += 32) {
+            for (int i = lane; i < z_rows; i += 32) {      // leading rows of [x_0..x_N | u | x_bar | u_bar]
                 double acc = 0.0;
 #pragma unroll 1
                 for (int k = 0; k < n; ++k) acc = fma(P.Phi[(size_t)i * npad + k], w.coef()[k], acc);
@@ -715,7 +715,7 @@ as_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double*
         const int status = as_solve_instance<R2, (MAXW * R2 <= 100) ? 2 : 1>(P, w, lane, x_init + (size_t)inst * nx,
                                                  ref ? ref + (size_t)inst * nx : nullptr,
                                                  warm ? warm + (size_t)inst * (P.npad + 1) : nullptr,
-                                                 z_out ? z_out + (size_t)inst * P.nz : nullptr,
+                                                 z_out ? z_out + (size_t)inst * P.nz : nullptr, P.nz,
                                                  U_out ? U_out + inst * usz : nullptr, cnt);
         if (lane == 0) {
             if (status_out) status_out[inst] = status;

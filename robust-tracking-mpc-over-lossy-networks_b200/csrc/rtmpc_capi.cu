@@ -84,7 +84,7 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
         !d->has_lo || !d->has_up || !d->Dscale || !d->Phi || !d->Psi)
         return fail("rtmpc_qp_create: null matrix in the description");
     // rows are padded to what the active-set kernel's instantiation works on (a multiple of 64)
-    const int mpad = as_padded_rows(d->mpad);
+    const int mpad = as_padded_rows(d->mpad > d->min_rows ? d->mpad : d->min_rows);
     if (mpad < 0) return fail("rtmpc_qp_create: too many rows for the compiled kernel set (mpad <= 1024)");
     if (d->nss > 0 && !d->Kss) return fail("rtmpc_qp_create: Kss required when nss > 0");
     rtmpc_qp* q = new rtmpc_qp();
@@ -270,6 +270,7 @@ int rtmpc_qp_set_work_counter(rtmpc_qp* q, uint64_t* d_counter) {
 }
 
 int32_t rtmpc_qp_warm_stride(rtmpc_qp* q) { return q ? q->dev.npad + 1 : -1; }
+int32_t rtmpc_qp_rows(rtmpc_qp* q) { return q ? q->dev.mpad : -1; }
 
 int rtmpc_qp_solve(rtmpc_qp* q, int32_t B, const double* d_x_init, const double* d_ref, const int32_t* d_sel,
                    int32_t sel_value, int32_t* d_warm, double* d_z, double* d_U_t, int32_t* d_status, int32_t* d_iters,
@@ -375,8 +376,10 @@ struct rtmpc_loop {
     // scratch of rtmpc_loop_rollout
     double *r_U = nullptr, *r_ref = nullptr;
     int *r_status = nullptr, *r_iters = nullptr, *r_inst_t = nullptr, *r_pending = nullptr, *r_npend = nullptr;
-    int* r_warm = nullptr;
-    int r_warm_stride = 0;
+    int *r_warm = nullptr, *r_warm1 = nullptr;
+    int r_warm_stride = 0, r_warm1_stride = 0;
+    double* r_z = nullptr;
+    int r_z_stride = 0;
     int* h_npend = nullptr;     // pinned
 };
 
@@ -451,7 +454,7 @@ int rtmpc_loop_create(const rtmpc_loop_desc* d, int32_t B, rtmpc_loop** out) {
 void rtmpc_loop_destroy(rtmpc_loop* l) {
     if (!l) return;
     for (void* p : l->allocs) cudaFree(p);
-    cudaFree(l->r_warm);
+    cudaFree(l->r_warm); cudaFree(l->r_warm1); cudaFree(l->r_z);
     if (l->h_npend) cudaFreeHost(l->h_npend);
     delete l;
 }
@@ -476,6 +479,7 @@ int rtmpc_loop_reset(rtmpc_loop* l, const double* h_x0) {
     CU(cudaMemcpy(L.last_loss, minus.data(), B * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(L.gamma_last, ones.data(), B * sizeof(int), cudaMemcpyHostToDevice));
     if (l->r_warm) CU(cudaMemset(l->r_warm, 0xFF, B * (size_t)l->r_warm_stride * sizeof(int)));
+    if (l->r_warm1) CU(cudaMemset(l->r_warm1, 0xFF, B * (size_t)l->r_warm1_stride * sizeof(int)));
     l->t = 0;
     return 0;
 }
@@ -510,7 +514,17 @@ int rtmpc_loop_step(rtmpc_loop* l, const double* d_U_t, const int32_t* d_status,
     return 0;
 }
 
-int rtmpc_loop_rollout(rtmpc_loop* l, rtmpc_qp* q, int32_t T, const double* d_ref, int64_t ref_stride_t,
+static int ensure_warm(int** buf, int* stride, int want, size_t B, cudaStream_t s) {
+    if (*buf && *stride == want) return 0;
+    cudaFree(*buf);
+    *buf = nullptr;
+    *stride = want;
+    CU(cudaMalloc(buf, B * (size_t)want * sizeof(int)));
+    CU(cudaMemsetAsync(*buf, 0xFF, B * (size_t)want * sizeof(int), s));
+    return 0;
+}
+
+int rtmpc_loop_rollout(rtmpc_loop* l, rtmpc_qp* q, rtmpc_qp* q1, int32_t T, const double* d_ref, int64_t ref_stride_t,
                        int64_t ref_stride_b, const int32_t* d_theta, const int32_t* d_gamma, const double* d_w,
                        const double* d_p_loss, uint64_t seed, int64_t id_offset, double* d_traj_x, int64_t traj_stride,
                        uint64_t* d_stats, void* stream) {
@@ -518,24 +532,37 @@ int rtmpc_loop_rollout(rtmpc_loop* l, rtmpc_qp* q, int32_t T, const double* d_re
     if (T <= 0) return 0;
     if ((d_theta == nullptr) != (d_gamma == nullptr)) return fail("rtmpc_loop_rollout: theta and gamma must be given together");
     const QPDev& P = q->dev;
-    if (P.nx != l->dev.nx || P.nu != l->dev.nu || P.N != l->dev.N) return fail("rtmpc_loop_rollout: QP and loop sizes differ");
-    if (l->dev.actuator == RTMPC_ACT_EXTENDED) return fail("rtmpc_loop_rollout: the extended variant switches between two QPs; use rtmpc_qp_solve + rtmpc_loop_step");
-    if (q->method != RTMPC_METHOD_ACTIVE_SET) return fail("rtmpc_loop_rollout: needs RTMPC_METHOD_ACTIVE_SET");
+    const bool ext = l->dev.actuator == RTMPC_ACT_EXTENDED;
+    if (ext && !q1) return fail("rtmpc_loop_rollout: the extended variant needs the 'packet received' problem as well");
+    if (!ext && q1) return fail("rtmpc_loop_rollout: a second problem is only meaningful for RTMPC_ACT_EXTENDED");
+    const QPDev& P1 = q1 ? q1->dev : q->dev;
+    if (P.nx != l->dev.nx || P.nu != l->dev.nu || P.N != l->dev.N || P1.nx != P.nx || P1.nu != P.nu || P1.N != P.N)
+        return fail("rtmpc_loop_rollout: QP and loop sizes differ");
+    if (P1.mpad != P.mpad) return fail("rtmpc_loop_rollout: both problems must be padded to the same row count (rtmpc_qp_desc.min_rows, rtmpc_qp_rows)");
+    if (q->method != RTMPC_METHOD_ACTIVE_SET || (q1 && q1->method != RTMPC_METHOD_ACTIVE_SET))
+        return fail("rtmpc_loop_rollout: needs RTMPC_METHOD_ACTIVE_SET");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t B = l->B;
-    if (!l->r_warm || l->r_warm_stride != P.npad + 1) {
-        cudaFree(l->r_warm);
-        l->r_warm = nullptr;
-        l->r_warm_stride = P.npad + 1;
-        CU(cudaMalloc(&l->r_warm, B * (size_t)l->r_warm_stride * sizeof(int)));
-        CU(cudaMemsetAsync(l->r_warm, 0xFF, B * (size_t)l->r_warm_stride * sizeof(int), s));
+    if (ensure_warm(&l->r_warm, &l->r_warm_stride, P.npad + 1, B, s)) return -1;
+    if (q1 && ensure_warm(&l->r_warm1, &l->r_warm1_stride, P1.npad + 1, B, s)) return -1;
+    if (ext) {
+        const int nzmax = P.nz > P1.nz ? P.nz : P1.nz;       // x_nom_0 of a handed-over step comes back through z
+        if (l->r_z_stride < nzmax) {
+            cudaFree(l->r_z);
+            l->r_z = nullptr;
+            CU(cudaMalloc(&l->r_z, B * (size_t)nzmax * sizeof(double)));
+            l->r_z_stride = nzmax;
+        }
     }
+    int max_smem = 0;
+    CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, q->device));
     RolloutArgs a;
     a.B = l->B; a.t0 = l->t; a.T = l->t + T;
     a.ref = d_ref; a.ref_stride_t = ref_stride_t; a.ref_stride_b = ref_stride_b;
     a.theta = d_theta; a.gamma = d_gamma; a.w = d_w; a.p_loss = d_p_loss;
     a.seed = seed; a.id_offset = id_offset; a.traj = d_traj_x; a.traj_stride = traj_stride;
-    a.warm = l->r_warm; a.U = l->r_U; a.z = nullptr; a.status = l->r_status; a.iters = l->r_iters;
+    a.warm = l->r_warm; a.warm1 = l->r_warm1; a.two = q1 ? 1 : 0;
+    a.U = l->r_U; a.z = l->r_z; a.z_stride = l->r_z_stride; a.status = l->r_status; a.iters = l->r_iters;
     a.inst_t = l->r_inst_t; a.pending = l->r_pending; a.ref_pending = l->r_ref; a.n_pending = l->r_npend;
     a.stats = reinterpret_cast<unsigned long long*>(d_stats);
     // every instance starts at the loop's common time
@@ -544,19 +571,23 @@ int rtmpc_loop_rollout(rtmpc_loop* l, rtmpc_qp* q, int32_t T, const double* d_re
     CU(cudaMemsetAsync(l->r_pending, 0, B * sizeof(int), s));
     for (int round = 0;; ++round) {
         CU(cudaMemsetAsync(l->r_npend, 0, sizeof(int), s));
-        CU(rollout_launch(P, l->dev, q->as_wpb, q->num_sms, a, s));
+        CU(rollout_launch(P, P1, l->dev, q->as_wpb, q->num_sms, max_smem, a, s));
         g_launches.fetch_add(1);
         CU(cudaMemcpyAsync(l->h_npend, l->r_npend, sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         if (*l->h_npend == 0) break;
         if (round > T * 4 + 16) return fail("rtmpc_loop_rollout: parked instances do not make progress");
-        // parked instances: interior-point solve of their current step, then resume
-        QPLaunch f;
-        f.B = l->B; f.x_init = l->dev.x_hat; f.ref = d_ref ? l->r_ref : nullptr; f.sel = l->r_status;
-        f.sel_value = RTMPC_FALLBACK_STATUS; f.z = nullptr; f.U = l->r_U; f.status = l->r_status; f.iters = l->r_iters;
-        f.warm = l->r_warm; f.work = nullptr; f.stream = s;
-        CU(ipm_launch(P, q->ipm_wpb, q->ipm_smem, q->num_sms, f));
-        g_launches.fetch_add(1);
+        // parked instances: interior-point solve of their current step (status says for which problem), then resume
+        for (int which = 0; which < (q1 ? 2 : 1); ++which) {
+            rtmpc_qp* qq = which ? q1 : q;
+            QPLaunch f;
+            f.B = l->B; f.x_init = l->dev.x_hat; f.ref = d_ref ? l->r_ref : nullptr; f.sel = l->r_status;
+            f.sel_value = RTMPC_FALLBACK_STATUS - which; f.z = ext ? l->r_z : nullptr; f.U = l->r_U;
+            f.status = l->r_status; f.iters = l->r_iters; f.warm = which ? l->r_warm1 : l->r_warm; f.work = nullptr;
+            f.stream = s;
+            CU(ipm_launch(qq->dev, qq->ipm_wpb, qq->ipm_smem, qq->num_sms, f));
+            g_launches.fetch_add(1);
+        }
     }
     l->t += T;
     return 0;

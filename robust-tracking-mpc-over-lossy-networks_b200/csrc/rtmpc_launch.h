@@ -39,7 +39,9 @@ struct RolloutArgs {
     long long id_offset;
     double* traj;
     long long traj_stride;
-    int* warm;                    // [B * (npad + 1)] warm-start records
+    int *warm, *warm1;            // [B * (npad + 1)] warm-start records of the problem(s)
+    int two;                      // 1: two problems, switched per step on gamma_{t-1}
+    long long z_stride;           // entries per instance of z
     double *U, *z;                // [B * (N+1) * nu] packet payloads; [B * nz] or NULL
     int *status, *iters;          // [B] of the last solve
     int *inst_t, *pending;        // [B] per-instance time; 1 = current step solved by the interior-point kernel
@@ -48,7 +50,7 @@ struct RolloutArgs {
     unsigned long long* stats;    // [8] status counts[4], IPM iterations, active-set steps, rounds, flops (or NULL)
 };
 bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err);
-cudaError_t rollout_launch(const QPDev& P, const LoopDev& L, int wpb, int num_sms, const RolloutArgs& a,
-                           cudaStream_t stream);
+cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, int wpb, int num_sms, int max_smem,
+                           const RolloutArgs& a, cudaStream_t stream);
 
 }  // namespace rtmpc

@@ -15,27 +15,38 @@
 
 namespace rtmpc {
 
-// per-warp shared memory of the rollout: solver scratch | closed-loop state | packet payload | warm-start record
-__host__ __device__ inline int rollout_warp_doubles(const QPDev& P) {
-    return as_warp_doubles(P) + loop_smem_doubles(P.N, P.nu) + (((P.N + 1) * P.nu + 1) & ~1) +
-           ((((P.npad + 2) >> 1) + 1) & ~1);     // every part even: 16-byte alignment of the next warp's block
+// per-warp shared memory of the rollout, in doubles:
+//   closed-loop state | packet payload | x_nom_0 of this step's solve | warm-start record of each QP | solver scratch
+__host__ __device__ inline int rollout_fixed_doubles(const QPDev& P0, const QPDev& P1) {
+    return loop_smem_doubles(P0.N, P0.nu) + (((P0.N + 1) * P0.nu + 1) & ~1) + LOOP_MAX_NX +
+           ((((P0.npad + 2) >> 1) + 1) & ~1) + ((((P1.npad + 2) >> 1) + 1) & ~1);      // every part even (16-byte alignment)
+}
+__host__ __device__ inline int rollout_warp_doubles(const QPDev& P0, const QPDev& P1) {
+    const int s0 = as_warp_doubles(P0), s1 = as_warp_doubles(P1);
+    return rollout_fixed_doubles(P0, P1) + (s0 > s1 ? s0 : s1);
 }
 
+// P0: the controller's problem; P1: the "packet received" problem of ExtendedTubeTrackingMPC, chosen per step and
+// instance on gamma_{t-1} (TubeTrackingMPC.py:307-349); P1 == P0 for the single-problem controllers.
 template <int R2, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
-rollout_kernel(QPDev P, LoopDev L, RolloutArgs a) {
+rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    const int nx = P.nx, nu = P.nu;
-    const int usz = (P.N + 1) * nu;
-    double* wbase = smem + (size_t)warp * rollout_warp_doubles(P);
-    ASWarp w = as_carve(wbase, P);
+    const int nx = P0.nx, nu = P0.nu;
+    const int usz = (P0.N + 1) * nu;
+    const bool two = a.two != 0;
+    double* wbase = smem + (size_t)warp * rollout_warp_doubles(P0, P1);
     LoopSmemState S;
-    S.base = wbase + as_warp_doubles(P);
-    double* U_s = S.base + loop_smem_doubles(P.N, nu);                  // this step's packet payload
-    int* warm_s = reinterpret_cast<int*>(U_s + ((usz + 1) & ~1));        // warm-start record
+    S.base = wbase;
+    double* U_s = S.base + loop_smem_doubles(P0.N, nu);                  // this step's packet payload
+    double* x0_s = U_s + ((usz + 1) & ~1);                                // x_nom[:,0] of this step's solve
+    int* warm0_s = reinterpret_cast<int*>(x0_s + LOOP_MAX_NX);            // warm-start records
+    int* warm1_s = warm0_s + 2 * ((((P0.npad + 2) >> 1) + 1) & ~1);
+    double* scratch = wbase + rollout_fixed_doubles(P0, P1);
+    const bool ext = L.actuator == RTMPC_ACT_EXTENDED;
 
 #pragma unroll 1
     // consecutive instances go to different SMs, so a last partial round is spread over all of them
@@ -45,21 +56,24 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a) {
         bool have = a.pending[inst] != 0;       // this step was solved by the interior-point kernel
         unsigned n_status[4] = {0, 0, 0, 0}, n_ipm = 0, n_steps = 0, n_rounds = 0;
         unsigned long long n_flops = 0;
-        double* z_inst = a.z ? a.z + (size_t)inst * P.nz : nullptr;
         double* traj_b = a.traj ? a.traj + (size_t)inst * a.traj_stride : nullptr;
         const double p = a.p_loss ? a.p_loss[inst] : 0.0;
-        // ---- state, payload and warm-start record move on chip for the whole rollout -------------------
+        // ---- state, payload and warm-start records move on chip for the whole rollout -------------------
         if (lane < nx) {
             S.x(lane) = L.x[(size_t)inst * nx + lane];
             S.x_nom(lane) = L.x_nom[(size_t)inst * nx + lane];
             S.x_hat(lane) = L.x_hat[(size_t)inst * nx + lane];
+            // x_nom_0 of a step the interior-point kernel solved: that kernel wrote z with its problem's own stride
+            const int zs = (two && L.gamma_last[inst] == 1) ? P1.nz : P0.nz;
+            x0_s[lane] = (have && ext) ? a.z[(size_t)inst * zs + lane] : 0.0;
         }
         if (lane < nu) S.u_last(lane) = L.u_last[(size_t)inst * nu + lane];
         for (int i = lane; i < usz; i += 32) {
             S.buf()[i] = L.buf[(size_t)inst * usz + i];
             U_s[i] = a.U[(size_t)inst * usz + i];
         }
-        for (int i = lane; i < P.npad + 1; i += 32) warm_s[i] = a.warm[(size_t)inst * (P.npad + 1) + i];
+        for (int i = lane; i < P0.npad + 1; i += 32) warm0_s[i] = a.warm[(size_t)inst * (P0.npad + 1) + i];
+        if (two) for (int i = lane; i < P1.npad + 1; i += 32) warm1_s[i] = a.warm1[(size_t)inst * (P1.npad + 1) + i];
         if (lane == 0) {
             S.err_acc() = L.err_acc[inst]; S.tube_max() = L.tube_max[inst];
             S.q_t() = L.q_t[inst]; S.s_t() = L.s_t[inst]; S.Theta() = L.Theta[inst]; S.alive() = L.alive[inst];
@@ -82,12 +96,16 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a) {
             } else {
                 ASCounters cnt;
                 cnt.steps = 0; cnt.rounds = 0; cnt.rows = 0; cnt.sq = 0;
-                status = as_solve_instance<R2, (MAXW * R2 <= 100) ? 2 : 1>(P, w, lane, &S.x_hat(0), ref_t, warm_s, z_inst,
-                                                                         U_s, cnt);
-                n_steps += cnt.steps; n_rounds += cnt.rounds; n_flops += as_flops(P, cnt, z_inst != nullptr);
+                const bool recv = two && S.gamma_last() == 1;           // gamma of the previous step
+                const QPDev& P = recv ? P1 : P0;
+                ASWarp w = as_carve(scratch, P);
+                status = as_solve_instance<R2, (MAXW * R2 <= 100) ? 2 : 1>(P, w, lane, &S.x_hat(0), ref_t,
+                                                                         recv ? warm1_s : warm0_s, ext ? x0_s : nullptr,
+                                                                         nx, U_s, cnt);
+                n_steps += cnt.steps; n_rounds += cnt.rounds; n_flops += as_flops(P, cnt, false);
                 if (status == RTMPC_FALLBACK) {
                     if (lane == 0) {
-                        a.status[inst] = RTMPC_FALLBACK;
+                        a.status[inst] = recv ? RTMPC_FALLBACK - 1 : RTMPC_FALLBACK;     // which problem the hand-over is for
                         a.pending[inst] = 1;
                         for (int j = 0; j < nx; ++j) a.ref_pending[(size_t)inst * nx + j] = ref_t ? ref_t[j] : 0.0;
                         atomicAdd(a.n_pending, 1);
@@ -107,7 +125,7 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a) {
                 if (L.nz_rows > 0) worst = as_wmax(loop_tube_rows(L, S, lane, 32));
                 if (lane == 0) {
                     const bool expl = a.theta != nullptr;
-                    loop_step_body(L, S, t, U_s, (L.actuator == RTMPC_ACT_EXTENDED) ? z_inst : nullptr, ref_t,
+                    loop_step_body(L, S, t, U_s, ext ? x0_s : nullptr, ref_t,
                                    expl ? a.theta[(size_t)k * a.B + inst] : -1, expl ? a.gamma[(size_t)k * a.B + inst] : -1,
                                    (expl && a.w) ? a.w + ((size_t)k * a.B + inst) * nx : nullptr, p, a.seed,
                                    (unsigned long long)(a.id_offset + inst), traj_b, worst);
@@ -126,7 +144,8 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a) {
             L.buf[(size_t)inst * usz + i] = S.buf()[i];
             a.U[(size_t)inst * usz + i] = U_s[i];
         }
-        for (int i = lane; i < P.npad + 1; i += 32) a.warm[(size_t)inst * (P.npad + 1) + i] = warm_s[i];
+        for (int i = lane; i < P0.npad + 1; i += 32) a.warm[(size_t)inst * (P0.npad + 1) + i] = warm0_s[i];
+        if (two) for (int i = lane; i < P1.npad + 1; i += 32) a.warm1[(size_t)inst * (P1.npad + 1) + i] = warm1_s[i];
         if (lane == 0) {
             L.err_acc[inst] = S.err_acc(); L.tube_max[inst] = S.tube_max();
             L.q_t[inst] = S.q_t(); L.s_t[inst] = S.s_t(); L.Theta[inst] = S.Theta(); L.alive[inst] = S.alive();
@@ -144,7 +163,7 @@ rollout_kernel(QPDev P, LoopDev L, RolloutArgs a) {
     }
 }
 
-typedef void (*ro_fn)(QPDev, LoopDev, RolloutArgs);
+typedef void (*ro_fn)(QPDev, QPDev, LoopDev, RolloutArgs);
 struct RoChoice { int r2, maxw; ro_fn fn; };
 static const RoChoice kRo[] = {
     {2, 24, rollout_kernel<2, 24>},  {5, 16, rollout_kernel<5, 16>},  {9, 16, rollout_kernel<9, 16>},
@@ -170,17 +189,18 @@ bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err) {
     return *err == cudaSuccess;
 }
 
-cudaError_t rollout_launch(const QPDev& P, const LoopDev& L, int wpb, int num_sms, const RolloutArgs& a,
-                           cudaStream_t stream) {
+cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, int wpb, int num_sms, int max_smem,
+                           const RolloutArgs& a, cudaStream_t stream) {
     const RoChoice* kc = pick(P.mpad);
     if (wpb > kc->maxw) wpb = kc->maxw;
+    const size_t per_warp = (size_t)rollout_warp_doubles(P, P1) * sizeof(double);
+    while (wpb > 1 && per_warp * wpb > (size_t)max_smem) --wpb;
     int per_cta = (a.B + num_sms - 1) / num_sms;
     int warps = per_cta < wpb ? per_cta : wpb;
     if (warps < 1) warps = 1;
     int blocks = (a.B + warps - 1) / warps;
     if (blocks > num_sms) blocks = num_sms;
-    const size_t per_warp = (size_t)rollout_warp_doubles(P) * sizeof(double);
-    kc->fn<<<blocks, warps * 32, per_warp * warps, stream>>>(P, L, a);
+    kc->fn<<<blocks, warps * 32, per_warp * warps, stream>>>(P, P1, L, a);
     return cudaGetLastError();
 }
 

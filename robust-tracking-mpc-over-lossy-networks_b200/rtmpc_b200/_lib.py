@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "librtmpc_b200.so")
 EXPORTS = [
     "rtmpc_abi_version", "rtmpc_last_error", "rtmpc_device_count", "rtmpc_set_device",
     "rtmpc_qp_create", "rtmpc_qp_destroy", "rtmpc_qp_solve", "rtmpc_qp_solve_host", "rtmpc_launch_count",
-    "rtmpc_qp_warm_stride", "rtmpc_qp_warm_reset", "rtmpc_qp_set_method", "rtmpc_qp_set_work_counter", "rtmpc_qp_set_step_cap",
+    "rtmpc_qp_warm_stride", "rtmpc_qp_rows", "rtmpc_qp_warm_reset", "rtmpc_qp_set_method", "rtmpc_qp_set_work_counter", "rtmpc_qp_set_step_cap",
     "rtmpc_loop_create", "rtmpc_loop_destroy", "rtmpc_loop_reset", "rtmpc_loop_x", "rtmpc_loop_x_nom",
     "rtmpc_loop_x_hat", "rtmpc_loop_q_t", "rtmpc_loop_s_t", "rtmpc_loop_Theta", "rtmpc_loop_alive",
     "rtmpc_loop_err_acc", "rtmpc_loop_tube_max", "rtmpc_loop_u", "rtmpc_loop_gamma", "rtmpc_loop_time",
@@ -40,7 +40,7 @@ class QPDesc(C.Structure):
                [(k, _dp) for k in ("Hs", "Hinv", "G", "Y", "Fx", "Fr", "lo0", "up0", "Lx", "Ux")] + \
                [("has_lo", _bp), ("has_up", _bp)] + \
                [(k, _dp) for k in ("parC", "parh", "Dscale", "Phi", "Psi", "Kss")] + \
-               [("s_floor", C.c_double), ("sc_b", C.c_double), ("max_iter", C.c_int32), ("reserved", C.c_int32),
+               [("s_floor", C.c_double), ("sc_b", C.c_double), ("max_iter", C.c_int32), ("min_rows", C.c_int32),
                 ("shift", _ip)]
 
 
@@ -80,6 +80,8 @@ def lib():
     L.rtmpc_qp_solve_host.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
     L.rtmpc_qp_warm_stride.argtypes = [vp]
     L.rtmpc_qp_warm_stride.restype = C.c_int32
+    L.rtmpc_qp_rows.argtypes = [vp]
+    L.rtmpc_qp_rows.restype = C.c_int32
     L.rtmpc_qp_warm_reset.argtypes = [vp]
     L.rtmpc_qp_set_method.argtypes = [vp, C.c_int32]
     L.rtmpc_qp_set_work_counter.argtypes = [vp, vp]
@@ -97,7 +99,7 @@ def lib():
     L.rtmpc_loop_time.restype = C.c_int32
     L.rtmpc_loop_step.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, C.c_uint64, C.c_int64, vp,
                                   C.c_int64, vp]
-    L.rtmpc_loop_rollout.argtypes = [vp, vp, C.c_int32, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, C.c_uint64, C.c_int64,
+    L.rtmpc_loop_rollout.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, C.c_uint64, C.c_int64,
                                      vp, C.c_int64, vp, vp]
     i32 = C.c_int32
     L.rtmpc_actuator_process.argtypes = [i32] * 6 + [vp] * 18

@@ -15,7 +15,7 @@ from .ipm_data import prepare
 
 
 class BatchedQP:
-    def __init__(self, spec: MPCSpec, Kss=None, max_iter=60):
+    def __init__(self, spec: MPCSpec, Kss=None, max_iter=60, min_rows=0):
         self.spec = spec
         self.cq = condense(spec)
         self.data = prepare(self.cq)
@@ -52,6 +52,7 @@ class BatchedQP:
         desc.has_lo = has_lo.ctypes.data_as(C.POINTER(C.c_uint8))
         desc.has_up = has_up.ctypes.data_as(C.POINTER(C.c_uint8))
         desc.s_floor, desc.sc_b, desc.max_iter = d.s_floor, d.sc_b, max_iter
+        desc.min_rows = int(min_rows)
         shift = np.ascontiguousarray(d.shift, np.int32)
         desc.shift = shift.ctypes.data_as(C.POINTER(C.c_int32))
         h = C.c_void_p()
@@ -59,6 +60,13 @@ class BatchedQP:
         self._h = h
         self._L = L
         self.warm_stride = int(L.rtmpc_qp_warm_stride(h))
+        self.rows = int(L.rtmpc_qp_rows(h))          # rows the kernels work on (padded)
+        self._Kss = Kss
+        self._max_iter = max_iter
+
+    def with_rows(self, min_rows):
+        """The same problem padded to at least ``min_rows`` rows (two problems one rollout switches between)."""
+        return self if self.rows >= min_rows else BatchedQP(self.spec, Kss=self._Kss, max_iter=self._max_iter, min_rows=min_rows)
 
     def set_method(self, method):
         """'active_set' (default: dual active-set kernel, interior point as fallback) or 'interior_point'."""

@@ -152,12 +152,12 @@ class RemoteLoop:
         """T steps.  ``ref`` [nx], [T,nx] or [T,B,nx]; explicit arrays theta/gamma [T,B], w [T,B,nx] (host or
         device) or p_loss [B].  Returns the trajectory tensor [B,T+1,nx] when ``record``.
 
-        ``fused`` (default: whenever the variant has a single QP) runs all T steps in one persistent launch
+        ``fused`` (default) runs all T steps in one persistent launch
         (``rtmpc_loop_rollout``); otherwise one QP launch + one loop-step launch per control step.  Both
         give identical results."""
         f64 = torch.float64
         if fused is None:
-            fused = self.kind != "extended"
+            fused = True
         if fused:
             return self._run_fused(T, ref, p_loss, theta, gamma, w, seed, id_offset, record)
         ref = np.asarray(ref, float)
@@ -184,8 +184,13 @@ class RemoteLoop:
 
     def _run_fused(self, T, ref, p_loss, theta, gamma, w, seed, id_offset, record):
         f64 = torch.float64
+        recv = None
         if self.kind == "extended":
-            raise _lib.RtmpcError("the fused rollout has one QP per step; the extended variant needs fused=False")
+            # both problems padded to the same row count (one kernel instantiation handles either)
+            rows = max(self.mpc._prob.rows, self.mpc._prob_packet_received.rows)
+            self.mpc._prob = self.mpc._prob.with_rows(rows)
+            self.mpc._prob_packet_received = self.mpc._prob_packet_received.with_rows(rows)
+            recv = self.mpc._prob_packet_received._h
         if torch.is_tensor(ref):
             ref_d = ref.to(self.dev, f64).contiguous()
         else:
@@ -210,7 +215,7 @@ class RemoteLoop:
             p_loss = torch.zeros(B, device=self.dev, dtype=f64)
         p = _lib.ptr
         stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(self.L.rtmpc_loop_rollout(self._h, self.mpc._prob._h, int(T), p(ref_d), st, sb, p(theta), p(gamma), p(w),
+        _lib.check(self.L.rtmpc_loop_rollout(self._h, self.mpc._prob._h, recv, int(T), p(ref_d), st, sb, p(theta), p(gamma), p(w),
                                              p(p_loss), int(seed), int(id_offset), p(traj),
                                              0 if traj is None else (T + 1) * nx, p(self.stats), stream),
                    "rtmpc_loop_rollout")

@@ -227,3 +227,35 @@ def test_fused_rollout_with_instances_handed_to_the_interior_point_kernel():
             assert loop.tube_max.max().item() < 1e-7
     finally:
         mpc._prob.set_step_cap(0)
+
+
+def test_fused_rollout_extended_variant_two_problems():
+    """Config 3: ExtendedTubeTrackingMPC (two QPs switched on gamma_{t-1}) + RobustEstimator + x_nom_0 in the packet,
+    all T steps in one launch: against the oracle's golden runs and bit for bit against the step-by-step path."""
+    from rtmpc_b200.rollout import RemoteLoop
+    for sets, golden, B in (("sets_di.npz", "loop_di_ext.npz", 1), ("sets_cp.npz", "loop_cp_ext.npz", 2)):
+        s, g = H.load(sets), H.load(golden)
+        nx = s["A"].shape[0]
+        if B == 1:
+            th, ga, w, x, xh, xn = (g[k][None] for k in ("theta", "gamma", "w", "x", "x_hat", "x_nom"))
+            x0 = np.array([[1.0, 2.0]])
+        else:
+            th, ga, w, x, xh, xn = (g[k] for k in ("theta", "gamma", "w", "x", "x_hat", "x_nom"))
+            x0 = np.zeros((B, nx))
+        T = th.shape[1]
+        out = {}
+        for fused in (True, False):
+            mpc = H.make_tube_mpc(s, extended=True)
+            loop = RemoteLoop(mpc, B, kind="extended", Z=H.poly(s, "Z"))
+            loop.reset(x0)
+            tr = loop.run(T, g["refs"], theta=th.T, gamma=ga.T, w=np.transpose(w, (1, 0, 2)), record=True,
+                          fused=fused).cpu().numpy()
+            out[fused] = (tr, loop.x_hat.cpu().numpy(), loop.x_nom.cpu().numpy(), loop.Theta.cpu().numpy(),
+                          loop.s_t.cpu().numpy(), loop.q_t.cpu().numpy())
+            assert loop.tube_max.max().item() < 1e-7
+            assert loop.status_count[0].item() == B * T
+        assert np.abs(out[True][0] - x).max() <= TOL, golden
+        assert np.abs(out[True][1] - xh[:, -1]).max() <= TOL
+        assert np.abs(out[True][2] - xn[:, -1]).max() <= TOL
+        for a, b in zip(out[True], out[False]):
+            assert np.array_equal(a, b), golden
