@@ -196,6 +196,57 @@ static __device__ __noinline__ void as_downdate(double* __restrict__ M, double* 
     __syncwarp();
 }
 
+// In-place Gauss-Jordan inverse of the nc x nc matrix in M (lane i owns row i; hi = even cover of nc).  A pivot that
+// has lost its size relative to the original diagonal (diag0) marks a row that depends on the rows before it: it is
+// skipped, and its row and column are cleared at the end, which leaves the inverse over the remaining rows.
+// Returns the mask of skipped rows.
+static __device__ __noinline__ unsigned as_invert(double* __restrict__ M, int ms, int nc, int hi, int lane, double diag0) {
+    unsigned dead = 0;
+#pragma unroll 1
+    for (int k = 0; k < nc; ++k) {
+        const double pk = M[k * ms + k];
+        const double dk = __shfl_sync(RTMPC_FULL_MASK, diag0, k);
+        if (!(pk > 1e-11 * dk)) { dead |= 1u << k; continue; }
+        const double ip = __drcp_rn(pk);
+        if (lane == k) {
+            double* row = M + k * ms;
+            row[k] = 1.0;
+#pragma unroll 1
+            for (int b = 0; b < hi; b += 2) {
+                double2 mm = ld2(row + b);
+                mm.x *= ip; mm.y *= ip;
+                *reinterpret_cast<double2*>(row + b) = mm;
+            }
+        }
+        __syncwarp();
+        if (lane < nc && lane != k) {
+            double* row = M + lane * ms;
+            const double* __restrict__ rk = M + k * ms;
+            const double f = row[k];
+            row[k] = 0.0;
+            if (f != 0.0) {
+#pragma unroll 1
+                for (int b = 0; b < hi; b += 2) {
+                    const double2 kk = ld2(rk + b);
+                    double2 mm = ld2(row + b);
+                    mm.x = fma(-f, kk.x, mm.x);
+                    mm.y = fma(-f, kk.y, mm.y);
+                    *reinterpret_cast<double2*>(row + b) = mm;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (dead && lane < nc) {
+        double* row = M + lane * ms;
+#pragma unroll 1
+        for (int b = 0; b < nc; ++b)
+            if (((dead >> b) & 1u) || ((dead >> lane) & 1u)) row[b] = 0.0;
+    }
+    __syncwarp();
+    return dead;
+}
+
 // flag / unflag row `row` as a member of the working set in its owner lane's bit masks
 __device__ __forceinline__ void as_mark(int lane, int row, int sgn, bool on, unsigned& actu, unsigned& actl) {
     if (lane == ((row & 63) >> 1)) {
@@ -554,36 +605,41 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
         const int wn = (warm_inst && P.shift) ? warm_inst[0] : 0;
         bool apply = false;
         if (wn > 0) {
-            const unsigned slots = (npad >= 32) ? 0xffffffffu : ((1u << npad) - 1u);
-#pragma unroll 1
-            for (int c = 0; c < wn && c < npad; ++c) {
-                const int code = warm_inst[1 + c];
+            // every lane decodes one candidate: moved one stage earlier, kept if the row has that bound
+            int prow = -1;
+            double psg = 1.0;
+            if (lane < wn && lane < n) {
+                const int code = warm_inst[1 + lane];
                 const int row0 = code >> 1;
-                const double sp = (code & 1) ? -1.0 : 1.0;
-                if (row0 < 0 || row0 >= mpad) continue;
-                const int p = P.shift[row0];
-                if (p < 0) continue;
-                if ((sp > 0) ? !(P.upI[p] < 0.5 * RTMPC_INF) : !(P.loI[p] > -0.5 * RTMPC_INF)) continue;
-                const unsigned freem = ~amask & slots;
-                if (!freem || __popc(amask) >= n) break;
-                const bool occ = (amask >> lane) & 1u;
-                const int na = __popc(amask);
-                const double* __restrict__ Wp = P.W + (size_t)p * mpad;
-                const double wpp = Wp[p];
-                const double v = occ ? sl.sa * sp * Wp[sl.ra] : 0.0;
-                if (lane < npad) w.v()[lane] = v;
+                psg = (code & 1) ? -1.0 : 1.0;
+                if (row0 >= 0 && row0 < mpad) prow = P.shift[row0];
+                if (prow >= 0 && ((psg > 0) ? !(P.upI[prow] < 0.5 * RTMPC_INF) : !(P.loI[prow] > -0.5 * RTMPC_INF))) prow = -1;
+            }
+            const unsigned okm = __ballot_sync(RTMPC_FULL_MASK, prow >= 0);
+            const int nc = __popc(okm);
+            if (prow >= 0) {
+                const int pos = __popc(okm & ((1u << lane) - 1u));
+                w.act_row()[pos] = prow;
+                w.act_sgn()[pos] = (int)psg;
+            }
+            __syncwarp();
+            if (nc > 0) {
+                // candidate c sits in slot c: S = signed sub-matrix of W, inverted in place
+                const int hi = (nc + 1) & ~1;
+                double diag0 = 1.0;
+                if (lane < nc) {
+                    sl.ra = w.act_row()[lane];
+                    sl.sa = (double)w.act_sgn()[lane];
+                    const double* __restrict__ Wa = P.W + (size_t)sl.ra * mpad;
+                    double* row = w.M() + lane * ms;
+#pragma unroll 1
+                    for (int b = 0; b < nc; ++b) row[b] = Wa[w.act_row()[b]] * sl.sa * (double)w.act_sgn()[b];
+                    diag0 = Wa[sl.ra];
+                }
                 __syncwarp();
-                const double rr = occ ? as_matvec(w.M(), ms, as_hi(amask), lane, npad, w.v()) : 0.0;
-                const double kappa = wpp - as_wsum(v * rr);
-                cnt.sq += 2 * na * na;
-                if (!(kappa > 1e-11 * wpp)) continue;           // depends on the rows taken so far
-                const int s = __ffs(freem) - 1;
-                if (lane < npad) w.rv()[lane] = rr;
-                __syncwarp();
-                as_border(w.M(), w.rv(), ms, as_hi(amask | (1u << s)), lane, s, rr, kappa);
-                if (lane == s) { sl.ra = p; sl.sa = sp; w.act_row()[s] = p; w.act_sgn()[s] = (int)sp; }
-                amask |= 1u << s;
-                __syncwarp();
+                const unsigned dead = as_invert(w.M(), ms, nc, hi, lane, diag0);
+                amask = (((nc >= 32) ? 0xffffffffu : ((1u << nc) - 1u))) & ~dead;
+                cnt.sq += nc * nc * nc / 2;
             }
             // multipliers of the equality-constrained problem; drop negative ones, most negative first
             double rhs = 0.0;
