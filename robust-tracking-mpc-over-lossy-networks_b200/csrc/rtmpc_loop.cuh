@@ -300,6 +300,178 @@ __device__ __forceinline__ void loop_step_body(const LoopDev& L, const State S, 
         loop_step_body_t<0, 0>(L, S, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
 }
 
+// The same closed-loop step taken by a whole warp (rollout kernel; state in shared memory): lane i owns row i of
+// the three mat-vecs, the Philox draws run in parallel lanes, scalars are computed redundantly.  Every output
+// element is produced by the same FMA sequence as in loop_step_body_t, so both give identical bits.
+template <class State>
+__device__ __forceinline__ void loop_step_body_warp(const LoopDev& L, const State S, int lane, int t, const double* Ub,
+                                                    const double* x_nom0_b, const double* ref_b, int theta_in,
+                                                    int gamma_in, const double* w_in_b, double p,
+                                                    unsigned long long seed, unsigned long long id, double* traj_b,
+                                                    double tube_worst) {
+    const int nx = L.nx, nu = L.nu, N = L.N;
+    // ---- statistics on the pre-step state ---------------------------------------------------------------
+    if (lane == 0) {
+        if (ref_b) {
+            double e = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < nx; ++k) { const double d = S.x(k) - ref_b[k]; e = fma(d, d, e); }
+            S.err_acc() += e;
+        }
+        if (L.nz_rows > 0) S.tube_max() = fmax(S.tube_max(), tube_worst);
+    }
+    // ---- network and disturbance realisation ------------------------------------------------------------
+    int theta, gamma;
+    double wi = 0.0;                                     // lane i < nx: disturbance on state i
+    if (theta_in >= 0) {
+        theta = theta_in;
+        gamma = gamma_in;
+        if (lane < nx && w_in_b) wi = w_in_b[lane];
+    } else {
+        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        // lane 0 draws (theta, gamma), lane 1 + j draws (w_2j, w_2j+1): counters as in loop_step_body_t
+        Philox4 r;
+        r.x = r.y = r.z = r.w = 0u;
+        if (lane <= ((nx + 1) >> 1)) r = loop_philox((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, (uint32_t)lane, k0, k1);
+        const int th0 = (t == 0) ? 1 : (u01_from_bits(r.x, r.y) < p ? 0 : 1);
+        const int ga0 = (t == 0) ? 1 : (u01_from_bits(r.z, r.w) < p ? 0 : 1);
+        theta = __shfl_sync(0xffffffffu, th0, 0);
+        gamma = __shfl_sync(0xffffffffu, ga0, 0);
+        double wa = 0.0, wb = 0.0;
+        if (lane >= 1 && lane <= ((nx + 1) >> 1)) {
+            const int k = 2 * (lane - 1);
+            wa = L.w_half[k] * (2.0 * u01_from_bits(r.x, r.y) - 1.0);
+            if (k + 1 < nx) wb = L.w_half[k + 1] * (2.0 * u01_from_bits(r.z, r.w) - 1.0);
+        }
+        const int src = 1 + ((lane < nx ? lane : 0) >> 1);
+        const double ga = __shfl_sync(0xffffffffu, wa, src), gb = __shfl_sync(0xffffffffu, wb, src);
+        if (lane < nx) wi = (lane & 1) ? gb : ga;
+    }
+    // ---- local side (scalars redundantly in every lane) ---------------------------------------------------
+    const int q_pkt = S.q_t();
+    int last_loss = S.last_loss();
+    int Theta = 0;
+    if (theta == 1) Theta = (last_loss <= q_pkt) ? 1 : 0;
+    else last_loss = t;
+    int s_t = S.s_t();
+    double* buf = S.buf();
+    __syncwarp();
+    if (Theta) {
+        s_t = t;
+        for (int i = lane; i < (N + 1) * nu; i += 32) buf[i] = Ub[i];
+        if (L.actuator != RTMPC_ACT_SMART && x_nom0_b && lane < nx) S.x_nom(lane) = x_nom0_b[lane];
+    }
+    __syncwarp();
+    const int kk = t - s_t;
+    const bool smart = L.actuator == RTMPC_ACT_SMART;
+    double u_nom[LOOP_MAX_NU], u[LOOP_MAX_NU], uh[LOOP_MAX_NU];
+#pragma unroll
+    for (int j = 0; j < LOOP_MAX_NU; ++j) {
+        u_nom[j] = 0.0; u[j] = 0.0; uh[j] = 0.0;
+        if (j < nu) {
+            if (kk < N) u_nom[j] = buf[kk * nu + j];
+            else {
+                double acc = buf[N * nu + j];
+#pragma unroll 1
+                for (int k = 0; k < nx; ++k) acc = fma(-L.K[j * nx + k], smart ? S.x(k) : S.x_nom(k), acc);
+                u_nom[j] = acc;
+            }
+            if (smart) u[j] = u_nom[j];
+            else {
+                double acc = u_nom[j];
+#pragma unroll 1
+                for (int k = 0; k < nx; ++k) acc = fma(-L.Kp[j * nx + k], S.x(k) - S.x_nom(k), acc);
+                u[j] = acc;
+            }
+        }
+    }
+    // remote side's input estimate (plant packet content = pre-update values: x_t field carries x_nom for the
+    // consistent actuator, x otherwise; the extended packet carries both)
+    const bool cons = L.actuator == RTMPC_ACT_CONSISTENT, ext = L.actuator == RTMPC_ACT_EXTENDED;
+    if (gamma == 1) {
+#pragma unroll
+        for (int j = 0; j < LOOP_MAX_NU; ++j) {
+            if (j < nu) {
+                double un;
+                if (kk < N) un = buf[kk * nu + j];
+                else {
+                    double acc = buf[N * nu + j];
+#pragma unroll 1
+                    for (int k = 0; k < nx; ++k) acc = fma(-L.K[j * nx + k], (ext || cons) ? S.x_nom(k) : S.x(k), acc);
+                    un = acc;
+                }
+                if (ext) {
+                    double acc = un;
+#pragma unroll 1
+                    for (int k = 0; k < nx; ++k) acc = fma(-L.Kp[j * nx + k], S.x(k) - S.x_nom(k), acc);
+                    un = acc;
+                }
+                uh[j] = un;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < LOOP_MAX_NU; ++j) if (j < nu) uh[j] = Ub[j];      // first input of the latest sent sequence
+    }
+    // ---- lane i: row i of nominal model, plant and estimator ----------------------------------------------
+    double xn_new = 0.0, x_new = 0.0, xh_new = 0.0;
+    if (lane < nx) {
+        const int i = lane;
+        if (!smart) {
+            double acc = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < nx; ++k) acc = fma(L.A[i * nx + k], S.x_nom(k), acc);
+#pragma unroll
+            for (int j = 0; j < LOOP_MAX_NU; ++j) if (j < nu) acc = fma(L.Bm[i * nu + j], u_nom[j], acc);
+            xn_new = acc;
+        } else xn_new = S.x_nom(i);
+        if (L.plant != RTMPC_PLANT_CARTPOLE) {
+            double acc = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < nx; ++k) acc = fma(L.A[i * nx + k], S.x(k), acc);
+#pragma unroll
+            for (int j = 0; j < LOOP_MAX_NU; ++j) if (j < nu) acc = fma(L.Bm[i * nu + j], u[j], acc);
+            x_new = acc + wi;
+        }
+        {
+            double acc = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < nx; ++k) {
+                double xb;
+                if (gamma == 1) xb = cons ? S.x_nom(k) : S.x(k);
+                else xb = (ext && x_nom0_b) ? x_nom0_b[k] : S.x_hat(k);
+                acc = fma(L.A[i * nx + k], xb, acc);
+            }
+#pragma unroll
+            for (int j = 0; j < LOOP_MAX_NU; ++j) if (j < nu) acc = fma(L.Bm[i * nu + j], uh[j], acc);
+            xh_new = acc;
+        }
+    }
+    double xc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (L.plant == RTMPC_PLANT_CARTPOLE && lane == 0) {
+        for (int k = 0; k < 4; ++k) xc[k] = S.x(k);
+        cartpole_substeps(xc, u[0], L.cart);
+    }
+    __syncwarp();
+    // ---- write back -----------------------------------------------------------------------------------------
+    if (lane < nx) {
+        if (L.plant != RTMPC_PLANT_CARTPOLE) S.x(lane) = x_new;
+        S.x_nom(lane) = xn_new;
+        S.x_hat(lane) = xh_new;
+    }
+    if (lane == 0) {
+        if (L.plant == RTMPC_PLANT_CARTPOLE) for (int k = 0; k < 4; ++k) S.x(k) = xc[k];
+        for (int j = 0; j < nu; ++j) S.u_last(j) = u[j];
+        if (gamma == 1) S.q_t() = t;
+        S.s_t() = s_t;
+        S.Theta() = Theta;
+        S.last_loss() = last_loss;
+        S.gamma_last() = gamma;
+    }
+    __syncwarp();
+    if (traj_b && lane < nx) traj_b[(size_t)(t + 1) * nx + lane] = S.x(lane);
+}
+
 #ifdef RTMPC_LOOP_KERNELS   // the non-template kernels are compiled in one translation unit (rtmpc_capi.cu)
 __global__ void loop_step_kernel(LoopDev L, int B, int t, const double* __restrict__ U_t,
                                  const int* __restrict__ status, const double* __restrict__ x_nom0,
