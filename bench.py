@@ -375,7 +375,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-solves", type=int, default=1024, dest="cpu_solves")
+    ap.add_argument("--cpu-solves", type=int, default=8192, dest="cpu_solves",
+                    help="QP solves of the CPU arm per step (bounded sample of the workload, ~10 s on 16 cores)")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
     ap.add_argument("--instances", type=int, default=B_PER_GPU, help="closed-loop instances per GPU (BASELINE configs[1]: 4096)")
     args = ap.parse_args()

@@ -172,7 +172,7 @@ class RemoteLoop:
             gamma = torch.as_tensor(np.ascontiguousarray(gamma), device=self.dev).to(torch.int32).contiguous()
             w = None if w is None else torch.as_tensor(np.ascontiguousarray(w), device=self.dev, dtype=f64).contiguous()
         elif p_loss is not None:
-            p_loss = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(p_loss, (self.B,))), device=self.dev, dtype=f64)
+            p_loss = torch.as_tensor(np.array(np.broadcast_to(p_loss, (self.B,)), dtype=float), device=self.dev, dtype=f64)
         else:
             p_loss = torch.zeros(self.B, device=self.dev, dtype=f64)
         for k in range(T):
@@ -210,7 +210,7 @@ class RemoteLoop:
             p_loss = None
         elif p_loss is not None:
             if not torch.is_tensor(p_loss):
-                p_loss = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(p_loss, (B,))), device=self.dev, dtype=f64)
+                p_loss = torch.as_tensor(np.array(np.broadcast_to(p_loss, (B,)), dtype=float), device=self.dev, dtype=f64)
         else:
             p_loss = torch.zeros(B, device=self.dev, dtype=f64)
         p = _lib.ptr
