@@ -179,3 +179,37 @@ def test_active_set_kernel_against_interior_point_kernel_on_random_instances():
         assert (err / scale).max() <= TOL_TIGHT, (name, (err / scale).max())
         # the active-set path certifies at least as many instances as the interior-point path
         assert np.count_nonzero(s1 == 0) >= np.count_nonzero(s2 == 0), name
+
+
+def test_tracking_mpc_without_terminal_set_uses_the_terminal_equality():
+    """TrackingMPC.generate_optimization_problem without Xf: x_N == x_bar (TrackingMPC.py:105-107).  The equality rows
+    are zero-width two-sided rows for the active-set kernel."""
+    from oracle import ref_qp as rq
+    from oracle.ref_polytope import Polytope
+    from rtmpc_b200.condense import MPCSpec
+    from rtmpc_b200.qp import BatchedQP
+    for name, box, rbox in (("sets_di.npz", np.array([2.0, 0.5]), 2.0), ("sets_cp.npz", np.array([0.5, 0.5, 0.05, 0.2]), 0.5)):
+        s = H.load(name)
+        nx, N = s["A"].shape[0], int(s["N"])
+        spec = MPCSpec(s["A"], s["B"], s["Q"], s["R"], N, P_term=s["P"], T_ss=10 * s["P"], stage_x=(s["X_A"], s["X_b"]),
+                       stage_u=(s["U_A"], s["U_b"]), terminal=None, terminal_eq=True)
+        qp = BatchedQP(spec, Kss=s["K"])
+        P = lambda k: Polytope(s[k + "_A"], s[k + "_b"], normalize=False)      # noqa: E731
+        oq = rq.build_tracking(s["A"], s["B"], s["Q"], s["R"], N, s["P"], P("X"), P("U"), None)
+        rng = np.random.default_rng(3)
+        X = rng.uniform(-1, 1, (24, nx)) * box
+        R = np.zeros((24, nx))
+        R[:, 0] = rng.uniform(-rbox, rbox, 24)
+        z, U, st, it = qp.solve_host(X, R)
+        n_ok = 0
+        for i in range(24):
+            sol, res = rq.solve_param(oq, X[i].copy(), R[i].copy())
+            if res.status == "infeasible":
+                assert st[i] == 2, (name, i, st[i])
+                continue
+            assert st[i] == 0, (name, i, st[i])
+            u = z[i, nx * (N + 1):nx * (N + 1) + N].reshape(N, 1)
+            assert np.abs(u - sol[1].T).max() <= TOL_TIGHT * max(1.0, np.abs(sol[1]).max()), (name, i)
+            assert np.abs(z[i, nx * N:nx * (N + 1)] - z[i, -(nx + 1):-1]).max() <= 1e-9      # x_N == x_bar
+            n_ok += 1
+        assert n_ok >= 12, name
