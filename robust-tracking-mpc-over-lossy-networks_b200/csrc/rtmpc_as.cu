@@ -14,7 +14,6 @@ static const AsChoice kAs[] = {
     {2, 24, as_solve_kernel<2, 24>},  {5, 20, as_solve_kernel<5, 20>},  {9, 16, as_solve_kernel<9, 16>},
     {12, 16, as_solve_kernel<12, 16>}, {16, 16, as_solve_kernel<16, 16>},
 };
-static const AsChoice kAsExp[] = {{5, 16, as_solve_kernel<5, 16>}, {5, 24, as_solve_kernel<5, 24>}};
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -23,10 +22,6 @@ static int env_int(const char* name, int dflt) {
 
 static const AsChoice* pick(int mpad) {
     const int r_need = (mpad + 63) / 64;
-    const int want = env_int("RTMPC_AS_MAXW", 0);     // experiment knob: register budget of the R2 = 5 kernel
-    if (want && r_need == 5)
-        for (const auto& c : kAsExp)
-            if (c.maxw == want) return &c;
     for (const auto& c : kAs)
         if (c.r2 >= r_need) return &c;
     return nullptr;
@@ -46,6 +41,7 @@ bool as_configure(const QPDev& P, int max_smem, int* wpb_out, size_t* smem_out, 
     const size_t per_warp = (size_t)as_warp_doubles(P) * sizeof(double);
     int wpb = (int)((size_t)max_smem / per_warp);
     if (wpb > kc->maxw) wpb = kc->maxw;
+    // tuning knob: fewer resident warps per SM (more L1 per warp); used by tools/gpu_as_knobs.py
     if (env_int("RTMPC_AS_WPB", 0) > 0 && env_int("RTMPC_AS_WPB", 0) < wpb) wpb = env_int("RTMPC_AS_WPB", 0);
     if (wpb < 1) return false;
     *err = cudaFuncSetAttribute((const void*)kc->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);

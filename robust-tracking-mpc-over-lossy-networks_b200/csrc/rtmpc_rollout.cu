@@ -7,8 +7,6 @@
 // single launch: no per-step launch latency and no waiting for the slowest instance of every step.
 // An instance whose solve has to be handed to the interior-point kernel parks itself (inst_t, pending,
 // ref_pending); the host runs that kernel on the parked instances and relaunches, which resumes them.
-#include <cstdlib>
-
 #include "rtmpc_as.cuh"
 #include "rtmpc_launch.h"
 #include "rtmpc_loop.cuh"
@@ -167,14 +165,8 @@ static const RoChoice kRo[] = {
     {2, 24, rollout_kernel<2, 24>},  {5, 16, rollout_kernel<5, 16>},  {9, 16, rollout_kernel<9, 16>},
     {12, 16, rollout_kernel<12, 16>}, {16, 16, rollout_kernel<16, 16>},
 };
-static const RoChoice kRoExp[] = {{5, 20, rollout_kernel<5, 20>}, {5, 28, rollout_kernel<5, 28>}};
 static const RoChoice* pick(int mpad) {
     const int r_need = (mpad + 63) / 64;
-    const char* v = getenv("RTMPC_RO_MAXW");       // experiment knob
-    const int want = v ? atoi(v) : 0;
-    if (want && r_need == 5)
-        for (const auto& c : kRoExp)
-            if (c.maxw == want) return &c;
     for (const auto& c : kRo)
         if (c.r2 >= r_need) return &c;
     return nullptr;

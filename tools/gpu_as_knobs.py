@@ -1,4 +1,4 @@
-"""Timing of one cold batch through the active-set kernel under the RTMPC_AS_* experiment knobs."""
+"""Timing of one cold batch through the active-set kernel (RTMPC_AS_WPB limits the resident warps per SM)."""
 import os, sys, time
 import numpy as np
 import torch
@@ -18,4 +18,4 @@ for rep in range(3):
     qp.solve_device(big, bigr, None, U_d, st_d, it_d)
     torch.cuda.synchronize(); dt = time.time() - t0
 steps = ((it_d >> 12) & 0xFFF).sum().item()
-print(f"MAXW={os.environ.get('RTMPC_AS_MAXW')} WPB={os.environ.get('RTMPC_AS_WPB')} GSMEM={os.environ.get('RTMPC_AS_GSMEM')}: B={B} {dt*1e3:.2f} ms -> {B/dt/1e6:.2f} M solves/s, {steps/dt/1e6:.1f} M steps/s; status {torch.bincount(st_d.clamp(min=0), minlength=4).tolist()}")
+print(f"WPB={os.environ.get('RTMPC_AS_WPB')}: B={B} {dt*1e3:.2f} ms -> {B/dt/1e6:.2f} M solves/s, {steps/dt/1e6:.1f} M steps/s; status {torch.bincount(st_d.clamp(min=0), minlength=4).tolist()}")
