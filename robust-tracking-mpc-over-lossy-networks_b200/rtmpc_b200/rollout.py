@@ -156,6 +156,8 @@ class RemoteLoop:
         (``rtmpc_loop_rollout``); otherwise one QP launch + one loop-step launch per control step.  Both
         give identical results."""
         f64 = torch.float64
+        if record and self.t != 0:
+            raise _lib.RtmpcError("record=True writes x_t at row t of a [B, T+1, nx] buffer: reset() the loop first")
         if fused is None:
             fused = True
         if fused:
