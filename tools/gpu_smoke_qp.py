@@ -8,7 +8,8 @@ from rtmpc_b200.qp import BatchedQP
 def report(tag, U, Ug, status, iters, dt):
     ok = np.isin(status, (0, 3))
     err = np.abs(U[ok] - Ug[ok]).reshape(ok.sum(), -1).max(axis=1) if ok.any() else np.zeros(0)
-    print(f"{tag}: B={len(status)} status={np.bincount(status, minlength=4)} iters mean={iters.mean():.2f} max={iters.max()} "
+    iters = iters & 0xFFF                                  # interior-point iterations (see BatchedQP.decode_iters)
+    print(f"{tag}: B={len(status)} status={np.bincount(status, minlength=4)} ipm iters mean={iters.mean():.2f} max={iters.max()} "
           f"maxerr={err.max(initial=0):.3e} p99={np.percentile(err,99) if err.size else 0:.3e} time={dt*1e3:.1f} ms", flush=True)
     return err
 
