@@ -53,9 +53,7 @@ bool as_configure(const QPDev& P, int max_smem, int* wpb_out, size_t* smem_out, 
 cudaError_t as_launch(const QPDev& P, int wpb, size_t smem, int num_sms, const QPLaunch& a) {
     const AsChoice* kc = pick(P.mpad);
     // spread the instances over all SMs first, then fill the warps of each CTA
-    int per_cta = (a.B + num_sms - 1) / num_sms;
-    int warps = per_cta < wpb ? per_cta : wpb;
-    if (warps < 1) warps = 1;
+    int warps = balanced_warps(a.B, num_sms, wpb);
     int blocks = (a.B + warps - 1) / warps;
     if (blocks > num_sms) blocks = num_sms;
     const size_t per_warp = (size_t)as_warp_doubles(P) * sizeof(double);

@@ -37,30 +37,32 @@ namespace rtmpc {
 
 constexpr int RTMPC_FALLBACK = RTMPC_FALLBACK_STATUS;
 
-// per-warp shared memory, in doubles: M, zu, z, v, coef, rvec, 16 parameters, slot lists (2*npad ints)
+// per-warp shared memory, in doubles: M (one row per working-set slot), zu, z, v, coef, 16 parameters, slot lists
+// (2*npad ints).  Kept as small as possible: what the warps do not take is L1 for the shared tables.
 __host__ __device__ inline int as_ms(const QPDev& P) { return P.npad + 2; }
+__host__ __device__ inline int as_mrows(const QPDev& P) { return (P.n + 1) & ~1; }      // slots: the working set has <= n rows
 __host__ __device__ inline int as_warp_doubles(const QPDev& P) {
-    return P.npad * as_ms(P) + 5 * P.npad + 16 + P.npad;
+    return as_mrows(P) * as_ms(P) + 4 * P.npad + 16 + P.npad;
 }
 
 // (offsets are added to one base pointer where they are used: nine live pointers would not stay in registers)
 struct ASWarp {
     double* base;
-    int npad, mm;     // mm = npad * ms
+    int npad, mm;     // mm = rows of M * ms
     __device__ __forceinline__ double* M() const { return base; }
     __device__ __forceinline__ double* zu() const { return base + mm; }
     __device__ __forceinline__ double* z() const { return base + mm + npad; }
     __device__ __forceinline__ double* v() const { return base + mm + 2 * npad; }
     __device__ __forceinline__ double* coef() const { return base + mm + 3 * npad; }
-    __device__ __forceinline__ double* rv() const { return base + mm + 4 * npad; }
-    __device__ __forceinline__ double* xr() const { return base + mm + 5 * npad; }
-    __device__ __forceinline__ int* act_row() const { return reinterpret_cast<int*>(base + mm + 5 * npad + 16); }
+    __device__ __forceinline__ double* rv() const { return base + mm + 3 * npad; }      // shares coef's storage
+    __device__ __forceinline__ double* xr() const { return base + mm + 4 * npad; }
+    __device__ __forceinline__ int* act_row() const { return reinterpret_cast<int*>(base + mm + 4 * npad + 16); }
     __device__ __forceinline__ int* act_sgn() const { return act_row() + npad; }
 };
 
 __device__ __forceinline__ ASWarp as_carve(double* base, const QPDev& P) {
     ASWarp w;
-    w.base = base; w.npad = P.npad; w.mm = P.npad * as_ms(P);
+    w.base = base; w.npad = P.npad; w.mm = as_mrows(P) * as_ms(P);
     return w;
 }
 
@@ -128,7 +130,7 @@ struct ASSlot { int ra; double sa, lam; };
 static __device__ __noinline__ double as_matvec(const double* __restrict__ M, int ms, int hi, int lane, int npad,
                                          const double* __restrict__ vec) {
     double s0 = 0.0, s1 = 0.0;
-    if (lane < npad) {
+    if (lane < hi) {
         const double* row = M + lane * ms;
 #pragma unroll 2
         for (int b = 0; b < hi; b += 2) {
@@ -267,7 +269,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                                      double (&e)[2 * R2], unsigned& actu, unsigned& actl, double tolp, int max_steps,
                                      bool apply_only, ASCounters& cnt) {
     const int npad = P.npad, n = P.n, mpad = P.mpad, ms = as_ms(P);
-    const unsigned slots = (npad >= 32) ? 0xffffffffu : ((1u << npad) - 1u);
+    const unsigned slots = (1u << n) - 1u;          // n <= 30
     while (true) {
         int p = 0;
         double sp = 1.0, cp = 0.0, lam_p = 0.0, wpp = 1.0;
@@ -374,6 +376,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 const unsigned freem = ~amask & slots;
                 if (na >= n || !freem) return RTMPC_FALLBACK;
                 const int s = __ffs(freem) - 1;
+                __syncwarp();                 // rv shares coef's storage: every lane is done streaming
                 if (lane < npad) w.rv()[lane] = rr;
                 __syncwarp();
                 as_border(w.M(), w.rv(), ms, as_hi(amask | (1u << s)), lane, s, rr, kappa);
@@ -594,9 +597,11 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
     else {
         // M starts empty
         if (lane < npad) {
-            double* row = w.M() + lane * ms;
+            if (lane < as_mrows(P)) {
+                double* row = w.M() + lane * ms;
 #pragma unroll 1
-            for (int b = 0; b < npad; b += 2) *reinterpret_cast<double2*>(row + b) = make_double2(0.0, 0.0);
+                for (int b = 0; b < npad; b += 2) *reinterpret_cast<double2*>(row + b) = make_double2(0.0, 0.0);
+            }
             w.act_row()[lane] = 0;
             w.act_sgn()[lane] = 0;
         }

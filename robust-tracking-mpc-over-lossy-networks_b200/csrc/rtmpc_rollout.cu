@@ -15,13 +15,13 @@ namespace rtmpc {
 
 // per-warp shared memory of the rollout, in doubles:
 //   closed-loop state | packet payload | x_nom_0 of this step's solve | warm-start record of each QP | solver scratch
-__host__ __device__ inline int rollout_fixed_doubles(const QPDev& P0, const QPDev& P1) {
+__host__ __device__ inline int rollout_fixed_doubles(const QPDev& P0, const QPDev& P1, bool two) {
     return loop_smem_doubles(P0.N, P0.nu) + (((P0.N + 1) * P0.nu + 1) & ~1) + LOOP_MAX_NX +
-           ((((P0.npad + 2) >> 1) + 1) & ~1) + ((((P1.npad + 2) >> 1) + 1) & ~1);      // every part even (16-byte alignment)
+           ((((P0.npad + 2) >> 1) + 1) & ~1) + (two ? ((((P1.npad + 2) >> 1) + 1) & ~1) : 0);   // every part even (16-byte alignment)
 }
-__host__ __device__ inline int rollout_warp_doubles(const QPDev& P0, const QPDev& P1) {
+__host__ __device__ inline int rollout_warp_doubles(const QPDev& P0, const QPDev& P1, bool two) {
     const int s0 = as_warp_doubles(P0), s1 = as_warp_doubles(P1);
-    return rollout_fixed_doubles(P0, P1) + (s0 > s1 ? s0 : s1);
+    return rollout_fixed_doubles(P0, P1, two) + (s0 > s1 ? s0 : s1);
 }
 
 // P0: the controller's problem; P1: the "packet received" problem of ExtendedTubeTrackingMPC, chosen per step and
@@ -36,14 +36,14 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
     const int nx = P0.nx, nu = P0.nu;
     const int usz = (P0.N + 1) * nu;
     const bool two = a.two != 0;
-    double* wbase = smem + (size_t)warp * rollout_warp_doubles(P0, P1);
+    double* wbase = smem + (size_t)warp * rollout_warp_doubles(P0, P1, two);
     LoopSmemState S;
     S.base = wbase;
     double* U_s = S.base + loop_smem_doubles(P0.N, nu);                  // this step's packet payload
     double* x0_s = U_s + ((usz + 1) & ~1);                                // x_nom[:,0] of this step's solve
     int* warm0_s = reinterpret_cast<int*>(x0_s + LOOP_MAX_NX);            // warm-start records
     int* warm1_s = warm0_s + 2 * ((((P0.npad + 2) >> 1) + 1) & ~1);
-    double* scratch = wbase + rollout_fixed_doubles(P0, P1);
+    double* scratch = wbase + rollout_fixed_doubles(P0, P1, two);
     const bool ext = L.actuator == RTMPC_ACT_EXTENDED;
 
 #pragma unroll 1
@@ -183,11 +183,9 @@ cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, in
                            const RolloutArgs& a, cudaStream_t stream) {
     const RoChoice* kc = pick(P.mpad);
     if (wpb > kc->maxw) wpb = kc->maxw;
-    const size_t per_warp = (size_t)rollout_warp_doubles(P, P1) * sizeof(double);
+    const size_t per_warp = (size_t)rollout_warp_doubles(P, P1, a.two != 0) * sizeof(double);
     while (wpb > 1 && per_warp * wpb > (size_t)max_smem) --wpb;
-    int per_cta = (a.B + num_sms - 1) / num_sms;
-    int warps = per_cta < wpb ? per_cta : wpb;
-    if (warps < 1) warps = 1;
+    int warps = balanced_warps(a.B, num_sms, wpb);
     int blocks = (a.B + warps - 1) / warps;
     if (blocks > num_sms) blocks = num_sms;
     kc->fn<<<blocks, warps * 32, per_warp * warps, stream>>>(P, P1, L, a);
