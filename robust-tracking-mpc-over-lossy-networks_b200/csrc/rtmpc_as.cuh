@@ -11,16 +11,19 @@
 // M is kept explicitly and updated by bordering (row added) / a rank-one downdate (row dropped): a step
 // is one small mat-vec, a few warp reductions and one pass over |A|+1 rows of W.  No factorisation.
 //
-// Data placement.  Per lane, in registers: value t = (G z)_i and bounds up_i, lo_i of its 2*R2 rows
-// (rows r2*64 + 2*lane + {0,1}: every table is read with 16-byte loads), plus the multiplier and row
-// of working-set slot `lane`.  Per warp, in shared memory: M (npad x npad), z_u, z and three scratch
-// vectors.  Shared by all warps, read through L1: W, G', Y and the parameter tables.
+// Data placement.  Per lane, in registers: e_i = (G z)_i - up_i of its 2*R2 rows (rows r2*64 + 2*lane + {0,1}:
+// every table is read with 16-byte loads; the lower side of a row is -e_i - wid_i with the constant width
+// wid = up - lo read from a table), plus the multiplier and row of working-set slot `lane`.  Per warp, in shared
+// memory: M (one row per slot), z_u, z and two scratch vectors.  Shared by all warps, read through L1: W, G', Y
+// and the parameter tables.  The kernel is kept small on purpose (real calls for the dense helpers, rolled
+// loops): the warps of an SM are all at different points of their solves and share one instruction cache.
 //
 // Per instance (mirrored by tools/as_model.py::solve_as_inv):
 //   0. parameter rows; z_u; row values at z_u; no row violated -> z_u is optimal.
-//   1. warm start: last control step's certified active set moved one stage earlier (QPDev.shift) is
-//      bordered in row by row (dependent rows skipped), multipliers = M rhs, rows with negative
-//      multipliers are dropped one at a time until the set is dual feasible.
+//   1. warm start: last control step's certified active set moved one stage earlier (QPDev.shift): its signed
+//      sub-matrix of W is inverted in place (Gauss-Jordan, rows that depend on earlier ones skipped -- the same
+//      pivots as bordering row by row), multipliers = M rhs, rows with negative multipliers are dropped one at
+//      a time until the set is dual feasible.
 //   2. Goldfarb-Idnani: add the most violated row with primal/dual ratio test (partial steps drop
 //      the blocking row) until no row is violated by more than 1e-11 (scaled).  Strictly increasing
 //      dual objective: no cycling.  Linear dependence without a blocking row = primal infeasible.
@@ -48,8 +51,12 @@ __host__ __device__ inline int as_warp_doubles(const QPDev& P) {
 // (offsets are added to one base pointer where they are used: nine live pointers would not stay in registers)
 struct ASWarp {
     double* base;
+    int off;          // base as an offset (in doubles) into the kernel's dynamic shared memory, for the real-call helpers
     int npad, mm;     // mm = rows of M * ms
     __device__ __forceinline__ double* M() const { return base; }
+    __device__ __forceinline__ int Mo() const { return off; }
+    __device__ __forceinline__ int vo() const { return off + mm + 2 * npad; }
+    __device__ __forceinline__ int rvo() const { return off + mm + 3 * npad; }
     __device__ __forceinline__ double* zu() const { return base + mm; }
     __device__ __forceinline__ double* z() const { return base + mm + npad; }
     __device__ __forceinline__ double* v() const { return base + mm + 2 * npad; }
@@ -61,8 +68,9 @@ struct ASWarp {
 };
 
 __device__ __forceinline__ ASWarp as_carve(double* base, const QPDev& P) {
+    extern __shared__ __align__(16) double as_smem[];
     ASWarp w;
-    w.base = base; w.npad = P.npad; w.mm = as_mrows(P) * as_ms(P);
+    w.base = base; w.off = (int)(base - as_smem); w.npad = P.npad; w.mm = as_mrows(P) * as_ms(P);
     return w;
 }
 
@@ -127,11 +135,14 @@ __device__ __forceinline__ double as_wsum(double v) { return warp_sum(v); }
 struct ASSlot { int ra; double sa, lam; };
 
 // out_a = sum_b M[a][b] vec[b] over the slots below hi (free slots hold zeros)
-static __device__ __noinline__ double as_matvec(const double* __restrict__ M, int ms, int hi, int lane, int npad,
-                                         const double* __restrict__ vec) {
+// (the helpers below are real calls; they address the per-warp block through offsets into the dynamic shared memory
+//  array so that their loads and stores are shared-memory instructions, not generic ones)
+static __device__ __noinline__ double as_matvec(int Mo, int ms, int hi, int lane, int vo) {
+    extern __shared__ __align__(16) double as_smem[];
     double s0 = 0.0, s1 = 0.0;
     if (lane < hi) {
-        const double* row = M + lane * ms;
+        const double* row = as_smem + Mo + lane * ms;
+        const double* vec = as_smem + vo;
 #pragma unroll 2
         for (int b = 0; b < hi; b += 2) {
             const double2 mm = ld2(row + b), vv = ld2(vec + b);
@@ -144,8 +155,10 @@ static __device__ __noinline__ double as_matvec(const double* __restrict__ M, in
 
 // M grows by slot s:  [[M + r r'/kappa, -r/kappa], [-r'/kappa, 1/kappa]]   (r in rv, zero on free slots;
 // hi = even number of slots covering every occupied one and s)
-static __device__ __noinline__ void as_border(double* __restrict__ M, const double* __restrict__ rv, int ms, int hi, int lane,
-                                       int s, double r_own, double kappa) {
+static __device__ __noinline__ void as_border(int Mo, int rvo, int ms, int hi, int lane, int s, double r_own, double kappa) {
+    extern __shared__ __align__(16) double as_smem[];
+    double* M = as_smem + Mo;
+    const double* rv = as_smem + rvo;
     const double ik = __drcp_rn(kappa);
     if (lane < hi) {
         double* row = M + lane * ms;
@@ -176,7 +189,10 @@ static __device__ __noinline__ void as_border(double* __restrict__ M, const doub
 }
 
 // slot j leaves:  M <- M - m_j m_j' / M_jj, row and column j cleared (tmp: npad doubles of scratch)
-static __device__ __noinline__ void as_downdate(double* __restrict__ M, double* __restrict__ tmp, int ms, int hi, int lane, int j) {
+static __device__ __noinline__ void as_downdate(int Mo, int tmpo, int ms, int hi, int lane, int j) {
+    extern __shared__ __align__(16) double as_smem[];
+    double* M = as_smem + Mo;
+    double* tmp = as_smem + tmpo;
     if (lane < hi) tmp[lane] = M[j * ms + lane];
     __syncwarp();
     const double ij = __drcp_rn(tmp[j]);
@@ -202,7 +218,9 @@ static __device__ __noinline__ void as_downdate(double* __restrict__ M, double* 
 // has lost its size relative to the original diagonal (diag0) marks a row that depends on the rows before it: it is
 // skipped, and its row and column are cleared at the end, which leaves the inverse over the remaining rows.
 // Returns the mask of skipped rows.
-static __device__ __noinline__ unsigned as_invert(double* __restrict__ M, int ms, int nc, int hi, int lane, double diag0) {
+static __device__ __noinline__ unsigned as_invert(int Mo, int ms, int nc, int hi, int lane, double diag0) {
+    extern __shared__ __align__(16) double as_smem[];
+    double* M = as_smem + Mo;
     unsigned dead = 0;
 #pragma unroll 1
     for (int k = 0; k < nc; ++k) {
@@ -223,7 +241,7 @@ static __device__ __noinline__ unsigned as_invert(double* __restrict__ M, int ms
         __syncwarp();
         if (lane < nc && lane != k) {
             double* row = M + lane * ms;
-            const double* __restrict__ rk = M + k * ms;
+            const double* rk = M + k * ms;
             const double f = row[k];
             row[k] = 0.0;
             if (f != 0.0) {
@@ -307,7 +325,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 const double v = occ ? sl.sa * sp * Wp[sl.ra] : 0.0;
                 if (lane < npad) w.v()[lane] = v;
                 __syncwarp();
-                rr = occ ? as_matvec(w.M(), ms, hi, lane, npad, w.v()) : 0.0;
+                rr = occ ? as_matvec(w.Mo(), ms, hi, lane, w.vo()) : 0.0;
                 kappa = wpp - as_wsum(v * rr);
                 dependent = !(kappa > 1e-11 * wpp);
                 const double rmax = as_wmax(fabs(rr));
@@ -379,7 +397,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 __syncwarp();                 // rv shares coef's storage: every lane is done streaming
                 if (lane < npad) w.rv()[lane] = rr;
                 __syncwarp();
-                as_border(w.M(), w.rv(), ms, as_hi(amask | (1u << s)), lane, s, rr, kappa);
+                as_border(w.Mo(), w.rvo(), ms, as_hi(amask | (1u << s)), lane, s, rr, kappa);
                 if (lane == s) { sl.ra = p; sl.sa = sp; sl.lam = lam_p; w.act_row()[s] = p; w.act_sgn()[s] = (int)sp; }
                 as_mark(lane, p, (int)sp, true, actu, actl);
                 amask |= 1u << s;
@@ -389,7 +407,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
             }
             // partial step: the blocking row leaves the working set
             as_mark(lane, w.act_row()[j1], w.act_sgn()[j1], false, actu, actl);
-            as_downdate(w.M(), w.v(), ms, hi, lane, j1);
+            as_downdate(w.Mo(), w.vo(), ms, hi, lane, j1);
             amask &= ~(1u << j1);
             cnt.sq += na * na;
         }
@@ -425,7 +443,7 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
         if (pass > 0) {
             if (lane < npad) w.v()[lane] = resid;
             __syncwarp();
-            const double dl = occ ? as_matvec(w.M(), ms, hi, lane, npad, w.v()) : 0.0;
+            const double dl = occ ? as_matvec(w.Mo(), ms, hi, lane, w.vo()) : 0.0;
             lam += dl;
             if (lane < npad) w.coef()[lane] = dl * sl.sa;
             __syncwarp();
@@ -642,7 +660,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                     diag0 = Wa[sl.ra];
                 }
                 __syncwarp();
-                const unsigned dead = as_invert(w.M(), ms, nc, hi, lane, diag0);
+                const unsigned dead = as_invert(w.Mo(), ms, nc, hi, lane, diag0);
                 amask = (((nc >= 32) ? 0xffffffffu : ((1u << nc) - 1u))) & ~dead;
                 cnt.sq += nc * nc * nc / 2;
             }
@@ -664,7 +682,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                 const int hi = as_hi(amask);
                 if (lane < npad) w.v()[lane] = occ ? rhs : 0.0;
                 __syncwarp();
-                const double lamv = occ ? as_matvec(w.M(), ms, hi, lane, npad, w.v()) : 0.0;
+                const double lamv = occ ? as_matvec(w.Mo(), ms, hi, lane, w.vo()) : 0.0;
                 const ASArg lm = as_wargmin(occ ? lamv : RTMPC_INF, lane);
                 const double lmaxabs = as_wmax(fabs(lamv));
                 cnt.sq += na * na;
@@ -673,7 +691,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                     sl.lam = occ ? fmax(lamv, 0.0) : 0.0;
                     break;
                 }
-                as_downdate(w.M(), w.v(), ms, hi, lane, lm.idx);
+                as_downdate(w.Mo(), w.vo(), ms, hi, lane, lm.idx);
                 amask &= ~(1u << lm.idx);
                 cnt.sq += na * na;
             }

@@ -98,9 +98,9 @@ __device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, const State
     double worst = -1e300;
 #pragma unroll 4
     for (int i = first; i < L.nz_rows; i += stride) {
-        double acc = -L.hz[i];
+        double acc = -__ldg(L.hz + i);
 #pragma unroll
-        for (int k = 0; k < AX; ++k) if (k < nx) acc = fma(L.Hz[i * nx + k], d[k], acc);
+        for (int k = 0; k < AX; ++k) if (k < nx) acc = fma(__ldg(L.Hz + i * nx + k), d[k], acc);
         worst = fmax(worst, acc);
     }
     return worst;
@@ -340,8 +340,8 @@ __device__ __forceinline__ void loop_step_body_warp(const LoopDev& L, const Stat
         double wa = 0.0, wb = 0.0;
         if (lane >= 1 && lane <= ((nx + 1) >> 1)) {
             const int k = 2 * (lane - 1);
-            wa = L.w_half[k] * (2.0 * u01_from_bits(r.x, r.y) - 1.0);
-            if (k + 1 < nx) wb = L.w_half[k + 1] * (2.0 * u01_from_bits(r.z, r.w) - 1.0);
+            wa = __ldg(L.w_half + k) * (2.0 * u01_from_bits(r.x, r.y) - 1.0);
+            if (k + 1 < nx) wb = __ldg(L.w_half + k + 1) * (2.0 * u01_from_bits(r.z, r.w) - 1.0);
         }
         const int src = 1 + ((lane < nx ? lane : 0) >> 1);
         const double ga = __shfl_sync(0xffffffffu, wa, src), gb = __shfl_sync(0xffffffffu, wb, src);
@@ -373,14 +373,14 @@ __device__ __forceinline__ void loop_step_body_warp(const LoopDev& L, const Stat
             else {
                 double acc = buf[N * nu + j];
 #pragma unroll 1
-                for (int k = 0; k < nx; ++k) acc = fma(-L.K[j * nx + k], smart ? S.x(k) : S.x_nom(k), acc);
+                for (int k = 0; k < nx; ++k) acc = fma(-__ldg(L.K + j * nx + k), smart ? S.x(k) : S.x_nom(k), acc);
                 u_nom[j] = acc;
             }
             if (smart) u[j] = u_nom[j];
             else {
                 double acc = u_nom[j];
 #pragma unroll 1
-                for (int k = 0; k < nx; ++k) acc = fma(-L.Kp[j * nx + k], S.x(k) - S.x_nom(k), acc);
+                for (int k = 0; k < nx; ++k) acc = fma(-__ldg(L.Kp + j * nx + k), S.x(k) - S.x_nom(k), acc);
                 u[j] = acc;
             }
         }
@@ -397,13 +397,13 @@ __device__ __forceinline__ void loop_step_body_warp(const LoopDev& L, const Stat
                 else {
                     double acc = buf[N * nu + j];
 #pragma unroll 1
-                    for (int k = 0; k < nx; ++k) acc = fma(-L.K[j * nx + k], (ext || cons) ? S.x_nom(k) : S.x(k), acc);
+                    for (int k = 0; k < nx; ++k) acc = fma(-__ldg(L.K + j * nx + k), (ext || cons) ? S.x_nom(k) : S.x(k), acc);
                     un = acc;
                 }
                 if (ext) {
                     double acc = un;
 #pragma unroll 1
-                    for (int k = 0; k < nx; ++k) acc = fma(-L.Kp[j * nx + k], S.x(k) - S.x_nom(k), acc);
+                    for (int k = 0; k < nx; ++k) acc = fma(-__ldg(L.Kp + j * nx + k), S.x(k) - S.x_nom(k), acc);
                     un = acc;
                 }
                 uh[j] = un;
@@ -420,17 +420,17 @@ __device__ __forceinline__ void loop_step_body_warp(const LoopDev& L, const Stat
         if (!smart) {
             double acc = 0.0;
 #pragma unroll 1
-            for (int k = 0; k < nx; ++k) acc = fma(L.A[i * nx + k], S.x_nom(k), acc);
+            for (int k = 0; k < nx; ++k) acc = fma(__ldg(L.A + i * nx + k), S.x_nom(k), acc);
 #pragma unroll
-            for (int j = 0; j < LOOP_MAX_NU; ++j) if (j < nu) acc = fma(L.Bm[i * nu + j], u_nom[j], acc);
+            for (int j = 0; j < LOOP_MAX_NU; ++j) if (j < nu) acc = fma(__ldg(L.Bm + i * nu + j), u_nom[j], acc);
             xn_new = acc;
         } else xn_new = S.x_nom(i);
         if (L.plant != RTMPC_PLANT_CARTPOLE) {
             double acc = 0.0;
 #pragma unroll 1
-            for (int k = 0; k < nx; ++k) acc = fma(L.A[i * nx + k], S.x(k), acc);
+            for (int k = 0; k < nx; ++k) acc = fma(__ldg(L.A + i * nx + k), S.x(k), acc);
 #pragma unroll
-            for (int j = 0; j < LOOP_MAX_NU; ++j) if (j < nu) acc = fma(L.Bm[i * nu + j], u[j], acc);
+            for (int j = 0; j < LOOP_MAX_NU; ++j) if (j < nu) acc = fma(__ldg(L.Bm + i * nu + j), u[j], acc);
             x_new = acc + wi;
         }
         {
@@ -440,10 +440,10 @@ __device__ __forceinline__ void loop_step_body_warp(const LoopDev& L, const Stat
                 double xb;
                 if (gamma == 1) xb = cons ? S.x_nom(k) : S.x(k);
                 else xb = (ext && x_nom0_b) ? x_nom0_b[k] : S.x_hat(k);
-                acc = fma(L.A[i * nx + k], xb, acc);
+                acc = fma(__ldg(L.A + i * nx + k), xb, acc);
             }
 #pragma unroll
-            for (int j = 0; j < LOOP_MAX_NU; ++j) if (j < nu) acc = fma(L.Bm[i * nu + j], uh[j], acc);
+            for (int j = 0; j < LOOP_MAX_NU; ++j) if (j < nu) acc = fma(__ldg(L.Bm + i * nu + j), uh[j], acc);
             xh_new = acc;
         }
     }
