@@ -527,22 +527,22 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
             }
         }
     }
-    double worst = -RTMPC_INF;
+    // any row outside the working set violated by more than the tolerance?
+    bool viol = false;
 #pragma unroll
     for (int r2 = 0; r2 < R2; ++r2) {
         const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane);
-        if (!((actu >> (2 * r2)) & 1u)) worst = fmax(worst, e[2 * r2]);
-        if (!((actl >> (2 * r2)) & 1u)) worst = fmax(worst, -e[2 * r2] - wd.x);
-        if (!((actu >> (2 * r2 + 1)) & 1u)) worst = fmax(worst, e[2 * r2 + 1]);
-        if (!((actl >> (2 * r2 + 1)) & 1u)) worst = fmax(worst, -e[2 * r2 + 1] - wd.y);
+        viol |= (!((actu >> (2 * r2)) & 1u) && e[2 * r2] > tolp) | (!((actl >> (2 * r2)) & 1u) && -e[2 * r2] - wd.x > tolp) |
+                (!((actu >> (2 * r2 + 1)) & 1u) && e[2 * r2 + 1] > tolp) |
+                (!((actl >> (2 * r2 + 1)) & 1u) && -e[2 * r2 + 1] - wd.y > tolp);
     }
-    worst = as_wmax(worst);
+    const bool violated = __any_sync(RTMPC_FULL_MASK, viol);
     const double lmin = as_wmin(occ ? lam : RTMPC_INF), lmaxabs = as_wmax(occ ? fabs(lam) : 0.0);
     const double rmax = as_wmax(fabs(resid));
     if (occ) sl.lam = fmax(lam, 0.0);
     if (rmax > tolp) return 2;                                   // refinement did not converge
     if (lmin < -1e-9 * (1.0 + lmaxabs)) return 2;
-    return (worst > tolp) ? 1 : 0;
+    return violated ? 1 : 0;
 }
 
 // One instance, one warp.  x_init / ref: this instance's parameters (ref may be NULL); warm_inst: this
@@ -597,13 +597,14 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             e[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, e[2 * r2 + 1]));
         }
     }
-    double vmax = -RTMPC_INF;
+    // is any row on or beyond a bound?  (only the sign matters here: compares and a vote, no FP64 max chain)
+    bool touched = false;
 #pragma unroll
     for (int r2 = 0; r2 < R2; ++r2) {
         const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane);
-        vmax = fmax(vmax, fmax(fmax(e[2 * r2], -e[2 * r2] - wd.x), fmax(e[2 * r2 + 1], -e[2 * r2 + 1] - wd.y)));
+        touched |= (e[2 * r2] >= 0.0) | (-e[2 * r2] - wd.x >= 0.0) | (e[2 * r2 + 1] >= 0.0) | (-e[2 * r2 + 1] - wd.y >= 0.0);
     }
-    vmax = as_wmax(vmax);
+    const bool feasible_u = !__any_sync(RTMPC_FULL_MASK, touched);
     __syncwarp();
 
     int status = RTMPC_OPTIMAL;
@@ -611,7 +612,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
     ASSlot sl;
     sl.ra = 0; sl.sa = 0.0; sl.lam = 0.0;
     if (par_bad) status = RTMPC_INFEASIBLE;
-    else if (vmax < 0.0) status = RTMPC_OPTIMAL;      // the unconstrained minimiser is feasible
+    else if (feasible_u) status = RTMPC_OPTIMAL;      // the unconstrained minimiser is feasible
     else {
         // M starts empty
         if (lane < npad) {

@@ -101,7 +101,7 @@ __device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, const State
         double acc = -__ldg(L.hz + i);
 #pragma unroll
         for (int k = 0; k < AX; ++k) if (k < nx) acc = fma(__ldg(L.Hz + i * nx + k), d[k], acc);
-        worst = fmax(worst, acc);
+        if (acc > worst) worst = acc;          // (a compare and a select: FP64 fmax is a seven-instruction sequence)
     }
     return worst;
 }
