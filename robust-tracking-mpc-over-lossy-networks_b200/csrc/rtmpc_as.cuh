@@ -231,7 +231,7 @@ static __device__ __noinline__ unsigned as_invert(int Mo, int ms, int nc, int hi
         if (lane == k) {
             double* row = M + k * ms;
             row[k] = 1.0;
-#pragma unroll 1
+#pragma unroll 2
             for (int b = 0; b < hi; b += 2) {
                 double2 mm = ld2(row + b);
                 mm.x *= ip; mm.y *= ip;
@@ -245,7 +245,7 @@ static __device__ __noinline__ unsigned as_invert(int Mo, int ms, int nc, int hi
             const double f = row[k];
             row[k] = 0.0;
             if (f != 0.0) {
-#pragma unroll 1
+#pragma unroll 2
                 for (int b = 0; b < hi; b += 2) {
                     const double2 kk = ld2(rk + b);
                     double2 mm = ld2(row + b);
@@ -532,9 +532,9 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
 #pragma unroll
     for (int r2 = 0; r2 < R2; ++r2) {
         const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane);
-        viol |= (!((actu >> (2 * r2)) & 1u) && e[2 * r2] > tolp) | (!((actl >> (2 * r2)) & 1u) && -e[2 * r2] - wd.x > tolp) |
-                (!((actu >> (2 * r2 + 1)) & 1u) && e[2 * r2 + 1] > tolp) |
-                (!((actl >> (2 * r2 + 1)) & 1u) && -e[2 * r2 + 1] - wd.y > tolp);
+        viol = viol || (!((actu >> (2 * r2)) & 1u) && e[2 * r2] > tolp) || (!((actl >> (2 * r2)) & 1u) && e[2 * r2] + wd.x < -tolp) ||
+               (!((actu >> (2 * r2 + 1)) & 1u) && e[2 * r2 + 1] > tolp) ||
+               (!((actl >> (2 * r2 + 1)) & 1u) && e[2 * r2 + 1] + wd.y < -tolp);
     }
     const bool violated = __any_sync(RTMPC_FULL_MASK, viol);
     const double lmin = as_wmin(occ ? lam : RTMPC_INF), lmaxabs = as_wmax(occ ? fabs(lam) : 0.0);
@@ -602,7 +602,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
 #pragma unroll
     for (int r2 = 0; r2 < R2; ++r2) {
         const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane);
-        touched |= (e[2 * r2] >= 0.0) | (-e[2 * r2] - wd.x >= 0.0) | (e[2 * r2 + 1] >= 0.0) | (-e[2 * r2 + 1] - wd.y >= 0.0);
+        touched = touched || e[2 * r2] >= 0.0 || e[2 * r2] + wd.x <= 0.0 || e[2 * r2 + 1] >= 0.0 || e[2 * r2 + 1] + wd.y <= 0.0;
     }
     const bool feasible_u = !__any_sync(RTMPC_FULL_MASK, touched);
     __syncwarp();
@@ -733,13 +733,17 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             for (int i = lane; i < nrow; i += 32) {
                 if (i >= N * nu && P.nss == 0) continue;
                 double acc = 0.0, acc2 = 0.0;
+                const double* __restrict__ up = P.UPhiT + i;          // zero-padded to npad columns
+                const double* zz = w.z();
 #pragma unroll 2
-                for (int k = 0; k < npad; k += 2) {          // UPhiT is zero-padded to npad columns
-                    acc = fma(P.UPhiT[(size_t)k * nrow + i], w.z()[k], acc);
-                    acc2 = fma(P.UPhiT[(size_t)(k + 1) * nrow + i], w.z()[k + 1], acc2);
+                for (int k = 0; k < npad; k += 2) {
+                    acc = fma(up[0], zz[k], acc);
+                    acc2 = fma(up[nrow], zz[k + 1], acc2);
+                    up += 2 * nrow;
                 }
+                const double* __restrict__ ps = P.UPsiT + i;
 #pragma unroll 1
-                for (int k = 0; k < nx; ++k) acc = fma(P.UPsiT[(size_t)k * nrow + i], w.xr()[k], acc);
+                for (int k = 0; k < nx; ++k) { acc = fma(ps[0], w.xr()[k], acc); ps += nrow; }
                 U_out_inst[i] = has_sol ? acc + acc2 : nanv;
             }
         }

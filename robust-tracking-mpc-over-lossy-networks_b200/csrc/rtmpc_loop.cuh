@@ -99,8 +99,18 @@ __device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, const State
 #pragma unroll 4
     for (int i = first; i < L.nz_rows; i += stride) {
         double acc = -__ldg(L.hz + i);
+        if (NX > 0 && (NX & 1) == 0) {
+            const double2* __restrict__ h2 = reinterpret_cast<const double2*>(L.Hz + i * NX);      // rows are 16-byte aligned
 #pragma unroll
-        for (int k = 0; k < AX; ++k) if (k < nx) acc = fma(__ldg(L.Hz + i * nx + k), d[k], acc);
+            for (int k = 0; k < AX / 2; ++k) {
+                const double2 hh = __ldg(h2 + k);
+                acc = fma(hh.x, d[2 * k], acc);
+                acc = fma(hh.y, d[2 * k + 1], acc);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < AX; ++k) if (k < nx) acc = fma(__ldg(L.Hz + i * nx + k), d[k], acc);
+        }
         if (acc > worst) worst = acc;          // (a compare and a select: FP64 fmax is a seven-instruction sequence)
     }
     return worst;
