@@ -43,7 +43,7 @@ constexpr int RTMPC_FALLBACK = RTMPC_FALLBACK_STATUS;
 // per-warp shared memory, in doubles: M (one row per working-set slot), zu, z, v, coef, 16 parameters, slot lists
 // (2*npad ints).  Kept as small as possible: what the warps do not take is L1 for the shared tables.
 __host__ __device__ inline int as_ms(const QPDev& P) { return P.npad + 2; }
-__host__ __device__ inline int as_mrows(const QPDev& P) { return (P.n + 1) & ~1; }      // slots: the working set has <= n rows
+__host__ __device__ inline int as_mrows(const QPDev& P) { return P.npad; }      // one row per slot (<= n rows in the working set), padded to 4
 __host__ __device__ inline int as_warp_doubles(const QPDev& P) {
     return as_mrows(P) * as_ms(P) + 4 * P.npad + 16 + P.npad;
 }
@@ -143,11 +143,14 @@ static __device__ __noinline__ double as_matvec(int Mo, int ms, int hi, int lane
     if (lane < hi) {
         const double* row = as_smem + Mo + lane * ms;
         const double* vec = as_smem + vo;
-#pragma unroll 2
-        for (int b = 0; b < hi; b += 2) {
-            const double2 mm = ld2(row + b), vv = ld2(vec + b);
-            s0 = fma(mm.x, vv.x, s0);
-            s1 = fma(mm.y, vv.y, s1);
+        // four columns per trip (npad is a multiple of 4; columns and entries beyond hi hold zeros)
+#pragma unroll 1
+        for (int b = 0; b < hi; b += 4) {
+            const double2 m0 = ld2(row + b), v0 = ld2(vec + b), m1 = ld2(row + b + 2), v1 = ld2(vec + b + 2);
+            s0 = fma(m0.x, v0.x, s0);
+            s1 = fma(m0.y, v0.y, s1);
+            s0 = fma(m1.x, v1.x, s0);
+            s1 = fma(m1.y, v1.y, s1);
         }
     }
     return s0 + s1;
@@ -164,22 +167,23 @@ static __device__ __noinline__ void as_border(int Mo, int rvo, int ms, int hi, i
         double* row = M + lane * ms;
         if (lane == s) {
 #pragma unroll 1
-            for (int b = 0; b < hi; b += 2) {
-                const double2 rr = ld2(rv + b);
-                row[b] = -rr.x * ik;
-                row[b + 1] = -rr.y * ik;
+            for (int b = 0; b < hi; b += 4) {
+                const double2 r0 = ld2(rv + b), r1 = ld2(rv + b + 2);
+                *reinterpret_cast<double2*>(row + b) = make_double2(-r0.x * ik, -r0.y * ik);
+                *reinterpret_cast<double2*>(row + b + 2) = make_double2(-r1.x * ik, -r1.y * ik);
             }
             row[s] = ik;
         } else {
             const double c = r_own * ik;
             if (c != 0.0) {
 #pragma unroll 1
-                for (int b = 0; b < hi; b += 2) {
-                    const double2 rr = ld2(rv + b);
-                    double2 mm = ld2(row + b);
-                    mm.x = fma(c, rr.x, mm.x);
-                    mm.y = fma(c, rr.y, mm.y);
-                    *reinterpret_cast<double2*>(row + b) = mm;
+                for (int b = 0; b < hi; b += 4) {
+                    const double2 r0 = ld2(rv + b), r1 = ld2(rv + b + 2);
+                    double2 m0 = ld2(row + b), m1 = ld2(row + b + 2);
+                    m0.x = fma(c, r0.x, m0.x); m0.y = fma(c, r0.y, m0.y);
+                    m1.x = fma(c, r1.x, m1.x); m1.y = fma(c, r1.y, m1.y);
+                    *reinterpret_cast<double2*>(row + b) = m0;
+                    *reinterpret_cast<double2*>(row + b + 2) = m1;
                 }
             }
             row[s] = -c;
@@ -193,7 +197,7 @@ static __device__ __noinline__ void as_downdate(int Mo, int tmpo, int ms, int hi
     extern __shared__ __align__(16) double as_smem[];
     double* M = as_smem + Mo;
     double* tmp = as_smem + tmpo;
-    if (lane < hi) tmp[lane] = M[j * ms + lane];
+    if (lane < hi) tmp[lane] = M[j * ms + lane];      // (columns between the highest slot and hi hold zeros)
     __syncwarp();
     const double ij = __drcp_rn(tmp[j]);
     if (lane < hi) {
@@ -201,12 +205,13 @@ static __device__ __noinline__ void as_downdate(int Mo, int tmpo, int ms, int hi
         const double c = (lane == j) ? -1.0 : -row[j] * ij;      // row j: m_j - m_j = 0
         if (c != 0.0) {
 #pragma unroll 1
-            for (int b = 0; b < hi; b += 2) {
-                const double2 vv = ld2(tmp + b);
-                double2 mm = ld2(row + b);
-                mm.x = (lane == j) ? 0.0 : fma(c, vv.x, mm.x);
-                mm.y = (lane == j) ? 0.0 : fma(c, vv.y, mm.y);
-                *reinterpret_cast<double2*>(row + b) = mm;
+            for (int b = 0; b < hi; b += 4) {
+                const double2 v0 = ld2(tmp + b), v1 = ld2(tmp + b + 2);
+                double2 m0 = ld2(row + b), m1 = ld2(row + b + 2);
+                m0.x = (lane == j) ? 0.0 : fma(c, v0.x, m0.x); m0.y = (lane == j) ? 0.0 : fma(c, v0.y, m0.y);
+                m1.x = (lane == j) ? 0.0 : fma(c, v1.x, m1.x); m1.y = (lane == j) ? 0.0 : fma(c, v1.y, m1.y);
+                *reinterpret_cast<double2*>(row + b) = m0;
+                *reinterpret_cast<double2*>(row + b + 2) = m1;
             }
         }
         row[j] = 0.0;
@@ -231,11 +236,12 @@ static __device__ __noinline__ unsigned as_invert(int Mo, int ms, int nc, int hi
         if (lane == k) {
             double* row = M + k * ms;
             row[k] = 1.0;
-#pragma unroll 2
-            for (int b = 0; b < hi; b += 2) {
-                double2 mm = ld2(row + b);
-                mm.x *= ip; mm.y *= ip;
-                *reinterpret_cast<double2*>(row + b) = mm;
+#pragma unroll 1
+            for (int b = 0; b < hi; b += 4) {
+                double2 m0 = ld2(row + b), m1 = ld2(row + b + 2);
+                m0.x *= ip; m0.y *= ip; m1.x *= ip; m1.y *= ip;
+                *reinterpret_cast<double2*>(row + b) = m0;
+                *reinterpret_cast<double2*>(row + b + 2) = m1;
             }
         }
         __syncwarp();
@@ -245,13 +251,14 @@ static __device__ __noinline__ unsigned as_invert(int Mo, int ms, int nc, int hi
             const double f = row[k];
             row[k] = 0.0;
             if (f != 0.0) {
-#pragma unroll 2
-                for (int b = 0; b < hi; b += 2) {
-                    const double2 kk = ld2(rk + b);
-                    double2 mm = ld2(row + b);
-                    mm.x = fma(-f, kk.x, mm.x);
-                    mm.y = fma(-f, kk.y, mm.y);
-                    *reinterpret_cast<double2*>(row + b) = mm;
+#pragma unroll 1
+                for (int b = 0; b < hi; b += 4) {
+                    const double2 k0 = ld2(rk + b), k1 = ld2(rk + b + 2);
+                    double2 m0 = ld2(row + b), m1 = ld2(row + b + 2);
+                    m0.x = fma(-f, k0.x, m0.x); m0.y = fma(-f, k0.y, m0.y);
+                    m1.x = fma(-f, k1.x, m1.x); m1.y = fma(-f, k1.y, m1.y);
+                    *reinterpret_cast<double2*>(row + b) = m0;
+                    *reinterpret_cast<double2*>(row + b + 2) = m1;
                 }
             }
         }
@@ -276,7 +283,7 @@ __device__ __forceinline__ void as_mark(int lane, int row, int sgn, bool on, uns
     }
 }
 
-__device__ __forceinline__ int as_hi(unsigned amask) { return (33 - __clz(amask | 1u)) & ~1; }   // even, covers amask
+__device__ __forceinline__ int as_hi(unsigned amask) { return (35 - __clz(amask | 1u)) & ~3; }   // multiple of 4, covers amask
 
 // Goldfarb-Idnani iteration.  `apply_only`: the warm start left its multipliers in w.coef(); the first pass
 // only moves the row values (the row streaming code exists once).  Returns 0 when no row is violated by
@@ -365,12 +372,12 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                     const int a = __ffs(mk) - 1;
                     mk &= mk - 1;
                     const double ca = w.coef()[a];
-                    const double* __restrict__ Wa = P.W + (size_t)w.act_row()[a] * mpad + 2 * lane;
+                    const double* __restrict__ Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
                     if (ILP >= 2) {
                         const int a2 = mk ? __ffs(mk) - 1 : a;
                         const double cb = mk ? w.coef()[a2] : 0.0;
                         mk &= mk - 1;
-                        const double* __restrict__ Wb = P.W + (size_t)w.act_row()[a2] * mpad + 2 * lane;
+                        const double* __restrict__ Wb = P.W + (unsigned)(w.act_row()[a2] * mpad + 2 * lane);
 #pragma unroll
                         for (int r2 = 0; r2 < R2; ++r2) {
                             const double2 g = ld2(Wa + r2 * 64), h = ld2(Wb + r2 * 64);
@@ -649,7 +656,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             __syncwarp();
             if (nc > 0) {
                 // candidate c sits in slot c: S = signed sub-matrix of W, inverted in place
-                const int hi = (nc + 1) & ~1;
+                const int hi = (nc + 3) & ~3;
                 double diag0 = 1.0;
                 if (lane < nc) {
                     sl.ra = w.act_row()[lane];
