@@ -359,25 +359,18 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 c = -step * sp;
             }
             if (!dependent) {
-                // row values move by  c W[p][:] + sum_a coef_a W[row_a][:]
-#pragma unroll
-                for (int r2 = 0; r2 < R2; ++r2) {
-                    const double2 g = ld2(Wp + r2 * 64 + 2 * lane);
-                    e[2 * r2] = fma(c, g.x, e[2 * r2]);
-                    e[2 * r2 + 1] = fma(c, g.y, e[2 * r2 + 1]);
-                }
+                // row values move by  c W[p][:] + sum_a coef_a W[row_a][:]; the entering row is paired with the first
+                // active row (ILP = 2: two rows per pass, twice the loads in flight)
+                double ca = c;
+                const double* __restrict__ Wa = Wp + 2 * lane;
+                unsigned mk = amask;
 #pragma unroll 1
-                for (unsigned mk = amask; mk;) {
-                    // two rows per pass: twice the loads in flight
-                    const int a = __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    const double ca = w.coef()[a];
-                    const double* __restrict__ Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
+                while (true) {
                     if (ILP >= 2) {
-                        const int a2 = mk ? __ffs(mk) - 1 : a;
+                        const int a2 = mk ? __ffs(mk) - 1 : 0;
                         const double cb = mk ? w.coef()[a2] : 0.0;
+                        const double* __restrict__ Wb = mk ? P.W + (unsigned)(w.act_row()[a2] * mpad + 2 * lane) : Wa;
                         mk &= mk - 1;
-                        const double* __restrict__ Wb = P.W + (unsigned)(w.act_row()[a2] * mpad + 2 * lane);
 #pragma unroll
                         for (int r2 = 0; r2 < R2; ++r2) {
                             const double2 g = ld2(Wa + r2 * 64), h = ld2(Wb + r2 * 64);
@@ -392,6 +385,11 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                             e[2 * r2 + 1] = fma(ca, g.y, e[2 * r2 + 1]);
                         }
                     }
+                    if (!mk) break;
+                    const int a = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    ca = w.coef()[a];
+                    Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
                 }
                 cp = fma(-step, kappa, cp);
                 cnt.rows += na + 1;
