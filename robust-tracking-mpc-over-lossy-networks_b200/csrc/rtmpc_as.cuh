@@ -734,22 +734,31 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
         const int nrow = (N + 1) * nu;
         if (U_out_inst) {
             // packet payload straight from the scaled decision: U = UPhi z + UPsi x_init, last column u_bar + K x_bar
+            if (P.Uidx) {
+                // every payload row is one scaled decision variable
 #pragma unroll 1
-            for (int i = lane; i < nrow; i += 32) {
-                if (i >= N * nu && P.nss == 0) continue;
-                double acc = 0.0, acc2 = 0.0;
-                const double* __restrict__ up = P.UPhiT + i;          // zero-padded to npad columns
-                const double* zz = w.z();
-#pragma unroll 2
-                for (int k = 0; k < npad; k += 2) {
-                    acc = fma(up[0], zz[k], acc);
-                    acc2 = fma(up[nrow], zz[k + 1], acc2);
-                    up += 2 * nrow;
+                for (int i = lane; i < nrow; i += 32) {
+                    if (i >= N * nu && P.nss == 0) continue;
+                    U_out_inst[i] = has_sol ? P.Ucoef[i] * w.z()[P.Uidx[i]] : nanv;
                 }
-                const double* __restrict__ ps = P.UPsiT + i;
+            } else {
 #pragma unroll 1
-                for (int k = 0; k < nx; ++k) { acc = fma(ps[0], w.xr()[k], acc); ps += nrow; }
-                U_out_inst[i] = has_sol ? acc + acc2 : nanv;
+                for (int i = lane; i < nrow; i += 32) {
+                    if (i >= N * nu && P.nss == 0) continue;
+                    double acc = 0.0, acc2 = 0.0;
+                    const double* __restrict__ up = P.UPhiT + i;          // zero-padded to npad columns
+                    const double* zz = w.z();
+    #pragma unroll 2
+                    for (int k = 0; k < npad; k += 2) {
+                        acc = fma(up[0], zz[k], acc);
+                        acc2 = fma(up[nrow], zz[k + 1], acc2);
+                        up += 2 * nrow;
+                    }
+                    const double* __restrict__ ps = P.UPsiT + i;
+    #pragma unroll 1
+                    for (int k = 0; k < nx; ++k) { acc = fma(ps[0], w.xr()[k], acc); ps += nrow; }
+                    U_out_inst[i] = has_sol ? acc + acc2 : nanv;
+                }
             }
         }
         if (z_out_inst) {

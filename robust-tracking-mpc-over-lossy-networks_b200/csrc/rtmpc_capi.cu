@@ -184,7 +184,23 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
             UPsiT[(size_t)k * nrow + i] = v;
         }
     }
+    // usually every payload row is a single (scaled) decision variable: u_k itself, u_bar + K x_bar = c * theta
+    std::vector<int> Uidx(nrow, 0);
+    std::vector<double> Ucoef(nrow, 0.0);
+    bool single = true;
+    for (int i = 0; i < nrow && single; ++i) {
+        int nnz = 0;
+        for (int k = 0; k < npad; ++k)
+            if (UPhiT[(size_t)k * nrow + i] != 0.0) { ++nnz; Uidx[i] = k; Ucoef[i] = UPhiT[(size_t)k * nrow + i]; }
+        for (int k = 0; k < nx; ++k)
+            if (UPsiT[(size_t)k * nrow + i] != 0.0) nnz = 2;
+        if (nnz > 1) single = false;
+    }
     int rc = 0;
+    if (single) {
+        rc |= upload(q, Uidx.data(), Uidx.size(), &P.Uidx);
+        rc |= upload(q, Ucoef.data(), Ucoef.size(), &P.Ucoef);
+    }
     rc |= upload(q, d->Hs, nn, &P.Hs);
     rc |= upload(q, d->Hinv, nn, &P.Hinv);
     rc |= upload(q, G.data(), mn, &P.G);
@@ -419,8 +435,36 @@ int rtmpc_loop_create(const rtmpc_loop_desc* d, int32_t B, rtmpc_loop** out) {
     rc |= lalloc(l, (size_t)nu * nx, &K, d->K);
     rc |= lalloc(l, (size_t)nu * nx, &Kp, d->K_plant ? d->K_plant : d->K);
     if (d->nz_rows > 0) {
-        rc |= lalloc(l, (size_t)d->nz_rows * nx, &Hz, d->Hz);
-        rc |= lalloc(l, (size_t)d->nz_rows, &hz, d->hz);
+        // A centrally symmetric tube (every facet a'x <= h has its mirror -a'x <= h; the mRPI set of a symmetric
+        // disturbance box is) needs one dot product per pair: max(a'd - h, -a'd - h) = |a'd| - h.
+        const int nr = d->nz_rows;
+        std::vector<int> mate(nr, -1);
+        bool sym = (nr % 2) == 0;
+        for (int i = 0; i < nr && sym; ++i) {
+            if (mate[i] >= 0) continue;
+            for (int j = i + 1; j < nr; ++j) {
+                if (mate[j] >= 0 || d->hz[j] != d->hz[i]) continue;
+                bool opp = true;
+                for (int k = 0; k < nx && opp; ++k) opp = d->Hz[(size_t)j * nx + k] == -d->Hz[(size_t)i * nx + k];
+                if (opp) { mate[i] = j; mate[j] = i; break; }
+            }
+            if (mate[i] < 0) sym = false;
+        }
+        if (sym) {
+            std::vector<double> Hh, hh;
+            for (int i = 0; i < nr; ++i)
+                if (mate[i] > i) {
+                    Hh.insert(Hh.end(), d->Hz + (size_t)i * nx, d->Hz + (size_t)(i + 1) * nx);
+                    hh.push_back(d->hz[i]);
+                }
+            L.nz_rows = nr / 2;
+            L.tube_sym = 1;
+            rc |= lalloc(l, Hh.size(), &Hz, Hh.data());
+            rc |= lalloc(l, hh.size(), &hz, hh.data());
+        } else {
+            rc |= lalloc(l, (size_t)nr * nx, &Hz, d->Hz);
+            rc |= lalloc(l, (size_t)nr, &hz, d->hz);
+        }
     }
     rc |= lalloc(l, (size_t)nx, &wh, d->w_half ? d->w_half : zeros.data());
     L.A = A; L.Bm = Bm; L.K = K; L.Kp = Kp; L.Hz = Hz; L.hz = hz; L.w_half = wh;

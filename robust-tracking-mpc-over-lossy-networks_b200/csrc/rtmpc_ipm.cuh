@@ -42,6 +42,8 @@ struct QPDev {
     const double *UxT, *LxT; // [nx*mpad]    Ux, Lx transposed
     const double *upI, *loI; // [mpad]       up0 / lo0 with +-1e30 where the row has no such bound
     const double* wid;       // [mpad]       up - lo (independent of x_init), 3e30 where the row has no lower bound
+    const int* Uidx;               // [(N+1)nu] or NULL: payload row i = Ucoef[i] * z[Uidx[i]] (every row of UPhi has one entry,
+    const double* Ucoef;           //                    UPsi = 0: inputs are decision variables; else the dense maps below)
     const double *UPhiT, *UPsiT;   // [npad*(N+1)nu], [nx*(N+1)nu]  packet payload from the scaled decision:
                                    // U_t = UPhi z + UPsi x_init, last column u_bar + K x_bar folded in
     const int* shift;        // [mpad] warm-start map: same constraint one stage earlier, -1 = none

@@ -22,6 +22,7 @@ constexpr int LOOP_MAX_NU = 4;
 
 struct LoopDev {
     int nx, nu, N, actuator, plant, nz_rows;
+    int tube_sym;      // 1: the tube is centrally symmetric and Hz/hz hold one facet of every +- pair: value |Hz d| - hz
     const double *A, *Bm, *K, *Kp, *Hz, *hz, *w_half;
     double cart[8];
     double *x, *x_nom, *x_hat, *buf, *u_last, *err_acc, *tube_max;
@@ -96,9 +97,11 @@ __device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, const State
 #pragma unroll
     for (int k = 0; k < AX; ++k) d[k] = (k < nx) ? S.x(k) - S.x_nom(k) : 0.0;
     double worst = -1e300;
+    const bool sym = L.tube_sym != 0;
 #pragma unroll 4
     for (int i = first; i < L.nz_rows; i += stride) {
         double acc = -__ldg(L.hz + i);
+        if (sym) acc = 0.0;
         if (NX > 0 && (NX & 1) == 0) {
             const double2* __restrict__ h2 = reinterpret_cast<const double2*>(L.Hz + i * NX);      // rows are 16-byte aligned
 #pragma unroll
@@ -111,6 +114,7 @@ __device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, const State
 #pragma unroll
             for (int k = 0; k < AX; ++k) if (k < nx) acc = fma(__ldg(L.Hz + i * nx + k), d[k], acc);
         }
+        if (sym) acc = fabs(acc) - __ldg(L.hz + i);       // both facets of the pair at once
         if (acc > worst) worst = acc;          // (a compare and a select: FP64 fmax is a seven-instruction sequence)
     }
     return worst;
