@@ -111,23 +111,56 @@ def run_cpu_arm(solves_per_step, steps, warmup, cores=None):
 # clocks sampler
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every 5 ms (the timed region is tens of
+    milliseconds), nvidia-smi every 200 ms as the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.sm, self.sm_max, self.reasons = [], None, set()
         self._stop = threading.Event()
         self._th = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
 
     def _run(self):
+        nv = self._nvml
+        if nv is not None:
+            bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                    (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                    (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                    (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                    for bit, name in bits:
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                self._stop.wait(0.005)
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [v.strip() for v in out.strip().split(",")]
                 if len(f) >= 6:
-                    self.samples.append(f)
+                    self.sm.append(float(f[0]))
+                    self.sm_max = float(f[1])
+                    for i, n in enumerate(self.NAMES):
+                        if f[2 + i].lower().startswith("active"):
+                            self.reasons.add(n)
             except Exception:
                 pass
             self._stop.wait(0.2)
@@ -141,13 +174,11 @@ class ClockSampler:
         self._th.join(timeout=3)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no clock samples"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------------
