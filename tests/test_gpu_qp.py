@@ -213,3 +213,47 @@ def test_tracking_mpc_without_terminal_set_uses_the_terminal_equality():
             assert np.abs(z[i, nx * N:nx * (N + 1)] - z[i, -(nx + 1):-1]).max() <= 1e-9      # x_N == x_bar
             n_ok += 1
         assert n_ok >= 12, name
+
+
+def test_multi_input_system_qp_and_rollout():
+    """A system that is not in the reference's scripts (nx = 3, nu = 2, two-dimensional steady-state family): the QP
+    against the oracle, and the persistent rollout against the step-by-step path (Pezzutto scheme, smart actuator)."""
+    import torch
+    from oracle import ref_qp as rq
+    from oracle.ref_polytope import Polytope as OP
+    from rtmpc_b200 import mpc
+    from rtmpc_b200.polytope import Polytope
+    from rtmpc_b200.rollout import RemoteLoop
+    A = np.array([[1.0, 0.1, 0.0], [0.0, 1.0, 0.1], [0.0, -0.05, 0.95]])
+    B = np.array([[0.0, 0.0], [0.1, 0.0], [0.0, 0.1]])
+    Q, R, N = np.diag([1.0, 1.0, 0.5]), np.diag([0.1, 0.2]), 6
+    XA, Xb = np.r_[np.eye(3), -np.eye(3)], np.array([2.0, 1.0, 1.0, 2.0, 1.0, 1.0])
+    UA, Ub = np.r_[np.eye(2), -np.eye(2)], np.array([0.5, 0.4, 0.5, 0.4])
+    c = mpc.TrackingMPC(A, B, Q, R, N)
+    c.set_state_constraints(Polytope(XA, Xb, normalize=False))
+    c.set_input_constraints(Polytope(UA, Ub, normalize=False))
+    c.generate_optimization_problem()                       # no terminal set: x_N == x_bar
+    oq = rq.build_tracking(A, B, Q, R, N, c._P, OP(XA, Xb, normalize=False), OP(UA, Ub, normalize=False), None)
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (40, 3)) * np.array([1.5, 0.6, 0.6])
+    Rf = np.c_[rng.uniform(-1.5, 1.5, 40), np.zeros((40, 2))]
+    out = c.solve_batch(X, Rf)
+    n_ok = 0
+    for i in range(40):
+        sol, res = rq.solve_param(oq, X[i].copy(), Rf[i].copy())
+        if res.status == "infeasible":
+            assert out["status"][i] == 2
+            continue
+        assert out["status"][i] == 0
+        assert np.abs(out["u"][i] - sol[1]).max() <= TOL_TIGHT
+        n_ok += 1
+    assert n_ok >= 15
+    res = {}
+    for fused in (True, False):
+        loop = RemoteLoop(c, 64, kind="track")
+        loop.reset(np.tile([0.5, 0.0, 0.0], (64, 1)))
+        tr = loop.run(60, np.array([1.0, 0.0, 0.0]), p_loss=np.linspace(0.0, 0.6, 64), seed=5, record=True, fused=fused)
+        res[fused] = (tr.cpu().numpy(), loop.status_count.cpu().numpy())
+    assert np.array_equal(res[True][0], res[False][0]) and np.array_equal(res[True][1], res[False][1])
+    assert res[True][1][0] == 64 * 60
+    assert np.abs(res[True][0][:, -1, 0] - 1.0).max() < 0.2       # every loop tracks the reference
