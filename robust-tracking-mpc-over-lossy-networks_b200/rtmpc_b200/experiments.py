@@ -28,8 +28,10 @@ class ExperimentResult:
     tracking_error_track: np.ndarray        # [n_p, n_mc]  NaN where R-MPC became infeasible (script :293-296)
     is_track_infeasible: np.ndarray         # [n_p]        runs in which R-MPC returned U_t = None (script :268-271)
     max_tube_violation: float               # max_t max_i (Hz (x - x_nom) - hz)_i over all runs: <= 0 means inside the tube
+    tracking_error_ext: np.ndarray = None   # [n_p, n_mc]  ERT-MPC (results_linear_system_with_extendedMPC.py), if requested
     trajectories_tube: dict = field(default_factory=dict)    # p -> x[nx, T+1] of run min(5, n_mc-1)   (script :298-301)
     trajectories_track: dict = field(default_factory=dict)
+    trajectories_ext: dict = field(default_factory=dict)
     solve_ms_tube: float = 0.0              # amortised time per determine_packet call of RT-MPC, in ms
     solve_ms_track: float = 0.0
     solves: int = 0
@@ -40,21 +42,29 @@ class ExperimentResult:
                  f"amortised time per solve [ms]: RT-MPC {self.solve_ms_tube:.6f}, R-MPC {self.solve_ms_track:.6f}",
                  f"max tube violation (<= 0: x - x_nom in Z at every step): {self.max_tube_violation:.3e}",
                  "Failed executions of Remote MPC:", str(self.is_track_infeasible.reshape(-1, 1)),
-                 " p     RT-MPC median / mean        R-MPC median / mean (feasible runs)"]
+                 " p     RT-MPC median / mean        R-MPC median / mean (feasible runs)" +
+                 ("        ERT-MPC median / mean" if self.tracking_error_ext is not None else "")]
         for i, p in enumerate(self.prob_packet_loss):
             tt, tr = self.tracking_error_tube[i], self.tracking_error_track[i]
             ok = ~np.isnan(tr)
-            lines.append(f"{p:4.2f}   {np.median(tt):.5f} / {tt.mean():.5f}        " +
-                         (f"{np.median(tr[ok]):.5f} / {tr[ok].mean():.5f}" if ok.any() else "   -    /    -"))
+            line = f"{p:4.2f}   {np.median(tt):.5f} / {tt.mean():.5f}        " + \
+                (f"{np.median(tr[ok]):.5f} / {tr[ok].mean():.5f}" if ok.any() else "   -    /    -   ")
+            if self.tracking_error_ext is not None:
+                te = self.tracking_error_ext[i]
+                line += f"                        {np.median(te):.5f} / {te.mean():.5f}"
+            lines.append(line)
         return "\n".join(lines)
 
 
 def linear_system_experiment(tube_mpc, track_mpc, Z, w_half, prob_packet_loss=None, n_mc=20, T=250, ref=0.5, x0=None,
-                             seed=679, store_run=None, plant="linear"):
+                             seed=679, store_run=None, plant="linear", ext_mpc=None):
     """Batched ``Results/results_linear_system.py``.  ``tube_mpc``: TubeTrackingMPC with its problem generated;
     ``track_mpc``: TrackingMPC with its problem generated, or None to skip R-MPC; ``Z``: the tube (for the containment
     check); ``w_half``: half-widths of the disturbance box; ``ref``: target of the first state (full-state target
-    ``(ref, 0, ..)`` as in the script, ``:240``)."""
+    ``(ref, 0, ..)`` as in the script, ``:240``); ``ext_mpc``: an ExtendedTubeTrackingMPC to add the ERT-MPC arm of
+    ``results_linear_system_with_extendedMPC.py`` (robust estimator, x_nom_0 in the packet, gamma_{t-1}-switched QP);
+    ``plant='cartpole'`` replaces the linear plant + disturbance by the analytic cartpole ODE
+    (``results_nonlinear_system*.py`` without PyBullet)."""
     probs = np.arange(10) / 10.0 if prob_packet_loss is None else np.asarray(prob_packet_loss, float)
     n_p = len(probs)
     total = n_p * n_mc
@@ -70,10 +80,10 @@ def linear_system_experiment(tube_mpc, track_mpc, Z, w_half, prob_packet_loss=No
     x0v = np.zeros((cnt, nx)) if x0 is None else np.broadcast_to(np.asarray(x0, float).reshape(-1, nx), (cnt, nx))
     store_run = min(5, n_mc - 1) if store_run is None else store_run
     out = {}
-    for name, mpc, kind in (("tube", tube_mpc, "tube"), ("track", track_mpc, "track")):
+    for name, mpc, kind in (("tube", tube_mpc, "tube"), ("track", track_mpc, "track"), ("ext", ext_mpc, "extended")):
         if mpc is None or cnt == 0:
             continue
-        loop = RemoteLoop(mpc, cnt, kind=kind, plant=plant, w_half=w_half, Z=Z if kind == "tube" else None)
+        loop = RemoteLoop(mpc, cnt, kind=kind, plant=plant, w_half=w_half, Z=Z if kind != "track" else None)
         loop.reset(x0v)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -92,12 +102,15 @@ def linear_system_experiment(tube_mpc, track_mpc, Z, w_half, prob_packet_loss=No
     res = ExperimentResult(prob_packet_loss=probs, tracking_error_tube=err_tube,
                            tracking_error_track=np.full((n_p, n_mc), np.nan), is_track_infeasible=np.zeros(n_p, int),
                            max_tube_violation=float(gathered("tube", "tube", -np.inf).max()), solves=total * T)
+    if ext_mpc is not None:
+        res.tracking_error_ext = gathered("err", "ext", np.nan).reshape(n_p, n_mc)
+        res.max_tube_violation = max(res.max_tube_violation, float(gathered("tube", "ext", -np.inf).max()))
     if track_mpc is not None:
         err_track = gathered("err", "track", np.nan).reshape(n_p, n_mc)
         alive = gathered("alive", "track", 1.0).reshape(n_p, n_mc)
         res.tracking_error_track = np.where(alive > 0.5, err_track, np.nan)
         res.is_track_infeasible = (alive < 0.5).sum(axis=1)
-    for name, store in (("tube", res.trajectories_tube), ("track", res.trajectories_track)):
+    for name, store in (("tube", res.trajectories_tube), ("track", res.trajectories_track), ("ext", res.trajectories_ext)):
         if name not in out:
             continue
         tr = out[name]["traj"]

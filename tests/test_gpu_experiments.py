@@ -33,3 +33,18 @@ def test_linear_system_experiment_statistics():
     again = linear_system_experiment(tube, track, Z, hw, prob_packet_loss=probs, n_mc=n_mc, T=T, seed=11)
     assert np.array_equal(again.tracking_error_tube, res.tracking_error_tube)
     assert "Failed executions of Remote MPC" in res.summary()
+
+
+def test_extended_arm_and_nonlinear_plant():
+    """results_linear_system_with_extendedMPC.py (ERT-MPC arm) and the nonlinear loop structure (analytic cartpole plant)."""
+    from rtmpc_b200.experiments import linear_system_experiment
+    s = H.load("sets_cp.npz")
+    hw = np.array([1e-4, 2.7e-3, 3e-4, 4.3e-2])
+    tube, ext, Z = H.make_tube_mpc(s), H.make_tube_mpc(s, extended=True), H.poly(s, "Z")
+    res = linear_system_experiment(tube, None, Z, hw, prob_packet_loss=[0.0, 0.6], n_mc=3, T=80, seed=5, ext_mpc=ext)
+    assert res.tracking_error_ext.shape == (2, 3) and np.all(np.isfinite(res.tracking_error_ext))
+    assert res.max_tube_violation < 1e-7
+    assert np.all(np.isnan(res.tracking_error_track)) and res.is_track_infeasible.sum() == 0      # R-MPC arm skipped
+    assert "ERT-MPC" in res.summary()
+    nl = linear_system_experiment(tube, None, None, hw, prob_packet_loss=[0.0, 0.6], n_mc=3, T=80, seed=5, plant="cartpole")
+    assert np.all(np.isfinite(nl.tracking_error_tube)) and nl.tracking_error_tube.max() < 0.2
