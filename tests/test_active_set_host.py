@@ -74,3 +74,17 @@ def test_numpy_model_of_the_kernel_matches_golden_solutions(fixture, spec_fn, ke
         worst = max(worst, np.abs(zz - zg).max() / max(1.0, np.abs(zg).max()))
     assert worst <= 1e-7, worst
     assert np.mean(steps) <= 8.0                      # warm starts keep the work small along a closed loop
+
+
+@pytest.mark.parametrize("name", ["sets_di.npz", "sets_cp.npz"])
+def test_terminal_set_pipeline_with_lazy_redundancy_removal(name):
+    """determine_Xf (maximal output admissible set of the augmented system, TubeTrackingMPC.py:35-61) with redundancy
+    removal only at the end gives the set the oracle's iteration-by-iteration restatement produced."""
+    from rtmpc_b200 import mpc, polytope as pc
+    s = H.load(name)
+    c = mpc.TubeTrackingMPC(s["A"], s["B"], s["Q"], s["R"], int(s["N"]))
+    c._Xc, c._Uc = H.poly(s, "Xc"), H.poly(s, "Uc")
+    c.determine_Xf()
+    G = H.poly(s, "Xf")
+    assert c._Xf.A.shape == G.A.shape
+    assert pc.is_subset(c._Xf, G) and pc.is_subset(G, c._Xf)
