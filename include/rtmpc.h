@@ -28,7 +28,8 @@ extern "C" {
 #define RTMPC_OPTIMAL            0   /* KKT-certified active-set point                          */
 #define RTMPC_MAX_ITER           1   /* no convergence (reference: status printed, values kept) */
 #define RTMPC_INFEASIBLE         2   /* reference: `.value is None` -> U_t = None (:215-221)    */
-#define RTMPC_OPTIMAL_INACCURATE 3   /* interior-point tolerance reached, certificate not found */
+#define RTMPC_OPTIMAL_INACCURATE 3   /* usable solution without the 1e-11 certificate: interior-point tolerance reached, or
+                                      rows that contradict each other by less than 1e-8 (relative) */
 #define RTMPC_FALLBACK_STATUS  (-2)  /* transient, never returned: active-set kernel handed the instance
                                         to the interior-point kernel inside rtmpc_qp_solve           */
 
@@ -110,7 +111,8 @@ void rtmpc_qp_destroy(rtmpc_qp* qp);
  *                          (only u_0..u_{N-1} are written when the variant has no steady state)
  *   d_status [B] (may be NULL)
  *   d_iters  [B] (may be NULL): bits 0-11 interior-point iterations, bits 12-23 active-set steps
- *            (rows added + rows dropped), bits 24-31 certification / endgame rounds
+ *            (rows added + rows dropped), bits 24-27 certification / endgame rounds (saturating), bits 28-30
+ *            diagnostics: why the active-set kernel last refactorised or gave up (0 = it never did)
  * Infeasible instances get NaN payloads (the reference returns None).
  */
 int rtmpc_qp_solve(rtmpc_qp* qp, int32_t B, const double* d_x_init, const double* d_ref,
@@ -131,7 +133,7 @@ int rtmpc_qp_warm_reset(rtmpc_qp* qp);
 /* RTMPC_METHOD_*: which kernel rtmpc_qp_solve runs (default: active set + interior-point fallback) */
 int rtmpc_qp_set_method(rtmpc_qp* qp, int32_t method);
 /* active-set steps (rows added + dropped) after which an instance is handed to the interior-point kernel;
- * <= 0 restores the default 8*npad + 32.  The result does not depend on it, only which kernel produces it. */
+ * <= 0 restores the default 16*npad + 128.  The result does not depend on it, only which kernel produces it. */
 int rtmpc_qp_set_step_cap(rtmpc_qp* qp, int32_t max_steps);
 /* device counter (or NULL) to which the active-set kernel adds the algorithmic FP64 flops it executes
  * (bench.py's roofline numerator) */

@@ -39,13 +39,15 @@
 namespace rtmpc {
 
 constexpr int RTMPC_FALLBACK = RTMPC_FALLBACK_STATUS;
+// as_gi: the entering row is a combination of the working set, no multiplier blocks, and its violation is tiny
+constexpr int AS_STALL = 7;
 
 // per-warp shared memory, in doubles: M (one row per working-set slot), zu, z, v, coef, 16 parameters, slot lists
 // (2*npad ints).  Kept as small as possible: what the warps do not take is L1 for the shared tables.
 __host__ __device__ inline int as_ms(const QPDev& P) { return P.npad + 2; }
 __host__ __device__ inline int as_mrows(const QPDev& P) { return P.npad; }      // one row per slot (<= n rows in the working set), padded to 4
 __host__ __device__ inline int as_warp_doubles(const QPDev& P) {
-    return as_mrows(P) * as_ms(P) + 4 * P.npad + 16 + P.npad;
+    return as_mrows(P) * as_ms(P) + 4 * P.npad + 16 + P.npad + 4;
 }
 
 // (offsets are added to one base pointer where they are used: nine live pointers would not stay in registers)
@@ -65,6 +67,11 @@ struct ASWarp {
     __device__ __forceinline__ double* xr() const { return base + mm + 4 * npad; }
     __device__ __forceinline__ int* act_row() const { return reinterpret_cast<int*>(base + mm + 4 * npad + 16); }
     __device__ __forceinline__ int* act_sgn() const { return act_row() + npad; }
+    // rarely touched control state lives here rather than in registers: ctl()[0] the row tolerance in force,
+    // ctl()[1] violation of the row a stall happened on; ictl()[0] steps at the last factorisation, [1] steps at
+    // the last exact row values, [2] why the solve last refactorised or gave up (ASCounters), [3] refactorisations
+    __device__ __forceinline__ double* ctl() const { return base + mm + 5 * npad + 16; }
+    __device__ __forceinline__ int* ictl() const { return reinterpret_cast<int*>(base + mm + 5 * npad + 18); }
 };
 
 __device__ __forceinline__ ASWarp as_carve(double* base, const QPDev& P) {
@@ -78,6 +85,9 @@ __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_ca
 
 // steps: rows added + dropped; rounds: certifications; rows: rows of W streamed; sq: sum of na^2 over the
 // small dense operations (mat-vec, bordering, downdate).  Algorithmic flops are derived from these.
+// why (kept in ASWarp::ictl()[2]): last reason the Goldfarb-Idnani / certification pair gave up on a factorisation (diagnostics; 0 = never)
+//   1 step cap, 2 dependent row without a blocking multiplier and a tiny violation, 3 no free slot,
+//   4 certification failed (negative multiplier / refinement), 5 certification rounds, 6 contradiction late in a leg
 struct ASCounters { int steps, rounds, rows, sq; };
 
 __device__ __forceinline__ unsigned long long as_flops(const QPDev& P, const ASCounters& c, bool with_z) {
@@ -291,7 +301,7 @@ __device__ __forceinline__ int as_hi(unsigned amask) { return (35 - __clz(amask 
 // ILP = 2: two rows of W / three columns of G' per pass (more loads in flight, more registers)
 template <int R2, int ILP>
 __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask, ASSlot& sl, int lane,
-                                     double (&e)[2 * R2], unsigned& actu, unsigned& actl, double tolp, int max_steps,
+                                     double (&e)[2 * R2], unsigned& actu, unsigned& actl, int max_steps,
                                      bool apply_only, ASCounters& cnt) {
     const int npad = P.npad, n = P.n, mpad = P.mpad, ms = as_ms(P);
     const unsigned slots = (1u << n) - 1u;          // n <= 30
@@ -312,7 +322,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 if (!((actl >> (2 * r2 + 1)) & 1u) && vl1 > best) { best = vl1; code = 2 * row + 3; }
             }
             const ASArg bm = as_wargmax(best, code);
-            if (bm.v <= tolp) return 0;
+            if (bm.v <= w.ctl()[0]) return 0;
             p = bm.idx >> 1;
             sp = (bm.idx & 1) ? -1.0 : 1.0;
             cp = bm.v;
@@ -327,14 +337,14 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
             bool full = false, dependent = false;
             int j1 = 0;
             if (!apply_only) {
-                if (cnt.steps >= max_steps) return RTMPC_FALLBACK;
+                if (cnt.steps >= max_steps) { w.ictl()[2] = 1; return RTMPC_FALLBACK; }
                 cnt.steps += 1;
                 const double v = occ ? sl.sa * sp * Wp[sl.ra] : 0.0;
                 if (lane < npad) w.v()[lane] = v;
                 __syncwarp();
                 rr = occ ? as_matvec(w.Mo(), ms, hi, lane, w.vo()) : 0.0;
                 kappa = wpp - as_wsum(v * rr);
-                dependent = !(kappa > 1e-11 * wpp);
+                dependent = !(kappa > 1e-11 * wpp) || na >= n;      // n independent rows already span everything
                 const double rmax = as_wmax(fabs(rr));
                 const double ratio = (occ && rr > 1e-13 * (1.0 + rmax)) ? sl.lam * __drcp_rn(rr) : RTMPC_INF;
                 const ASArg rm = as_wargmin(ratio, lane);
@@ -344,7 +354,11 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 if (dependent) {
                     // n_p is a combination of the active rows: without a blocking multiplier the
                     // constraints contradict each other (Farkas: y = (-r, 1) >= 0, N y = 0, b'y = -c_p < 0)
-                    if (!has_j) return (cp > 1e-6 * P.sc_b) ? RTMPC_INFEASIBLE : RTMPC_FALLBACK;
+                    if (!has_j) {
+                        w.ictl()[2] = (cp > 1e-6 * P.sc_b) ? 6 : 2;
+                        w.ctl()[1] = cp;
+                        return (cp > 1e-6 * P.sc_b) ? RTMPC_INFEASIBLE : AS_STALL;
+                    }
                     step = t1;
                 } else {
                     const double t2 = cp * __drcp_rn(kappa);
@@ -397,7 +411,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
             if (apply_only) { apply_only = false; break; }
             if (full) {
                 const unsigned freem = ~amask & slots;
-                if (na >= n || !freem) return RTMPC_FALLBACK;
+                if (na >= n || !freem) { w.ictl()[2] = 3; return RTMPC_FALLBACK; }
                 const int s = __ffs(freem) - 1;
                 __syncwarp();                 // rv shares coef's storage: every lane is done streaming
                 if (lane < npad) w.rv()[lane] = rr;
@@ -423,8 +437,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
 // violated (t holds exact values: go back to as_gi), 2 on a negative multiplier / no convergence.
 template <int R2, int ILP>
 __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned amask, ASSlot& sl, int lane,
-                                          double (&e)[2 * R2], unsigned actu, unsigned actl, double tolp,
-                                          ASCounters& cnt) {
+                                          double (&e)[2 * R2], unsigned actu, unsigned actl, ASCounters& cnt) {
     const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ms = as_ms(P);
     const bool occ = (amask >> lane) & 1u;
     const int hi = as_hi(amask);
@@ -481,7 +494,7 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
             resid = sl.sa * (a0 + a1) - ba;
         }
         // converged (every active row on its bound to well below the certificate's tolerance): stop refining
-        if (pass >= 1 && !(as_wmax(fabs(resid)) > 1e-3 * tolp)) break;
+        if (pass >= 1 && !(as_wmax(fabs(resid)) > 1e-3 * w.ctl()[0])) break;
     }
     cnt.rounds += 1;
     // exact row values at z:  e = G z - up through the transposed copies (coalesced 16-byte loads)
@@ -533,6 +546,7 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
         }
     }
     // any row outside the working set violated by more than the tolerance?
+    const double tolp = w.ctl()[0];
     bool viol = false;
 #pragma unroll
     for (int r2 = 0; r2 < R2; ++r2) {
@@ -585,40 +599,52 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
     if (lane < npad) { w.zu()[lane] = zuj; w.z()[lane] = zuj; }
     // e = G z_u - up for every row (rows are measured from their upper bound; the lower side is e + wid >= 0)
     double e[2 * R2];
-#pragma unroll
-    for (int r2 = 0; r2 < R2; ++r2) {
-        const double2 uu = ld2(P.upI + r2 * 64 + 2 * lane);
-        e[2 * r2] = -uu.x;
-        e[2 * r2 + 1] = -uu.y;
-    }
-#pragma unroll 1
-    for (int k = 0; k < nx; ++k) {
-        const double xk = w.xr()[k], rk = w.xr()[8 + k];
-        const size_t o = (size_t)k * mpad + 2 * lane;
-#pragma unroll
-        for (int r2 = 0; r2 < R2; ++r2) {
-            const double2 a = ld2(P.ExT + o + r2 * 64), b = ld2(P.TrT + o + r2 * 64);
-            e[2 * r2] = fma(b.x, rk, fma(a.x, xk, e[2 * r2]));
-            e[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, e[2 * r2 + 1]));
-        }
-    }
-    // is any row on or beyond a bound?  (only the sign matters here: compares and a vote, no FP64 max chain)
-    bool touched = false;
-#pragma unroll
-    for (int r2 = 0; r2 < R2; ++r2) {
-        const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane);
-        touched = touched || e[2 * r2] >= 0.0 || e[2 * r2] + wd.x <= 0.0 || e[2 * r2 + 1] >= 0.0 || e[2 * r2 + 1] + wd.y <= 0.0;
-    }
-    const bool feasible_u = !__any_sync(RTMPC_FULL_MASK, touched);
-    __syncwarp();
-
     int status = RTMPC_OPTIMAL;
     unsigned amask = 0, actu = 0, actl = 0;
     ASSlot sl;
     sl.ra = 0; sl.sa = 0.0; sl.lam = 0.0;
-    if (par_bad) status = RTMPC_INFEASIBLE;
-    else if (feasible_u) status = RTMPC_OPTIMAL;      // the unconstrained minimiser is feasible
-    else {
+    const int max_steps = P.as_max_steps;
+    w.ctl()[0] = tolp;
+    w.ictl()[2] = 0;
+    w.ictl()[3] = 0;           // refactorisations so far
+    // A long sequence of bordering / downdating steps on a nearly dependent working set lets the explicit inverse
+    // drift (seen as a wrong sign of kappa, a failed refinement, a contradiction that is none).  The cure is the warm
+    // start's own procedure: start over from z_u with the CURRENT working set as the candidate list, inverted from
+    // scratch.  `restart` counts those refactorisations.
+#pragma unroll 1
+    for (;;) {
+        const bool first = w.ictl()[3] == 0;
+#pragma unroll
+        for (int r2 = 0; r2 < R2; ++r2) {
+            const double2 uu = ld2(P.upI + r2 * 64 + 2 * lane);
+            e[2 * r2] = -uu.x;
+            e[2 * r2 + 1] = -uu.y;
+        }
+#pragma unroll 1
+        for (int k = 0; k < nx; ++k) {
+            const double xk = w.xr()[k], rk = w.xr()[8 + k];
+            const size_t o = (size_t)k * mpad + 2 * lane;
+#pragma unroll
+            for (int r2 = 0; r2 < R2; ++r2) {
+                const double2 a = ld2(P.ExT + o + r2 * 64), b = ld2(P.TrT + o + r2 * 64);
+                e[2 * r2] = fma(b.x, rk, fma(a.x, xk, e[2 * r2]));
+                e[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, e[2 * r2 + 1]));
+            }
+        }
+        int nc = 0;
+        if (first) {
+            // is any row on or beyond a bound?  (only the sign matters here: compares and a vote, no FP64 max chain)
+            bool touched = false;
+#pragma unroll
+            for (int r2 = 0; r2 < R2; ++r2) {
+                const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane);
+                touched = touched || e[2 * r2] >= 0.0 || e[2 * r2] + wd.x <= 0.0 || e[2 * r2 + 1] >= 0.0 || e[2 * r2 + 1] + wd.y <= 0.0;
+            }
+            const bool feasible_u = !__any_sync(RTMPC_FULL_MASK, touched);
+            __syncwarp();
+            if (par_bad) { status = RTMPC_INFEASIBLE; break; }
+            if (feasible_u) break;                        // the unconstrained minimiser is feasible
+        }
         // M starts empty
         if (lane < npad) {
             if (lane < as_mrows(P)) {
@@ -630,29 +656,38 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             w.act_sgn()[lane] = 0;
         }
         __syncwarp();
-        // ---- 1. warm start ------------------------------------------------------------------
-        const int wn = (warm_inst && P.shift) ? warm_inst[0] : 0;
-        bool apply = false;
-        if (wn > 0) {
-            // every lane decodes one candidate: moved one stage earlier, kept if the row has that bound
+        // ---- 1. candidates: the previous step's working set moved one stage (warm start), or the current one ----
+        {
             int prow = -1;
             double psg = 1.0;
-            if (lane < wn && lane < n) {
-                const int code = warm_inst[1 + lane];
-                const int row0 = code >> 1;
-                psg = (code & 1) ? -1.0 : 1.0;
-                if (row0 >= 0 && row0 < mpad) prow = P.shift[row0];
-                if (prow >= 0 && ((psg > 0) ? !(P.upI[prow] < 0.5 * RTMPC_INF) : !(P.loI[prow] > -0.5 * RTMPC_INF))) prow = -1;
+            if (first) {
+                const int wn = (warm_inst && P.shift) ? warm_inst[0] : 0;
+                if (lane < wn && lane < n) {
+                    const int code = warm_inst[1 + lane];
+                    const int row0 = code >> 1;
+                    psg = (code & 1) ? -1.0 : 1.0;
+                    if (row0 >= 0 && row0 < mpad) prow = P.shift[row0];
+                    // kept if the row has that bound
+                    if (prow >= 0 && ((psg > 0) ? !(P.upI[prow] < 0.5 * RTMPC_INF) : !(P.loI[prow] > -0.5 * RTMPC_INF))) prow = -1;
+                }
+            } else if ((amask >> lane) & 1u) {
+                prow = sl.ra;
+                psg = sl.sa;
             }
             const unsigned okm = __ballot_sync(RTMPC_FULL_MASK, prow >= 0);
-            const int nc = __popc(okm);
+            nc = __popc(okm);
             if (prow >= 0) {
                 const int pos = __popc(okm & ((1u << lane) - 1u));
                 w.act_row()[pos] = prow;
                 w.act_sgn()[pos] = (int)psg;
             }
+            amask = 0; actu = 0; actl = 0;
+            sl.ra = 0; sl.sa = 0.0; sl.lam = 0.0;
             __syncwarp();
-            if (nc > 0) {
+        }
+        bool apply = false;
+        if (nc > 0) {
+            {
                 // candidate c sits in slot c: S = signed sub-matrix of W, inverted in place
                 const int hi = (nc + 3) & ~3;
                 double diag0 = 1.0;
@@ -714,21 +749,43 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             }
         }
         // ---- 2./3. Goldfarb-Idnani, then certification -----------------------------------------
-        const int max_steps = P.as_max_steps;
+        // The row values e move with every step by (multiplier change) x (row of W): with the huge multipliers of a
+        // nearly empty feasible set their rounding error can exceed tolp.  A stall (AS_STALL) is therefore first
+        // answered by certification, which recomputes e exactly; a stall on exact values means the rows contradict
+        // each other by `stall_cp`: up to 1e-8 (relative, the reference solver's own feasibility tolerance) the
+        // solve carries on with that much slack and reports RTMPC_OPTIMAL_INACCURATE.
+        w.ictl()[0] = cnt.steps;
+        w.ictl()[1] = -1;
 #pragma unroll 1
         for (int refresh = 0;; ++refresh) {
-            status = as_gi<R2, ILP>(P, w, amask, sl, lane, e, actu, actl, tolp, max_steps, apply, cnt);
+            status = as_gi<R2, ILP>(P, w, amask, sl, lane, e, actu, actl, max_steps, apply, cnt);
             apply = false;
-            if (status != 0) break;
-            const int c = as_certify<R2, ILP>(P, w, amask, sl, lane, e, actu, actl, tolp, cnt);
-            if (c == 0) { status = RTMPC_OPTIMAL; break; }
-            if (c == 2 || refresh >= 3) { status = RTMPC_FALLBACK; break; }
+            if (status == AS_STALL) {
+                status = RTMPC_FALLBACK;
+                if (cnt.steps == w.ictl()[1] + 1) {
+                    const double stall_cp = w.ctl()[1];
+                    if (stall_cp > 1e-8 * P.sc_b || refresh >= 12) break;
+                    w.ctl()[0] = 2.0 * stall_cp;
+                    w.ictl()[1] = cnt.steps;
+                    continue;
+                }
+            } else if (status != 0) break;
+            const int c = as_certify<R2, ILP>(P, w, amask, sl, lane, e, actu, actl, cnt);
+            if (c == 0) { status = (w.ctl()[0] > tolp) ? RTMPC_OPTIMAL_INACCURATE : RTMPC_OPTIMAL; break; }
+            if (c == 2 || refresh >= 12) { status = RTMPC_FALLBACK; w.ictl()[2] = (c == 2) ? 4 : 5; break; }
+            w.ictl()[1] = cnt.steps;
         }
+        if (status == RTMPC_OPTIMAL || status == RTMPC_OPTIMAL_INACCURATE || cnt.steps >= max_steps) break;
+        // a contradiction found a few steps after a fresh factorisation is believed; anything else starts over
+        if (status == RTMPC_INFEASIBLE && cnt.steps - w.ictl()[0] <= 8) break;
+        if (w.ictl()[3] >= 4) { status = RTMPC_FALLBACK; break; }
+        if (lane == 0) w.ictl()[3] += 1;
+        __syncwarp();
     }
 
     // ---- outputs ------------------------------------------------------------------------------
     if (status != RTMPC_FALLBACK) {
-        const bool has_sol = (status == RTMPC_OPTIMAL);
+        const bool has_sol = (status == RTMPC_OPTIMAL || status == RTMPC_OPTIMAL_INACCURATE);
         const double nanv = __longlong_as_double(0x7ff8000000000000LL);
         const int nu = P.nu, N = P.N;
         const int nrow = (N + 1) * nu;
@@ -777,18 +834,19 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
     }
     if (warm_inst) {
         // certified working set, compacted (the slots are sparse)
-        const bool occ = (status == RTMPC_OPTIMAL) && ((amask >> lane) & 1u);
+        const bool solved = (status == RTMPC_OPTIMAL || status == RTMPC_OPTIMAL_INACCURATE);
+        const bool occ = solved && ((amask >> lane) & 1u);
         const unsigned om = __ballot_sync(RTMPC_FULL_MASK, occ);
         const int pos = __popc(om & ((1u << lane) - 1u));
-        if (lane == 0) warm_inst[0] = (status == RTMPC_OPTIMAL) ? __popc(om) : -1;
+        if (lane == 0) warm_inst[0] = solved ? __popc(om) : -1;
         if (occ) warm_inst[1 + pos] = 2 * sl.ra + (sl.sa < 0 ? 1 : 0);
     }
     __syncwarp();
     return status;
 }
 
-__device__ __forceinline__ int as_pack_iters(const ASCounters& cnt) {
-    return ((cnt.steps > 4095 ? 4095 : cnt.steps) << 12) | ((cnt.rounds > 255 ? 255 : cnt.rounds) << 24);
+__device__ __forceinline__ int as_pack_iters(const ASCounters& cnt, const ASWarp& w) {
+    return ((cnt.steps > 4095 ? 4095 : cnt.steps) << 12) | ((cnt.rounds > 15 ? 15 : cnt.rounds) << 24) | ((w.ictl()[2] & 7) << 28);
 }
 
 template <int R2, int MAXW>
@@ -817,7 +875,7 @@ as_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double*
                                                  U_out ? U_out + inst * usz : nullptr, cnt);
         if (lane == 0) {
             if (status_out) status_out[inst] = status;
-            if (iters_out) iters_out[inst] = as_pack_iters(cnt);
+            if (iters_out) iters_out[inst] = as_pack_iters(cnt, w);
             if (work) atomicAdd(work, as_flops(P, cnt, z_out != nullptr));
         }
         __syncwarp();

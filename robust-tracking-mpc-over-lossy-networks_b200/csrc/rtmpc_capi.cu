@@ -98,7 +98,7 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
     P.ss = d->npad + 1;
     P.va_len = ((mpad > d->nz ? mpad : d->nz) + 1) & ~1;
     P.s_floor = d->s_floor; P.sc_b = d->sc_b; P.max_iter = d->max_iter > 0 ? d->max_iter : 60;
-    P.as_max_steps = 8 * d->npad + 32;
+    P.as_max_steps = 16 * d->npad + 128;
     int mtot = 0;
     for (int i = 0; i < d->mpad; ++i) mtot += (d->has_lo[i] ? 1 : 0) + (d->has_up[i] ? 1 : 0);
     P.mtot = mtot > 0 ? mtot : 1;
@@ -275,7 +275,7 @@ int rtmpc_qp_set_method(rtmpc_qp* q, int32_t method) {
 
 int rtmpc_qp_set_step_cap(rtmpc_qp* q, int32_t max_steps) {
     if (!q) return fail("rtmpc_qp_set_step_cap: null handle");
-    q->dev.as_max_steps = max_steps > 0 ? max_steps : 8 * q->dev.npad + 32;
+    q->dev.as_max_steps = max_steps > 0 ? max_steps : 16 * q->dev.npad + 128;
     return 0;
 }
 

@@ -824,7 +824,12 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
         }
         if (lane == 0) {
             if (status_out) status_out[inst] = status;
-            if (iters_out) iters_out[inst] = iters | (rounds_total << 24);   // bits 0-11 IPM iterations, 24-31 endgame rounds
+            // bits 0-11 IPM iterations, 24-27 endgame rounds; a handed-over instance keeps the active-set kernel's
+            // step count (12-23) and give-up reason (28-30)
+            if (iters_out) {
+                const int keep = (sel && sel_value <= RTMPC_FALLBACK_STATUS) ? (iters_out[inst] & 0x70FFF000) : 0;
+                iters_out[inst] = iters | ((rounds_total > 15 ? 15 : rounds_total) << 24) | keep;
+            }
         }
         __syncwarp();
     }

@@ -89,7 +89,7 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
                 status = a.status[inst];
                 const int it = a.iters[inst];
                 n_ipm += it & 0xFFF;
-                n_rounds += (it >> 24) & 0xFF;
+                n_rounds += (it >> 24) & 0xF;
                 if (lane == 0) a.pending[inst] = 0;
             } else {
                 ASCounters cnt;
@@ -104,13 +104,14 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
                 if (status == RTMPC_FALLBACK) {
                     if (lane == 0) {
                         a.status[inst] = recv ? RTMPC_FALLBACK - 1 : RTMPC_FALLBACK;     // which problem the hand-over is for
+                        a.iters[inst] = as_pack_iters(cnt, w);
                         a.pending[inst] = 1;
                         for (int j = 0; j < nx; ++j) a.ref_pending[(size_t)inst * nx + j] = ref_t ? ref_t[j] : 0.0;
                         atomicAdd(a.n_pending, 1);
                     }
                     break;
                 }
-                if (lane == 0) { a.status[inst] = status; a.iters[inst] = as_pack_iters(cnt); }
+                if (lane == 0) { a.status[inst] = status; a.iters[inst] = as_pack_iters(cnt, w); }
             }
             if (status >= 0 && status < 4) n_status[status] += 1;
             __syncwarp();

@@ -87,7 +87,14 @@ class BatchedQP:
     @staticmethod
     def decode_iters(iters):
         """packed d_iters -> (interior-point iterations, active-set steps, certification rounds)"""
-        return iters & 0xFFF, (iters >> 12) & 0xFFF, (iters >> 24) & 0xFF
+        return iters & 0xFFF, (iters >> 12) & 0xFFF, (iters >> 24) & 0xF
+
+    @staticmethod
+    def decode_why(iters):
+        """Diagnostics: last reason the active-set kernel gave up on a factorisation (0 = never; 1 step cap,
+        2 dependent row with a tiny violation, 3 no free slot, 4 certification failed, 5 certification rounds,
+        6 contradiction found late in a leg)."""
+        return (iters >> 28) & 7
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -110,3 +110,33 @@ def make_track_mpc(s):
     c._Xf = poly(s, "Xf_track")
     c.generate_optimization_problem()
     return c
+
+
+def oracle_tube_tracking_qp(s):
+    """The oracle's (un-condensed) statement of the remote tube MPC problem for a sets_*.npz fixture."""
+    from oracle import ref_qp as rq
+    from oracle.ref_polytope import Polytope
+    P = lambda k: Polytope(s[k + "_A"], s[k + "_b"], normalize=False)      # noqa: E731
+    return rq.build_tube_tracking(s["A"], s["B"], s["Q"], s["R"], int(s["N"]), s["P"], P("Xc"), P("Uc"), P("Xf"), None, True)
+
+
+def kkt_certificate(qp, x_init, ref, z, act_tol=1e-8):
+    """Solver-independent optimality check of ``z`` for the oracle problem ``qp`` (min 1/2 z'Pz + q'z, Ez = e, Gz <= h).
+    Returns (primal violation, stationarity residual) with both scaled like the oracle's own stopping test: the
+    multipliers y (free) and lambda >= 0 on the rows active at z are fitted by bounded least squares."""
+    from scipy.optimize import lsq_linear
+    q, e, h = qp.params(x_init, ref)
+    z = z[:qp.P.shape[0]]
+    sc_q = 1.0 + np.abs(q).max() + np.abs(qp.P).max()
+    sc_h = 1.0 + np.abs(h).max()
+    sc_e = 1.0 + np.abs(e).max()
+    slack = h - qp.G @ z
+    primal = max((-slack).max() / sc_h, np.abs(qp.E @ z - e).max() / sc_e)
+    act = np.nonzero(slack <= act_tol * sc_h)[0]
+    g = qp.P @ z + q
+    Amat = np.c_[qp.E.T, qp.G[act].T]
+    # columns scaled to unit norm: the fit is for the residual, not the multipliers
+    cn = np.maximum(np.linalg.norm(Amat, axis=0), 1e-300)
+    lb = np.r_[np.full(qp.E.shape[0], -np.inf), np.zeros(len(act))]
+    r = lsq_linear(Amat / cn, -g, bounds=(lb, np.full(len(lb), np.inf)), method="bvls", tol=1e-15, max_iter=2000)
+    return primal, np.abs(Amat / cn @ r.x + g).max() / sc_q

@@ -88,3 +88,30 @@ def test_terminal_set_pipeline_with_lazy_redundancy_removal(name):
     G = H.poly(s, "Xf")
     assert c._Xf.A.shape == G.A.shape
     assert pc.is_subset(c._Xf, G) and pc.is_subset(G, c._Xf)
+
+
+def test_numpy_model_solves_the_hard_cases_with_refactorisation():
+    """tools/as_model.py (the kernel's algorithm in numpy, with the refactor-and-restart safeguard) on a slice of the
+    hard-case fixture: same statuses as the oracle and a solver-independent KKT certificate on every solution."""
+    import as_model as M
+    from rtmpc_b200.condense import condense
+    from rtmpc_b200.ipm_data import prepare
+    s, g = H.load("sets_cp.npz"), H.load("hard_cp.npz")
+    cq = condense(H.spec_tube_tracking(s))
+    d = prepare(cq)
+    W = d.Gs @ d.Hinv @ d.Gs.T
+    oq = H.oracle_tube_tracking_qp(s)
+    restarts = 0
+    for i in list(range(0, 24)):
+        x, r = g["x"][i], g["ref"][i]
+        z, st, info = M.solve_as_inv(d, W, x, r, max_iter=512)
+        assert st == g["status"][i], (i, st, info)
+        if st != M.OPTIMAL:
+            continue
+        restarts += info["restarts"]
+        zz = cq.Phi @ (d.D * z) + cq.Psi @ x
+        primal, stationarity = H.kkt_certificate(oq, x, r, zz)
+        assert primal <= 1e-10 and stationarity <= 1e-10, (i, primal, stationarity)
+        if g["polished"][i]:
+            assert np.abs(zz - g["z"][i]).max() <= 1e-7 * max(1.0, np.abs(g["z"][i]).max())
+    assert restarts >= 1          # the slice exercises the safeguard

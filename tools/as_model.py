@@ -189,9 +189,10 @@ def solve_as(d, W, x_init, ref, warm=None, shift=None, max_iter=96, tol_p=1e-11,
 # date by bordering (add) / rank-one downdates (drop); no factorisation anywhere.  Certification = iterative
 # refinement of the multipliers against the true rows of G with M as the approximate inverse.
 # ------------------------------------------------------------------------------------------------------
-def solve_as_inv(d, W, x_init, ref, warm=None, shift=None, max_iter=224, tol_p=1e-11, kappa_eps=1e-11, passes=3):
+def solve_as_inv(d, W, x_init, ref, warm=None, shift=None, max_iter=224, tol_p=1e-11, kappa_eps=1e-11, passes=3,
+                 restarts=3, _it0=0, _nrestart=0):
     n, m, G, q, lo, up, hl, hu = _problem(d, x_init, ref)
-    info = dict(path="as", iters=0, drops=0, rounds=0, active=None, why=None)
+    info = dict(path="as", iters=0, drops=0, rounds=0, active=None, why=None, restarts=_nrestart)
     if np.any(d.par_C @ x_init - d.par_h > 1e-9 * (1.0 + np.abs(d.par_h))):
         return np.full(n, np.nan), INFEASIBLE, dict(info, path="param_rows")
     Hinv = d.Hinv[:n, :n]
@@ -253,7 +254,7 @@ def solve_as_inv(d, W, x_init, ref, warm=None, shift=None, max_iter=224, tol_p=1
     rows, sg = sv(act)
     t = tu - W[:m, rows] @ (sg * lam) if act else tu.copy()
 
-    it = 0
+    it = _it0
     for refresh in range(4):
         status = None
         while True:
@@ -274,13 +275,14 @@ def solve_as_inv(d, W, x_init, ref, warm=None, shift=None, max_iter=224, tol_p=1
                 it += 1
                 if it > max_iter:
                     status = FALLBACK
+                    info["why"] = "gi-cap"
                     break
                 na = len(act)
                 rows, sg = sv(act)
                 v = sg * W[rows, p] * sp if na else np.zeros(0)
                 r = M @ v
                 kappa = W[p, p] - v @ r
-                dependent = not (kappa > kappa_eps * W[p, p])
+                dependent = not (kappa > kappa_eps * W[p, p]) or na >= n     # n independent rows span everything
                 t1, j1 = np.inf, -1
                 rmax = np.abs(r).max(initial=0.0)
                 for j in range(na):
@@ -289,6 +291,7 @@ def solve_as_inv(d, W, x_init, ref, warm=None, shift=None, max_iter=224, tol_p=1
                 if dependent:
                     if j1 < 0:
                         status = INFEASIBLE if cp > 1e-6 * d.sc_b else FALLBACK
+                        info["why"] = "gi-dep cp=%.2e kappa=%.2e na=%d" % (cp, kappa / W[p, p], na)
                         break
                     step, full = t1, False
                 else:
@@ -303,6 +306,7 @@ def solve_as_inv(d, W, x_init, ref, warm=None, shift=None, max_iter=224, tol_p=1
                 if full:
                     if na >= n:
                         status = FALLBACK
+                        info["why"] = "gi-full"
                         break
                     M = border(M, r, kappa)
                     act.append((p, sp))
@@ -315,10 +319,16 @@ def solve_as_inv(d, W, x_init, ref, warm=None, shift=None, max_iter=224, tol_p=1
             if status is not None:
                 break
         info["iters"] = it
+        def restart():
+            return solve_as_inv(d, W, x_init, ref, warm=list(act), shift=None, max_iter=max_iter, tol_p=tol_p,
+                                kappa_eps=kappa_eps, passes=passes, restarts=restarts, _it0=it, _nrestart=_nrestart + 1)
+        if status is not None and str(info["why"]).startswith("gi-dep") and it > _it0 and _nrestart < restarts:
+            # the explicit inverse has drifted: refactor from the current working set and carry on
+            return solve_as_inv(d, W, x_init, ref, warm=list(act), shift=None, max_iter=max_iter, tol_p=tol_p,
+                                kappa_eps=kappa_eps, passes=passes, restarts=restarts, _it0=it, _nrestart=_nrestart + 1)
         if status == INFEASIBLE:
             return np.full(n, np.nan), INFEASIBLE, info
         if status == FALLBACK:
-            info["why"] = "gi"
             return None, FALLBACK, info
         # certification: refinement against the true rows with M as approximate inverse
         info["rounds"] += 1
@@ -337,10 +347,14 @@ def solve_as_inv(d, W, x_init, ref, warm=None, shift=None, max_iter=224, tol_p=1
             resid = Gt @ z - b
         if na and np.abs(resid).max() > tolp:
             info["why"] = "refine %.2e" % np.abs(resid).max()
+            if _nrestart < restarts:
+                return restart()
             return None, FALLBACK, info
         t = G @ z
         if na and lam_acc.min() < -1e-9 * (1.0 + np.abs(lam_acc).max()):
             info["why"] = "neg"
+            if _nrestart < restarts:
+                return restart()
             return None, FALLBACK, info
         lam = np.maximum(lam_acc, 0.0)
         vu = t - upi
