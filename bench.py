@@ -184,16 +184,33 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def build_controller():
+def build_controller(extended=False):
     from rtmpc_b200 import mpc
     from rtmpc_b200.polytope import Polytope
     s = load_sets()
     P = lambda k: Polytope(s[k + "_A"], s[k + "_b"], normalize=False)      # noqa: E731
-    c = mpc.TubeTrackingMPC(s["A"], s["B"], s["Q"], s["R"], int(s["N"]))
+    cls = mpc.ExtendedTubeTrackingMPC if extended else mpc.TubeTrackingMPC
+    c = cls(s["A"], s["B"], s["Q"], s["R"], int(s["N"]))
     c.set_input_constraints(P("U"))
     c.set_state_constraints(P("X"))
-    c.load_sets(P("Z"), P("Xc"), P("Uc"), P("Xf"), fixed_initial_state=True)
+    if extended:
+        c.load_sets(P("Z"), P("Xc"), P("Uc"), P("Xf"), ZmW=P("ZmW"), fixed_initial_state=True)
+    else:
+        c.load_sets(P("Z"), P("Xc"), P("Uc"), P("Xf"), fixed_initial_state=True)
     return c, P("Z")
+
+
+# BASELINE.json configs[1..3]: the same closed loop with another controller variant / plant
+WORKLOADS = {
+    "c2": dict(kind="tube", plant="linear", extended=False, seed=679,
+               text="results_linear_system.py remote tube MPC (linearised cartpole nx=4 nu=1 N=20)"),
+    "c3": dict(kind="extended", plant="linear", extended=True, seed=347,
+               text="results_linear_system_with_extendedMPC.py extended remote tube MPC (two QPs switched by gamma_{t-1}, "
+                    "robust estimator, x_nom_0 in the packet; linearised cartpole)"),
+    "c4": dict(kind="tube", plant="cartpole", extended=False, seed=124,
+               text="results_nonlinear_system.py remote tube MPC on the analytic cartpole ODE (10 sub-steps of 1/500 s per "
+                    "control step, no added disturbance)"),
+}
 
 
 def measure_fp64_peak(torch, dev):
@@ -232,14 +249,17 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
-    mpc, Z = build_controller()
+    wl = WORKLOADS[args.workload]
+    SEED = wl["seed"]
+    mpc, Z = build_controller(extended=wl["extended"])
     B, T = args.instances, T_STEPS
-    loop = RemoteLoop(mpc, B, kind="tube", w_half=HW, Z=Z)
+    loop = RemoteLoop(mpc, B, kind=wl["kind"], plant=wl["plant"], w_half=HW if wl["plant"] == "linear" else None, Z=Z)
     ids0, _ = D.shard(B * world, rank, world)          # weak scaling: B instances per rank, global ids
     p_loss = torch.as_tensor(np.array([0.1 * ((ids0 + i) % 10) for i in range(B)]), device=dev)
     ref_d = torch.as_tensor(np.tile(REF, (B, 1)), device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)    # > 126 MB L2
     n, m = mpc._prob.n, mpc._prob.m
+    kernel_name = "rollout_kernel<%d,16>" % ((mpc._prob.rows + 63) // 64)
     f_it = ipm_flops_per_iteration(n, m)
     stream = torch.cuda.current_stream()
 
@@ -338,7 +358,8 @@ def run_gpu_arm(args):
         try:
             # dram__bytes_read.sum + dram__bytes_write.sum of one rollout launch of this workload, from the
             # committed `ncu --set full` capture (profiles/)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "rollout_traffic.json")))["dram_bytes_per_launch"]
+            if args.workload == "c2" and B == B_PER_GPU:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "rollout_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
         flops = as_flops + f_it * int(iters_sum[0])      # rank 0's timed region: active-set kernel + IPM fallback
@@ -348,15 +369,15 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "results_linear_system.py remote tube MPC (linearised cartpole nx=4 nu=1 N=20), "
-                                   f"{B} closed-loop instances per GPU x {T} control steps per bench step",
+            "config": {"workload": wl["text"] + f", {B} closed-loop instances per GPU x {T} control steps per bench step",
+                       "baseline_config": args.workload,
                        "instances_per_gpu": B, "control_steps": T, "qp_n": n, "qp_rows_two_sided": m,
                        "l2": "256 MB buffer written between timed rollouts (L2 flush)",
-                       "rng": "Philox4x32-10 on device, seed 679, counter = global instance id"},
+                       "rng": f"Philox4x32-10 on device, seed {SEED}, counter = global instance id"},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": "rollout_kernel<5,16> (dual active-set QP + closed-loop step, one warp per instance for all T steps; ipm_solve_kernel on handed-over instances)",
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": kernel_name + " (dual active-set QP + closed-loop step, one warp per instance for all T steps; ipm_solve_kernel on handed-over instances)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure; "
@@ -410,6 +431,8 @@ def main():
                     help="QP solves of the CPU arm per step (bounded sample of the workload, ~10 s on 16 cores)")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
     ap.add_argument("--instances", type=int, default=B_PER_GPU, help="closed-loop instances per GPU (BASELINE configs[1]: 4096)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
+                    help="c2 (default, the headline): BASELINE configs[1]; c3: extended variant; c4: analytic cartpole plant")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -239,7 +239,7 @@ __device__ bool polish_warp(const QPDev& P, const double* __restrict__ Gs, WarpS
     int rounds = 0;
     bool success = false;
     for (; rounds < max_rounds; ++rounds) {
-        if (na > n) break;
+        if (na > npad) break;      // more rows than unknowns is fine (a degenerate vertex): the factorisation drops the dependent ones
         const bool mine = lane < na;
         const int ra = mine ? w.act_row[lane] : 0;
         const double sa = mine ? (double)w.act_sgn[lane] : 0.0;
@@ -596,10 +596,11 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
             // there the dual residual stalls while primal residual and gap collapse.
             const bool conv1 = (res <= 1e-7 && relgap <= 1e-8) || (rp_rel <= 1e-8 && relgap <= 1e-9 && rd_rel <= 1e-3);
             const bool conv2 = (res <= 1e-9 && relgap <= 1e-12);
-            const bool diverged = bad || merit > 1e3 * best_merit;
+            // losing a good point, not the wobble of the first iterations (the relative gap is not monotone there)
+            const bool diverged = bad || (best_merit <= 1e-4 && merit > 1e3 * best_merit);
             if (!diverged && conv1 && !conv2 && iters >= next_try && iters < P.max_iter) {
                 int na = build_active<R>(st, w.act_row, w.act_sgn, lane, mask_u, mask_l, nslots, 2 * npad);
-                if (na <= n && polish_warp<R>(P, Gs, w, na, lane, mask_u, mask_l, nslots, 24, &rounds_total, &na_final)) {
+                if (na <= npad && polish_warp<R>(P, Gs, w, na, lane, mask_u, mask_l, nslots, 24, &rounds_total, &na_final)) {
                     status = RTMPC_OPTIMAL;
                     break;
                 }
@@ -615,7 +616,7 @@ ipm_solve_kernel(QPDev P, int B, const double* __restrict__ x_init, const double
                         for (int i = lane; i < na && i < 2 * npad; i += 32) { w.act_row[i] = w.best_row[i]; w.act_sgn[i] = w.best_sgn[i]; }
                         __syncwarp();
                     }
-                    if (na <= n && polish_warp<R>(P, Gs, w, na, lane, mask_u, mask_l, nslots, 24, &rounds_total, &na_final)) {
+                    if (na <= npad && polish_warp<R>(P, Gs, w, na, lane, mask_u, mask_l, nslots, 24, &rounds_total, &na_final)) {
                         status = RTMPC_OPTIMAL;
                         break;
                     }

@@ -31,7 +31,7 @@ def polish_model(d, x_init, ref, act, max_rounds=24, tol_p=1e-11, tol_d=1e-9):
     act = list(act)
     for rnd in range(max_rounds):
         na = len(act)
-        if na > n:
+        if na > d.npad:
             return None, rnd, "too_many", act
         rows = np.array([a[0] for a in act], int)
         sg = np.array([a[1] for a in act], float)
@@ -165,7 +165,7 @@ def solve_model(d, x_init, ref, max_iter=60, verbose=False, warm=None, shift=Non
             break
         conv1 = (res <= 1e-7 and relgap <= 1e-8) or (rp_rel <= 1e-8 and relgap <= 1e-9 and rd_rel <= 1e-3)
         conv2 = res <= 1e-9 and relgap <= 1e-12
-        diverged = bad or merit > 1e3 * best_merit
+        diverged = bad or (best_merit <= 1e-4 and merit > 1e3 * best_merit)     # losing a good point, not early wobble
         if not diverged and conv1 and iters >= next_try and iters < max_iter and not conv2:
             zp = try_polish(active())
             if zp is not None:
