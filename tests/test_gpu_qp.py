@@ -282,3 +282,10 @@ def test_cartpole_hard_cases_after_reference_jumps():
     ipm, steps, _ = qp.decode_iters(it)
     assert ipm.max() == 0, int((ipm > 0).sum())
     assert steps.max() <= 16 * 24 + 128
+    # the interior-point kernel (the fallback) on its own: same statuses, certified by its endgame (more active rows
+    # than unknowns at a degenerate vertex are thinned by the dependency-dropping factorisation)
+    qp.set_method("interior_point")
+    z2, _, st2, it2 = qp.solve_host(g["x"], g["ref"])
+    assert np.array_equal(st2, g["status"]), np.bincount(st2, minlength=4)
+    assert (it2 & 0xFFF)[ok].min() >= 1
+    assert np.abs(z2[ok] - z[ok]).max() <= TOL_TIGHT * max(1.0, np.abs(z[ok]).max())
