@@ -145,7 +145,7 @@ class RemoteLoop:
 
     def accumulate_iters(self):
         it = self.iters
-        self.iters_total += torch.stack(((it & 0xFFF).sum(), ((it >> 12) & 0xFFF).sum(), ((it >> 24) & 0xFF).sum()))
+        self.iters_total += torch.stack(((it & 0xFFF).sum(), ((it >> 12) & 0xFFF).sum(), ((it >> 24) & 0xF).sum()))
 
     def run(self, T, ref, p_loss=None, theta=None, gamma=None, w=None, seed=0, id_offset=0, record=False, stats=True,
             fused=None):
