@@ -259,3 +259,43 @@ def test_fused_rollout_extended_variant_two_problems():
         assert np.abs(out[True][2] - xn[:, -1]).max() <= TOL
         for a, b in zip(out[True], out[False]):
             assert np.array_equal(a, b), golden
+
+
+def test_full_size_baseline_config_properties():
+    """BASELINE configs[1] at its full size (4096 closed loops x 250 steps, device RNG): what must hold irrespective of
+    size - every solve certified, the tube invariant x - x_nom in Z and the true state / input constraints at every
+    step (robust constraint satisfaction is the method's guarantee), results independent of how the batch is cut
+    (bit for bit), and solves at states visited by the big run that pass a solver-independent KKT check."""
+    import bench
+    from rtmpc_b200.rollout import RemoteLoop
+    s = H.load("sets_cp.npz")
+    mpc, Z = bench.build_controller()
+    B, T = bench.B_PER_GPU, bench.T_STEPS
+    p = np.array([0.1 * (i % 10) for i in range(B)])
+    loop = RemoteLoop(mpc, B, kind="tube", w_half=bench.HW, Z=Z)
+    loop.reset()
+    tr = loop.run(T, bench.REF, p_loss=p, seed=bench.SEED, record=True).cpu().numpy()
+    st = loop.stats.cpu().numpy()
+    assert st[:4].tolist() == [B * T, 0, 0, 0] and st[4] == 0            # all optimal, nothing handed over
+    assert int(loop.alive.sum().item()) == B
+    assert loop.tube_max.max().item() <= 0.0
+    X = H.poly(s, "X")
+    assert (tr.reshape(-1, 4) @ X.A.T - X.b).max() <= 0.0                 # |x| <= (5, 5, 0.3, 2) at every step of every loop
+    err = loop.tracking_error(T).cpu().numpy()
+    assert np.all(np.isfinite(err)) and err.max() < 0.1
+    lossless = tr[::10]                                                    # loss probability 0: settles on the reference
+    assert np.abs(lossless[:, -1, 0] - bench.REF[0]).max() <= 0.02
+    # cut invariance: instances 1000..1127 on their own (global ids through id_offset) - bit for bit
+    sub = RemoteLoop(mpc, 128, kind="tube", w_half=bench.HW, Z=Z)
+    sub.reset()
+    tr2 = sub.run(T, bench.REF, p_loss=p[1000:1128], seed=bench.SEED, id_offset=1000, record=True).cpu().numpy()
+    assert np.array_equal(tr2, tr[1000:1128])
+    # solves at visited states, checked without any solver in the loop
+    rng = np.random.default_rng(5)
+    xs = tr[rng.integers(0, B, 48), rng.integers(0, 60, 48)]              # the transient, where constraints are active
+    z, U, stq, _ = mpc._prob.solve_host(xs, np.tile(bench.REF, (48, 1)))
+    assert np.all(stq == 0)
+    oq = H.oracle_tube_tracking_qp(s)
+    for x, zz in zip(xs, z):
+        primal, stationarity = H.kkt_certificate(oq, x, bench.REF, zz)
+        assert primal <= 1e-10 and stationarity <= 1e-10
