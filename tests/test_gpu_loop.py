@@ -283,8 +283,10 @@ def test_full_size_baseline_config_properties():
     assert (tr.reshape(-1, 4) @ X.A.T - X.b).max() <= 0.0                 # |x| <= (5, 5, 0.3, 2) at every step of every loop
     err = loop.tracking_error(T).cpu().numpy()
     assert np.all(np.isfinite(err)) and err.max() < 0.1
-    lossless = tr[::10]                                                    # loss probability 0: settles on the reference
-    assert np.abs(lossless[:, -1, 0] - bench.REF[0]).max() <= 0.02
+    # loss probability 0: the nominal state settles on the reference, the state stays within the tube around it
+    from scipy.optimize import linprog
+    half = -linprog(-np.eye(4)[0], A_ub=Z.A, b_ub=Z.b, bounds=(None, None)).fun       # h_Z(e_1)
+    assert np.abs(tr[::10, -1, 0] - bench.REF[0]).max() <= half + 1e-3
     # cut invariance: instances 1000..1127 on their own (global ids through id_offset) - bit for bit
     sub = RemoteLoop(mpc, 128, kind="tube", w_half=bench.HW, Z=Z)
     sub.reset()
@@ -294,8 +296,14 @@ def test_full_size_baseline_config_properties():
     rng = np.random.default_rng(5)
     xs = tr[rng.integers(0, B, 48), rng.integers(0, 60, 48)]              # the transient, where constraints are active
     z, U, stq, _ = mpc._prob.solve_host(xs, np.tile(bench.REF, (48, 1)))
-    assert np.all(stq == 0)
+    # (plant states, not estimates: with x_0 fixed to a disturbed state some of these problems are infeasible)
+    from oracle import ref_qp as rq
+    assert set(np.unique(stq)) <= {0, 2} and (stq == 0).sum() >= 24
     oq = H.oracle_tube_tracking_qp(s)
-    for x, zz in zip(xs, z):
-        primal, stationarity = H.kkt_certificate(oq, x, bench.REF, zz)
-        assert primal <= 1e-10 and stationarity <= 1e-10
+    for x, zz, sq in zip(xs, z, stq):
+        if sq == 0:
+            primal, stationarity = H.kkt_certificate(oq, x, bench.REF, zz)
+            assert primal <= 1e-10 and stationarity <= 1e-10
+        else:
+            _, e, h = oq.params(x, bench.REF)
+            assert not rq.is_feasible(oq.E, e, oq.G, h)
