@@ -14,47 +14,60 @@ from .condense import MPCSpec, condense
 from .ipm_data import prepare
 
 
+def desc_arrays(spec: MPCSpec, Kss=None, max_iter=60, min_rows=0):
+    """Everything ``rtmpc_qp_desc`` (include/rtmpc.h) points at, prepared on the host: returns (cq, d, ints, floats,
+    arrays) with the arrays C-contiguous and named like the struct's fields.  Used by :class:`BatchedQP` and by
+    ``examples/dump_qp_desc.py`` (which writes them to a flat file for a C host program)."""
+    cq = condense(spec)
+    d = prepare(cq)
+    nz = cq.Phi.shape[0]
+    has_ss = spec.T_ss is not None
+    Phi = np.zeros((nz, d.npad))
+    Phi[:, :cq.n] = cq.Phi
+    Dp = np.zeros(d.npad)
+    Dp[:cq.n] = d.D
+    Hs = np.zeros((d.npad, d.npad))
+    Hs[:cq.n, :cq.n] = d.Hs
+    if has_ss and Kss is None:
+        raise ValueError("Kss (steady-state gain) is required for the tracking variants")
+    arrays = dict(Hs=_lib.f64(Hs), Hinv=_lib.f64(d.Hinv), G=_lib.f64(d.Gs), Y=_lib.f64(d.Y), Fx=_lib.f64(d.Fx),
+                  Fr=_lib.f64(d.Fr), lo0=_lib.f64(d.lo0), up0=_lib.f64(d.up0), Lx=_lib.f64(d.Lx),
+                  Ux=_lib.f64(d.Ux), parC=_lib.f64(d.par_C), parh=_lib.f64(d.par_h), Dscale=_lib.f64(Dp),
+                  Phi=_lib.f64(Phi), Psi=_lib.f64(cq.Psi))
+    if Kss is not None:
+        arrays["Kss"] = _lib.f64(np.atleast_2d(Kss))
+    arrays["has_lo"] = np.ascontiguousarray(d.has_lo, np.uint8)
+    arrays["has_up"] = np.ascontiguousarray(d.has_up, np.uint8)
+    arrays["shift"] = np.ascontiguousarray(d.shift, np.int32)
+    ints = dict(nx=cq.nx, nu=cq.nu, N=cq.N, n=cq.n, npad=d.npad, m=cq.m, mpad=d.mpad, np=len(d.par_h), nz=nz,
+                nss=(cq.nx + cq.nu) if has_ss else 0, max_iter=int(max_iter), min_rows=int(min_rows))
+    floats = dict(s_floor=float(d.s_floor), sc_b=float(d.sc_b))
+    return cq, d, ints, floats, arrays
+
+
 class BatchedQP:
     def __init__(self, spec: MPCSpec, Kss=None, max_iter=60, min_rows=0):
         self.spec = spec
-        self.cq = condense(spec)
-        self.data = prepare(self.cq)
-        cq, d = self.cq, self.data
+        self.cq, self.data, ints, floats, keep = desc_arrays(spec, Kss, max_iter, min_rows)
+        cq = self.cq
         self.nx, self.nu, self.N = cq.nx, cq.nu, cq.N
-        self.nz = cq.Phi.shape[0]
+        self.nz = ints["nz"]
         self.has_ss = spec.T_ss is not None
         self.n, self.m = cq.n, cq.m
         L = _lib.lib()
         _lib.require_cuda()
-        Phi = np.zeros((self.nz, d.npad))
-        Phi[:, :cq.n] = cq.Phi
-        Dp = np.zeros(d.npad)
-        Dp[:cq.n] = d.D
-        Hs = np.zeros((d.npad, d.npad))
-        Hs[:cq.n, :cq.n] = d.Hs
-        if self.has_ss and Kss is None:
-            raise ValueError("Kss (steady-state gain) is required for the tracking variants")
-        keep = dict(Hs=_lib.f64(Hs), Hinv=_lib.f64(d.Hinv), G=_lib.f64(d.Gs), Y=_lib.f64(d.Y), Fx=_lib.f64(d.Fx),
-                    Fr=_lib.f64(d.Fr), lo0=_lib.f64(d.lo0), up0=_lib.f64(d.up0), Lx=_lib.f64(d.Lx),
-                    Ux=_lib.f64(d.Ux), parC=_lib.f64(d.par_C), parh=_lib.f64(d.par_h), Dscale=_lib.f64(Dp),
-                    Phi=_lib.f64(Phi), Psi=_lib.f64(cq.Psi))
-        if Kss is not None:
-            keep["Kss"] = _lib.f64(np.atleast_2d(Kss))
-        has_lo = np.ascontiguousarray(d.has_lo, np.uint8)
-        has_up = np.ascontiguousarray(d.has_up, np.uint8)
         desc = _lib.QPDesc()
-        desc.nx, desc.nu, desc.N = cq.nx, cq.nu, cq.N
-        desc.n, desc.npad, desc.m, desc.mpad = cq.n, d.npad, cq.m, d.mpad
-        desc.np, desc.nz, desc.nss = len(d.par_h), self.nz, (cq.nx + cq.nu) if self.has_ss else 0
+        for k, v in ints.items():
+            setattr(desc, k, v)
+        for k, v in floats.items():
+            setattr(desc, k, v)
         dp = C.POINTER(C.c_double)
         for k, v in keep.items():
-            setattr(desc, k, v.ctypes.data_as(dp) if v.size else None)
-        desc.has_lo = has_lo.ctypes.data_as(C.POINTER(C.c_uint8))
-        desc.has_up = has_up.ctypes.data_as(C.POINTER(C.c_uint8))
-        desc.s_floor, desc.sc_b, desc.max_iter = d.s_floor, d.sc_b, max_iter
-        desc.min_rows = int(min_rows)
-        shift = np.ascontiguousarray(d.shift, np.int32)
-        desc.shift = shift.ctypes.data_as(C.POINTER(C.c_int32))
+            if v.dtype == np.float64:
+                setattr(desc, k, v.ctypes.data_as(dp) if v.size else None)
+        desc.has_lo = keep["has_lo"].ctypes.data_as(C.POINTER(C.c_uint8))
+        desc.has_up = keep["has_up"].ctypes.data_as(C.POINTER(C.c_uint8))
+        desc.shift = keep["shift"].ctypes.data_as(C.POINTER(C.c_int32))
         h = C.c_void_p()
         _lib.check(L.rtmpc_qp_create(C.byref(desc), C.byref(h)), "rtmpc_qp_create")
         self._h = h
