@@ -271,6 +271,15 @@ int rtmpc_support_sweep(const double* d_V, int32_t nv, int32_t dim, const double
 int rtmpc_support_sweep_host(const double* h_V, int32_t nv, int32_t dim, const double* h_dirs, int64_t M,
                              double* h_out);
 
+/* Model-error sweep for the disturbance set W (Results/estimate_W_for_Cartpole.py:79-127, analytic cartpole ODE instead
+ * of PyBullet): B independent runs; run b starts at x0[b], the plant is driven by the zero-order-hold LQR law
+ * u_k = -K x_k for T control periods (cart_params as in rtmpc_loop_desc: M, m, I, g, l, dt, substeps), and
+ * w[b][k][:] = x_{k+1} - Acl x_k  is recorded.  x_final may be NULL.  nx = 4, nu = 1. */
+int rtmpc_model_error_sweep(const double cart_params[8], int32_t B, int32_t T, const double* d_x0, const double* d_K,
+                            const double* d_Acl, double* d_w, double* d_x_final, void* stream);
+int rtmpc_model_error_sweep_host(const double cart_params[8], int32_t B, int32_t T, const double* h_x0,
+                                 const double* h_K, const double* h_Acl, double* h_w, double* h_x_final);
+
 #ifdef __cplusplus
 }
 #endif

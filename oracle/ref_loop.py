@@ -184,3 +184,24 @@ def cartpole_ode_step(x, F, dt=1.0 / 500.0, M=1.0, m=0.1, I=0.001, g=9.8, l=0.5)
     vel2 = vel + dt * acc
     om2 = om + dt * alp
     return np.array([pos + dt * vel2, vel2, phi + dt * om2, om2])
+
+
+def estimate_model_error(x0s, K, Acl, n_steps, substeps=10, dt=1.0 / 500.0):
+    """``Results/estimate_W_for_Cartpole.py:79-127`` with the analytic plant: for every initial condition hold
+    ``u = -K x`` over ``substeps`` physics steps (the script's ``lim_zoh`` counter, ``:96-113``), record
+    ``w(k) = x(k) - Acl x(k-1)`` at the control instants (``:104-110``).  Returns w [runs, n_steps, 4] and the final
+    states."""
+    x0s = np.asarray(x0s, float).reshape(-1, 4)
+    K = np.asarray(K, float).reshape(1, 4)
+    W = np.zeros((len(x0s), n_steps, 4))
+    XF = np.zeros((len(x0s), 4))
+    for r, x in enumerate(x0s):
+        x = x.copy()
+        for k in range(n_steps):
+            u = float(-(K @ x)[0])
+            prev = x.copy()
+            for _ in range(substeps):
+                x = cartpole_ode_step(x, u, dt=dt)
+            W[r, k] = x - Acl @ prev
+        XF[r] = x
+    return W, XF

@@ -726,4 +726,47 @@ int rtmpc_support_sweep_host(const double* h_V, int32_t nv, int32_t dim, const d
     return rc;
 }
 
+int rtmpc_model_error_sweep(const double cart_params[8], int32_t B, int32_t T, const double* d_x0, const double* d_K,
+                            const double* d_Acl, double* d_w, double* d_x_final, void* stream) {
+    if (!cart_params || !d_x0 || !d_K || !d_Acl || !d_w) return fail("rtmpc_model_error_sweep: null argument");
+    if (B < 0 || T < 0) return fail("rtmpc_model_error_sweep: negative size");
+    if (B == 0 || T == 0) return 0;
+    double* d_c = nullptr;
+    CU(cudaMalloc(&d_c, 8 * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d_c, cart_params, 8 * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e == cudaSuccess) {
+        const int threads = 128;
+        model_error_kernel<<<(B + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(d_c, B, T, d_x0, d_K, d_Acl, d_w, d_x_final);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);      // d_c is freed below
+    cudaFree(d_c);
+    if (e != cudaSuccess) return fail("rtmpc_model_error_sweep", e);
+    return 0;
+}
+
+int rtmpc_model_error_sweep_host(const double cart_params[8], int32_t B, int32_t T, const double* h_x0,
+                                 const double* h_K, const double* h_Acl, double* h_w, double* h_x_final) {
+    if (!cart_params || !h_x0 || !h_K || !h_Acl || !h_w) return fail("rtmpc_model_error_sweep_host: null argument");
+    if (B <= 0 || T <= 0) return 0;
+    double *dx = nullptr, *dk = nullptr, *da = nullptr, *dw = nullptr, *df = nullptr;
+    int rc = 0;
+    const size_t nw = (size_t)B * T * 4 * sizeof(double), nxb = (size_t)B * 4 * sizeof(double);
+    do {
+        if (cudaMalloc(&dx, nxb) != cudaSuccess || cudaMalloc(&dk, 4 * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&da, 16 * sizeof(double)) != cudaSuccess || cudaMalloc(&dw, nw) != cudaSuccess ||
+            cudaMalloc(&df, nxb) != cudaSuccess) { rc = fail("cudaMalloc"); break; }
+        if (cudaMemcpy(dx, h_x0, nxb, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(dk, h_K, 4 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(da, h_Acl, 16 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
+        rc = rtmpc_model_error_sweep(cart_params, B, T, dx, dk, da, dw, df, nullptr);
+        if (rc) break;
+        if (cudaMemcpy(h_w, dw, nw, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
+        if (h_x_final && cudaMemcpy(h_x_final, df, nxb, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
+    } while (0);
+    cudaFree(dx); cudaFree(dk); cudaFree(da); cudaFree(dw); cudaFree(df);
+    return rc;
+}
+
 }  // extern "C"

@@ -649,6 +649,32 @@ __global__ void estimator_update_kernel(EstArgs e, int B) {
     if (e.gamma[b] == 1) e.q_t[b] = e.t;
 }
 
+// Model-error sweep (estimate_W_for_Cartpole.py:79-127): one thread per run, T control periods of the nonlinear plant
+// under the zero-order-hold LQR law, w_k = x_{k+1} - Acl x_k.
+__global__ void model_error_kernel(const double* __restrict__ cart, int B, int T, const double* __restrict__ x0,
+                                   const double* __restrict__ K, const double* __restrict__ Acl,
+                                   double* __restrict__ w, double* __restrict__ x_final) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double c[8], x[4], k[4], a[16];
+    for (int i = 0; i < 8; ++i) c[i] = cart[i];
+    for (int i = 0; i < 4; ++i) { x[i] = x0[(size_t)b * 4 + i]; k[i] = K[i]; }
+    for (int i = 0; i < 16; ++i) a[i] = Acl[i];
+    for (int t = 0; t < T; ++t) {
+        double u = 0.0, lin[4];
+        for (int i = 0; i < 4; ++i) u = fma(-k[i], x[i], u);
+        for (int i = 0; i < 4; ++i) {
+            double acc = 0.0;
+            for (int j = 0; j < 4; ++j) acc = fma(a[i * 4 + j], x[j], acc);
+            lin[i] = acc;
+        }
+        cartpole_substeps(x, u, c);
+        double* wo = w + ((size_t)b * T + t) * 4;
+        for (int i = 0; i < 4; ++i) wo[i] = x[i] - lin[i];
+    }
+    if (x_final) for (int i = 0; i < 4; ++i) x_final[(size_t)b * 4 + i] = x[i];
+}
+
 #endif  // RTMPC_LOOP_KERNELS
 
 }  // namespace rtmpc

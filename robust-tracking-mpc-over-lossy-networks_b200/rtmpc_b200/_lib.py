@@ -22,6 +22,7 @@ EXPORTS = [
     "rtmpc_loop_err_acc", "rtmpc_loop_tube_max", "rtmpc_loop_u", "rtmpc_loop_gamma", "rtmpc_loop_time",
     "rtmpc_loop_step", "rtmpc_loop_rollout",
     "rtmpc_actuator_process", "rtmpc_estimator_update", "rtmpc_support_sweep", "rtmpc_support_sweep_host",
+    "rtmpc_model_error_sweep", "rtmpc_model_error_sweep_host",
 ]
 
 OPTIMAL, MAX_ITER, INFEASIBLE, OPTIMAL_INACCURATE = 0, 1, 2, 3
@@ -106,6 +107,8 @@ def lib():
     L.rtmpc_estimator_update.argtypes = [i32] * 7 + [vp] * 13
     L.rtmpc_support_sweep.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int64, vp, vp]
     L.rtmpc_support_sweep_host.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int64, vp]
+    L.rtmpc_model_error_sweep.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.rtmpc_model_error_sweep_host.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -122,3 +122,42 @@ def linear_system_experiment(tube_mpc, track_mpc, Z, w_half, prob_packet_loss=No
     ms = D.all_reduce_max(ms).cpu().numpy()
     res.solve_ms_tube, res.solve_ms_track = float(ms[0]), float(ms[1])
     return res
+
+
+CARTPOLE_PARAMS = dict(M=1.0, m=0.1, I=0.001, g=9.8, l=0.5)       # Results/estimate_W_for_Cartpole.py:32-38, cartpole.urdf
+
+
+def estimate_disturbance_set(A, B, K, n_runs=100, n_steps=400, x0_half=(1.0, 0.5, 0.3, 0.5), seed=456, outlier=0.025,
+                             physics_timestep=1.0 / 500.0, Th=0.02, x0=None):
+    """Batched ``Results/estimate_W_for_Cartpole.py:79-127``: ``n_runs`` random initial conditions in the box
+    ``+-x0_half`` (script ``:67-75``), each stabilised for ``n_steps`` control periods (the script's 4000 physics steps)
+    by the zero-order-hold LQR law ``u = -K x`` on the nonlinear cartpole (analytic ODE instead of PyBullet, one
+    launch for all runs); the model error ``w(k) = x(k) - (A - BK) x(k-1)`` (``:104-110``) is collected and the
+    interval that discards the ``outlier`` share of largest absolute values per component is returned (``:123-127``).
+
+    Returns ``(intervals [nx, 2], w [n_runs, n_steps, nx], x_final [n_runs, nx])``; ``max |intervals|`` per component
+    is the half-width vector ``hw`` the experiment scripts build ``W`` from."""
+    import ctypes as C
+    from . import _lib
+    A, B, K = np.asarray(A, float), np.asarray(B, float), np.atleast_2d(np.asarray(K, float))
+    if A.shape != (4, 4) or K.shape != (1, 4):
+        raise ValueError("the cartpole plant has nx = 4, nu = 1")
+    L = _lib.lib()
+    _lib.require_cuda()
+    if x0 is None:
+        rng = np.random.default_rng(seed)
+        h = np.asarray(x0_half, float)
+        x0 = rng.uniform(-h, h, size=(n_runs, 4))                      # the script draws the four components in this order
+    x0 = _lib.f64(np.asarray(x0, float).reshape(-1, 4))
+    n_runs = x0.shape[0]
+    Acl = _lib.f64(A - B @ K)
+    Kf = _lib.f64(K.reshape(-1))
+    p = CARTPOLE_PARAMS
+    cart = (C.c_double * 8)(p["M"], p["m"], p["I"], p["g"], p["l"], physics_timestep, round(Th / physics_timestep), 0.0)
+    w = np.empty((n_runs, n_steps, 4))
+    xf = np.empty((n_runs, 4))
+    _lib.check(L.rtmpc_model_error_sweep_host(cart, n_runs, n_steps, _lib.ptr(x0), _lib.ptr(Kf), _lib.ptr(Acl), _lib.ptr(w),
+                                              _lib.ptr(xf)), "rtmpc_model_error_sweep_host")
+    flat = w.reshape(-1, 4)
+    iv = np.stack([np.quantile(flat, outlier / 2, axis=0), np.quantile(flat, 1.0 - outlier / 2, axis=0)], axis=1)
+    return iv, w, xf

@@ -48,3 +48,25 @@ def test_extended_arm_and_nonlinear_plant():
     assert "ERT-MPC" in res.summary()
     nl = linear_system_experiment(tube, None, None, hw, prob_packet_loss=[0.0, 0.6], n_mc=3, T=80, seed=5, plant="cartpole")
     assert np.all(np.isfinite(nl.tracking_error_tube)) and nl.tracking_error_tube.max() < 0.2
+
+
+def test_disturbance_set_estimation_matches_oracle():
+    """Results/estimate_W_for_Cartpole.py on the analytic plant: the batched sweep against the oracle's loop, and the
+    properties the script relies on (every run is stabilised; the model error vanishes with the state)."""
+    from oracle import ref_loop as rl
+    from rtmpc_b200.experiments import estimate_disturbance_set
+    s = H.load("sets_cp.npz")
+    A, B, K = s["A"], s["B"], s["K"]
+    iv, w, xf = estimate_disturbance_set(A, B, K, n_runs=100, n_steps=400)
+    assert w.shape == (100, 400, 4) and iv.shape == (4, 2)
+    assert np.abs(xf).max() < 1e-3                                   # script :117-118 "System not stabilized"
+    rng = np.random.default_rng(456)
+    x0 = rng.uniform(-np.array([1.0, 0.5, 0.3, 0.5]), np.array([1.0, 0.5, 0.3, 0.5]), size=(100, 4))
+    wo, xfo = rl.estimate_model_error(x0[:12], K, A - B @ K, 400)
+    assert np.abs(w[:12] - wo).max() <= 1e-10 * max(1.0, np.abs(wo).max())
+    assert np.abs(xf[:12] - xfo).max() <= 1e-10
+    assert np.all(iv[:, 0] < 0) and np.all(iv[:, 1] > 0)
+    assert np.abs(w[:, -1]).max() < 1e-6 * max(1e-30, np.abs(w[:, 0]).max()) + 1e-9     # linearisation exact at the origin
+    # a second call with explicit initial conditions and another length
+    iv2, w2, _ = estimate_disturbance_set(A, B, K, n_steps=50, x0=x0[:7])
+    assert np.array_equal(w2, w[:7, :50])

@@ -79,3 +79,25 @@ def test_cartpole_ode_linearises_to_reference_matrices():
     J = np.stack([(step(x0 + eps * e, 0.0) - step(x0 - eps * e, 0.0)) / (2 * eps) for e in np.eye(4)], axis=1)
     Bd = (step(x0, eps) - step(x0, -eps)) / (2 * eps)
     assert np.abs(J - A).max() < 5e-3 and np.abs(Bd - B[:, 0]).max() < 5e-4   # Euler vs ZOH
+
+
+def test_model_error_restatement_properties():
+    """estimate_W_for_Cartpole.py:79-127 restated on the analytic plant: zero model error at the origin, second order
+    in the state (the linearisation is exact to first order), LQR stabilises the nonlinear plant from the script's box."""
+    from oracle import ref_loop as rl
+    s = H.load("sets_cp.npz")
+    A, B, K = s["A"], s["B"], s["K"]
+    Acl = A - B @ K
+    w0, _ = rl.estimate_model_error(np.zeros((1, 4)), K, Acl, 3)
+    assert np.abs(w0).max() == 0.0
+    x0 = np.array([[0.2, 0.1, 0.05, 0.1]])
+    w1, _ = rl.estimate_model_error(x0, K, Acl, 1)
+    w2, _ = rl.estimate_model_error(0.5 * x0, K, Acl, 1)
+    # the discretisations differ (ZOH-exact A, B against semi-implicit Euler sub-steps): that part is linear in x;
+    # what is left after removing it halves-squared
+    lin = 2.0 * w2 - w1            # = linear part of w1 (up to third order)
+    quad = w1 - lin
+    assert np.abs(quad).max() <= 4.0 * np.abs(w1).max()
+    assert np.abs(w1).max() < 0.1
+    _, xf = rl.estimate_model_error(np.array([[1.0, 0.5, 0.3, 0.5], [-1.0, -0.5, -0.3, -0.5]]), K, Acl, 400)
+    assert np.abs(xf).max() < 1e-3
