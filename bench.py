@@ -400,6 +400,121 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def support_directions(s, M, seed=1):
+    """BASELINE configs[4]: rows of Hd Acl^j and Hw Acl^j of the cartpole (the directions Darup's RPI
+    and the constraint tightening evaluate), filled up with unit-normal Gaussian directions to M rows."""
+    Acl = s["A"] - s["B"] @ np.atleast_2d(s["K"])
+    Hd = np.vstack([s["X_A"], -s["U_A"] @ np.atleast_2d(s["K"])])
+    rows, P = [], np.eye(4)
+    for _ in range(308):                      # k* of the cartpole's Darup RPI
+        rows.append(Hd @ P)
+        rows.append(s["W_A"] @ P)
+        P = P @ Acl
+    D = np.vstack(rows)
+    rng = np.random.default_rng(seed)
+    return np.ascontiguousarray(np.vstack([D, rng.normal(size=(M - len(D), 4))])[:M])
+
+
+def run_support_arm(args):
+    """--workload c5: h_Z(a) = max over the vertices of the tube Z for 10^6 directions, sharded over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from rtmpc_b200 import _lib, polytope as pc, sets as up
+    from rtmpc_b200 import distributed as D
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the GPU arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    s = load_sets()
+    Mtot = 1_000_000
+    off, M = D.shard(Mtot, rank, world)
+    dirs_h = support_directions(s, Mtot)[off:off + M]
+    V_h = np.ascontiguousarray(pc.extreme(pc.Polytope(s["Z_A"], s["Z_b"], normalize=False)))
+    nv, dim = V_h.shape
+    V = torch.as_tensor(V_h, device=dev); dirs = torch.as_tensor(dirs_h, device=dev); out = torch.empty(M, device=dev, dtype=torch.float64)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+    stream = torch.cuda.current_stream()
+
+    def sweep():
+        _lib.check(L.rtmpc_support_sweep(_lib.ptr(V), nv, dim, _lib.ptr(dirs), M, _lib.ptr(out), stream.cuda_stream), "rtmpc_support_sweep")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        sweep()
+    barrier()
+    total_ms = 0.0
+    launches0 = L.rtmpc_launch_count()
+    with ClockSampler(local) as clk:
+        barrier()
+        for k in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); sweep(); e1.record(stream)
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        barrier()
+    launches = L.rtmpc_launch_count() - launches0
+    t_ms = float(D.all_reduce_max(torch.tensor([total_ms], device=dev, dtype=torch.float64)).item())
+    value = Mtot * args.steps / (t_ms * 1e-3)
+    # e2e: host directions in, host values out through the reference-facing call (sets.support_sweep)
+    hv = up.support_sweep(V_h, dirs_h[:1000])
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        hv = up.support_sweep(V_h, dirs_h)
+    barrier()
+    dt = float(D.all_reduce_max(torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)).item())
+    same = bool(np.array_equal(hv, out.cpu().numpy()))
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fp64_peak = measure_fp64_peak(torch, dev)
+        flops = 2.0 * dim * nv * M
+        byts = (dim + 1) * 8.0 * M
+        ms_launch = total_ms / args.steps
+        # CPU arm: the oracle's support function (one HiGHS LP per direction) on a bounded sample
+        from oracle import ref_sets as rs
+        from oracle.ref_polytope import Polytope as OP
+        Zo = OP(s["Z_A"], s["Z_b"], normalize=False)
+        n_cpu = 300
+        c0 = time.perf_counter()
+        ref_vals = np.array([rs.support(Zo, d) for d in dirs_h[:n_cpu]])
+        cpu_dt = time.perf_counter() - c0
+        err = float(np.abs(ref_vals - hv[:n_cpu]).max())
+        print(json.dumps({
+            "metric": "support-function sweep directions/sec (BASELINE configs[4])", "value": value, "unit": "directions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"h_Z(a) over 10^6 directions (rows of Hd Acl^j, Hw Acl^j of the cartpole + Gaussian directions, seed 1) "
+                                   f"sharded over the ranks; Z = the cartpole tube, {nv} vertices in {dim}-D staged in shared memory",
+                       "baseline_config": "c5", "l2": "256 MB buffer written between timed sweeps (L2 flush)"},
+            "e2e": {"value": Mtot * args.steps / dt, "unit": "directions/s", "h2d_bytes_per_step": int(dirs_h.nbytes + V_h.nbytes),
+                    "d2h_bytes_per_step": int(M * 8), "api": "rtmpc_b200.sets.support_sweep(V, dirs) on host arrays -> rtmpc_support_sweep_host",
+                    "identical_to_device_call": same},
+            "gpu_launches": int(launches), "clocks": clk.summary(),
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA)", "kernel": "support_sweep_kernel",
+                         "achieved": flops / (ms_launch * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": flops / (ms_launch * 1e-3) / 1e12 / fp64_peak, "traffic": None,
+                         "algorithmic_hbm_gbs": byts / (ms_launch * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                         "peak_source": "cuBLAS DGEMM 6144^3 measured in this run"},
+            "cpu_baseline": {"value": n_cpu / cpu_dt, "unit": "directions/s", "cores": 1, "kind": "port",
+                             "sample": f"{n_cpu} directions, oracle support() = one HiGHS LP each (utils_polytope.py:12-23)"},
+            "checks": {"max_abs_diff_vs_oracle_lp": err}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -430,12 +545,16 @@ def main():
     ap.add_argument("--cpu-solves", type=int, default=8192, dest="cpu_solves",
                     help="QP solves of the CPU arm per step (bounded sample of the workload, ~10 s on 16 cores)")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
-    ap.add_argument("--instances", type=int, default=B_PER_GPU, help="closed-loop instances per GPU (BASELINE configs[1]: 4096)")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
-                    help="c2 (default, the headline): BASELINE configs[1]; c3: extended variant; c4: analytic cartpole plant")
+    ap.add_argument("--instances", type=int, default=B_PER_GPU, help="closed-loop instances per GPU (BASELINE configs[1]: 4096; configs[2] = --workload c3 --instances 8192 on 8 GPUs, "
+                         "configs[3] = --workload c4 --instances 32768 on 8 GPUs)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"],
+                    help="c2 (default, the headline): BASELINE configs[1]; c3: extended variant; c4: analytic cartpole plant; "
+                         "c5: support-function sweep over 10^6 directions (its own metric)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "c5":
+        run_support_arm(args)
     else:
         run_gpu_arm(args)
 

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -686,44 +687,66 @@ int rtmpc_support_sweep(const double* d_V, int32_t nv, int32_t dim, const double
     if (!d_V || !d_dirs || !d_out) return fail("rtmpc_support_sweep: null argument");
     if (dim < 1 || dim > 16) return fail("rtmpc_support_sweep: need 1 <= dim <= 16");
     if (M <= 0) return 0;
-    const size_t smem = (size_t)nv * dim * sizeof(double);
-    if (smem > 200 * 1024) return fail("rtmpc_support_sweep: vertex set does not fit in shared memory");
+    const int kc = (dim + 3) / 4, nv8 = (nv + 7) & ~7;
+    const size_t smem = (size_t)kc * nv8 * 4 * sizeof(double);
+    if (nv < 1 || smem > 200 * 1024) return fail("rtmpc_support_sweep: vertex set does not fit in shared memory");
+    typedef void (*sweep_fn)(const double*, int, int, const double*, long long, double*);
+    static const sweep_fn fns[4] = {support_sweep_kernel<4, 1>, support_sweep_kernel<4, 2>, support_sweep_kernel<2, 3>,
+                                    support_sweep_kernel<2, 4>};
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute((const void*)support_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (int i = 0; i < 4; ++i)
+            CU(cudaFuncSetAttribute((const void*)fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
     int dev = 0, sms = 0;
     CU(cudaGetDevice(&dev));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int threads = 256;
-    long long blocks = (M + threads - 1) / threads;
-    const long long cap = (long long)sms * 8;
-    if (blocks > cap) blocks = cap;
-    support_sweep_kernel<<<(int)blocks, threads, smem, (cudaStream_t)stream>>>(d_V, nv, dim, d_dirs, (long long)M, d_out);
+    // one block per SM stages the vertices once; a warp takes 8 * RT directions per trip
+    const int threads = 512;
+    const int per_block = (threads / 32) * 8 * (kc <= 2 ? 4 : 2);
+    long long blocks = (M + per_block - 1) / per_block;
+    if (blocks > sms) blocks = sms;
+    fns[kc - 1]<<<(int)blocks, threads, smem, (cudaStream_t)stream>>>(d_V, nv, dim, d_dirs, (long long)M, d_out);
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
     return 0;
 }
 
+// device staging of the host-buffer entry points: grown on demand, kept for the life of the process (a cudaMalloc /
+// cudaFree pair per call costs more than the sweep itself)
+namespace {
+struct HostStage {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const cudaError_t e = cudaMalloc(&p, bytes + bytes / 4);
+        if (e == cudaSuccess) cap = bytes + bytes / 4;
+        return e;
+    }
+};
+std::mutex g_stage_mu;
+HostStage g_stage[5];
+}  // namespace
+
 int rtmpc_support_sweep_host(const double* h_V, int32_t nv, int32_t dim, const double* h_dirs, int64_t M,
                              double* h_out) {
     if (!h_V || !h_dirs || !h_out) return fail("rtmpc_support_sweep_host: null argument");
     if (M <= 0) return 0;
-    double *dV = nullptr, *dD = nullptr, *dO = nullptr;
-    int rc = 0;
-    do {
-        if (cudaMalloc(&dV, (size_t)nv * dim * sizeof(double)) != cudaSuccess) { rc = fail("cudaMalloc"); break; }
-        if (cudaMalloc(&dD, (size_t)M * dim * sizeof(double)) != cudaSuccess) { rc = fail("cudaMalloc"); break; }
-        if (cudaMalloc(&dO, (size_t)M * sizeof(double)) != cudaSuccess) { rc = fail("cudaMalloc"); break; }
-        if (cudaMemcpy(dV, h_V, (size_t)nv * dim * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
-        if (cudaMemcpy(dD, h_dirs, (size_t)M * dim * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
-        rc = rtmpc_support_sweep(dV, nv, dim, dD, M, dO, nullptr);
-        if (rc) break;
-        if (cudaMemcpy(h_out, dO, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
-    } while (0);
-    cudaFree(dV); cudaFree(dD); cudaFree(dO);
-    return rc;
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    const size_t bV = (size_t)nv * dim * sizeof(double), bD = (size_t)M * dim * sizeof(double), bO = (size_t)M * sizeof(double);
+    CU(g_stage[0].need(bV));
+    CU(g_stage[1].need(bD));
+    CU(g_stage[2].need(bO));
+    double *dV = (double*)g_stage[0].p, *dD = (double*)g_stage[1].p, *dO = (double*)g_stage[2].p;
+    CU(cudaMemcpy(dV, h_V, bV, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dD, h_dirs, bD, cudaMemcpyHostToDevice));
+    if (rtmpc_support_sweep(dV, nv, dim, dD, M, dO, nullptr)) return -1;
+    CU(cudaMemcpy(h_out, dO, bO, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int rtmpc_model_error_sweep(const double cart_params[8], int32_t B, int32_t T, const double* d_x0, const double* d_K,
@@ -750,23 +773,22 @@ int rtmpc_model_error_sweep_host(const double cart_params[8], int32_t B, int32_t
                                  const double* h_K, const double* h_Acl, double* h_w, double* h_x_final) {
     if (!cart_params || !h_x0 || !h_K || !h_Acl || !h_w) return fail("rtmpc_model_error_sweep_host: null argument");
     if (B <= 0 || T <= 0) return 0;
-    double *dx = nullptr, *dk = nullptr, *da = nullptr, *dw = nullptr, *df = nullptr;
-    int rc = 0;
+    std::lock_guard<std::mutex> lock(g_stage_mu);
     const size_t nw = (size_t)B * T * 4 * sizeof(double), nxb = (size_t)B * 4 * sizeof(double);
-    do {
-        if (cudaMalloc(&dx, nxb) != cudaSuccess || cudaMalloc(&dk, 4 * sizeof(double)) != cudaSuccess ||
-            cudaMalloc(&da, 16 * sizeof(double)) != cudaSuccess || cudaMalloc(&dw, nw) != cudaSuccess ||
-            cudaMalloc(&df, nxb) != cudaSuccess) { rc = fail("cudaMalloc"); break; }
-        if (cudaMemcpy(dx, h_x0, nxb, cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(dk, h_K, 4 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(da, h_Acl, 16 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
-        rc = rtmpc_model_error_sweep(cart_params, B, T, dx, dk, da, dw, df, nullptr);
-        if (rc) break;
-        if (cudaMemcpy(h_w, dw, nw, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
-        if (h_x_final && cudaMemcpy(h_x_final, df, nxb, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail("cudaMemcpy"); break; }
-    } while (0);
-    cudaFree(dx); cudaFree(dk); cudaFree(da); cudaFree(dw); cudaFree(df);
-    return rc;
+    CU(g_stage[0].need(nxb));
+    CU(g_stage[1].need(nw));
+    CU(g_stage[2].need(nxb));
+    CU(g_stage[3].need(4 * sizeof(double)));
+    CU(g_stage[4].need(16 * sizeof(double)));
+    double *dx = (double*)g_stage[0].p, *dw = (double*)g_stage[1].p, *df = (double*)g_stage[2].p;
+    double *dk = (double*)g_stage[3].p, *da = (double*)g_stage[4].p;
+    CU(cudaMemcpy(dx, h_x0, nxb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dk, h_K, 4 * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(da, h_Acl, 16 * sizeof(double), cudaMemcpyHostToDevice));
+    if (rtmpc_model_error_sweep(cart_params, B, T, dx, dk, da, dw, df, nullptr)) return -1;
+    CU(cudaMemcpy(h_w, dw, nw, cudaMemcpyDeviceToHost));
+    if (h_x_final) CU(cudaMemcpy(h_x_final, df, nxb, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 }  // extern "C"

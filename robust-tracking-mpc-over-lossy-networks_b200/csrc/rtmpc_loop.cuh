@@ -508,22 +508,70 @@ __global__ void loop_step_kernel(LoopDev L, int B, int t, const double* __restri
                    (unsigned long long)(id_offset + b), traj_b, worst);
 }
 
-// out[j] = max_v <dirs[j,:], V[v,:]> ; one thread per direction, vertices staged in shared memory
-__global__ void support_sweep_kernel(const double* __restrict__ V, int nv, int dim,
-                                     const double* __restrict__ dirs, long long M, double* __restrict__ out) {
+// out[j] = max_v <dirs[j,:], V[v,:]> as a product  dirs [M x dim] * V' [dim x nv]  reduced by a row maximum, on the FP64
+// tensor pipe: mma.sync m8n8k4 (the instruction cuBLAS DGEMM runs on here; tcgen05 has no f64 kind).  One warp owns
+// RT tiles of 8 directions (A fragments stay in registers for the whole sweep); the vertices are staged once per
+// block in shared memory as [KC][nv8][4] (KC chunks of four coordinates, zero padded; nv rounded up to a multiple
+// of 8 by repeating vertex 0), so the B fragment of a tile of 8 vertices is 32 consecutive doubles: one conflict-free
+// 8-byte load per lane, shared by the RT products.  Each product is followed by two compare-selects per lane; the
+// maxima of a row's four lanes are combined at the very end.
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b, double c0, double c1) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                 : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
+template <int RT, int KC>
+__global__ void __launch_bounds__(512, 1)
+support_sweep_kernel(const double* __restrict__ V, int nv, int dim, const double* __restrict__ dirs, long long M,
+                     double* __restrict__ out) {
     extern __shared__ __align__(16) double sv[];
-    for (int i = threadIdx.x; i < nv * dim; i += blockDim.x) sv[i] = V[i];
+    const int nv8 = (nv + 7) & ~7;
+    for (int i = threadIdx.x; i < KC * nv8 * 4; i += blockDim.x) {
+        const int kc = i / (nv8 * 4), r = i - kc * (nv8 * 4), v = r >> 2, k = kc * 4 + (r & 3);
+        sv[i] = (k < dim) ? V[(size_t)(v < nv ? v : 0) * dim + k] : 0.0;
+    }
     __syncthreads();
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (long long)gridDim.x * blockDim.x) {
-        double a[16];
-        for (int k = 0; k < dim; ++k) a[k] = dirs[j * dim + k];
-        double best = -RTMPC_INF;
-        for (int v = 0; v < nv; ++v) {
-            double acc = 0.0;
-            for (int k = 0; k < dim; ++k) acc = fma(a[k], sv[v * dim + k], acc);
-            best = fmax(best, acc);
+    const int lane = threadIdx.x & 31;
+    const int row = lane >> 2, col = lane & 3;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp0 * (8 * RT); base < M; base += nwarps * (8 * RT)) {
+        double a[RT][KC], best0[RT], best1[RT];
+#pragma unroll
+        for (int t = 0; t < RT; ++t) {
+            const long long j = base + 8 * t + row;
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) {
+                const int k = kc * 4 + col;
+                a[t][kc] = (j < M && k < dim) ? dirs[j * dim + k] : 0.0;
+            }
+            best0[t] = -RTMPC_INF;
+            best1[t] = -RTMPC_INF;
         }
-        out[j] = best;
+#pragma unroll 2
+        for (int vt = 0; vt < nv8; vt += 8) {
+            double b[KC];
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) b[kc] = sv[(kc * nv8 + vt) * 4 + lane];
+#pragma unroll
+            for (int t = 0; t < RT; ++t) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) dmma884(c0, c1, a[t][kc], b[kc], c0, c1);
+                best0[t] = (c0 > best0[t]) ? c0 : best0[t];       // (a compare and a select; FP64 fmax is a longer sequence)
+                best1[t] = (c1 > best1[t]) ? c1 : best1[t];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < RT; ++t) {
+            double m = (best0[t] > best1[t]) ? best0[t] : best1[t];
+            double o = __shfl_xor_sync(RTMPC_FULL_MASK, m, 1);
+            m = (o > m) ? o : m;
+            o = __shfl_xor_sync(RTMPC_FULL_MASK, m, 2);
+            m = (o > m) ? o : m;
+            const long long j = base + 8 * t + row;
+            if (col == 0 && j < M) out[j] = m;
+        }
     }
 }
 

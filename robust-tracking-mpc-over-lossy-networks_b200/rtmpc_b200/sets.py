@@ -37,7 +37,7 @@ def support_sweep(V, dirs):
     _lib.require_cuda()
     out = np.empty(dirs.shape[0])
     nv, dim = V.shape
-    chunk = max(1, (190 * 1024) // (8 * dim))          # vertices per launch (shared-memory staging)
+    chunk = max(8, ((190 * 1024) // (8 * 4 * ((dim + 3) // 4))) & ~7)     # vertices per launch (shared-memory staging, coordinates padded to 4)
     best = np.full(dirs.shape[0], -np.inf)
     for s in range(0, nv, chunk):
         Vc = _lib.f64(V[s:s + chunk])
