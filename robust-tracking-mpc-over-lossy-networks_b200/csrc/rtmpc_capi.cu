@@ -509,22 +509,13 @@ int rtmpc_loop_reset(rtmpc_loop* l, const double* h_x0) {
     LoopDev& L = l->dev;
     const size_t B = l->B, nx = L.nx, nu = L.nu;
     CU(cudaMemcpy(L.x, h_x0, B * nx * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(L.x_nom, h_x0, B * nx * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(L.x_hat, h_x0, B * nx * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemset(L.buf, 0, B * (L.N + 1) * nu * sizeof(double)));
-    CU(cudaMemset(L.u_last, 0, B * nu * sizeof(double)));
-    CU(cudaMemset(L.err_acc, 0, B * sizeof(double)));
-    std::vector<double> neg(B, -1e300);
-    CU(cudaMemcpy(L.tube_max, neg.data(), B * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaMemset(L.q_t, 0, B * sizeof(int)));
-    CU(cudaMemset(L.s_t, 0, B * sizeof(int)));
-    CU(cudaMemset(L.Theta, 0, B * sizeof(int)));
-    std::vector<int> ones(B, 1), minus(B, -1);
-    CU(cudaMemcpy(L.alive, ones.data(), B * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(L.last_loss, minus.data(), B * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(L.gamma_last, ones.data(), B * sizeof(int), cudaMemcpyHostToDevice));
-    if (l->r_warm) CU(cudaMemset(l->r_warm, 0xFF, B * (size_t)l->r_warm_stride * sizeof(int)));
-    if (l->r_warm1) CU(cudaMemset(l->r_warm1, 0xFF, B * (size_t)l->r_warm1_stride * sizeof(int)));
+    (void)nu;
+    const int threads = 128;
+    loop_reset_kernel<<<(int)((B + threads - 1) / threads), threads>>>(L, (int)B, l->r_warm, l->r_warm_stride, l->r_warm1,
+                                                                        l->r_warm1_stride);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());        // callers may continue on any stream
     l->t = 0;
     return 0;
 }

@@ -697,6 +697,27 @@ __global__ void estimator_update_kernel(EstArgs e, int B) {
     if (e.gamma[b] == 1) e.q_t[b] = e.t;
 }
 
+// (re)initialisation of every instance in one launch: x_nom = x_hat = x (already copied in), empty buffers, t = 0 state
+// of the actuator / estimator objects (SmartActuator.py:13-24,129-144, Estimator.py:11-26), warm-start records cleared
+__global__ void loop_reset_kernel(LoopDev L, int B, int* __restrict__ warm0, int stride0, int* __restrict__ warm1, int stride1) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nx = L.nx, nu = L.nu, usz = (L.N + 1) * nu;
+    for (int k = 0; k < nx; ++k) {
+        const double v = L.x[(size_t)b * nx + k];
+        L.x_nom[(size_t)b * nx + k] = v;
+        L.x_hat[(size_t)b * nx + k] = v;
+    }
+    for (int i = 0; i < usz; ++i) L.buf[(size_t)b * usz + i] = 0.0;
+    for (int j = 0; j < nu; ++j) L.u_last[(size_t)b * nu + j] = 0.0;
+    L.err_acc[b] = 0.0;
+    L.tube_max[b] = -1e300;
+    L.q_t[b] = 0; L.s_t[b] = 0; L.Theta[b] = 0;
+    L.alive[b] = 1; L.last_loss[b] = -1; L.gamma_last[b] = 1;
+    if (warm0) for (int i = 0; i < stride0; ++i) warm0[(size_t)b * stride0 + i] = -1;
+    if (warm1) for (int i = 0; i < stride1; ++i) warm1[(size_t)b * stride1 + i] = -1;
+}
+
 // Model-error sweep (estimate_W_for_Cartpole.py:79-127): one thread per run, T control periods of the nonlinear plant
 // under the zero-order-hold LQR law, w_k = x_{k+1} - Acl x_k.
 __global__ void model_error_kernel(const double* __restrict__ cart, int B, int T, const double* __restrict__ x0,
