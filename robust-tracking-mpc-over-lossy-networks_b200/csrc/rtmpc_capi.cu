@@ -21,6 +21,16 @@ static int fail(const char* what, cudaError_t e = cudaSuccess) {
     if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
     return -1;
 }
+// a handle's arrays live on the device that was current when it was created
+static int wrong_device(int handle_device, const char* who) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != handle_device) {
+        g_err = std::string(who) + ": the handle belongs to device " + std::to_string(handle_device) +
+                " but device " + std::to_string(cur) + " is current (rtmpc_set_device)";
+        return 1;
+    }
+    return 0;
+}
 #define CU(call)                                                    \
     do {                                                            \
         cudaError_t _e = (call);                                    \
@@ -293,6 +303,7 @@ int rtmpc_qp_solve(rtmpc_qp* q, int32_t B, const double* d_x_init, const double*
                    int32_t sel_value, int32_t* d_warm, double* d_z, double* d_U_t, int32_t* d_status, int32_t* d_iters,
                    void* stream) {
     if (!q) return fail("rtmpc_qp_solve: null handle");
+    if (wrong_device(q->device, "rtmpc_qp_solve")) return -1;
     if (B <= 0) return 0;
     if (!d_x_init) return fail("rtmpc_qp_solve: d_x_init is null");
     QPLaunch a;
@@ -348,6 +359,7 @@ int rtmpc_qp_solve_host(rtmpc_qp* q, int32_t B, const double* h_x_init, const do
                         int32_t sel_value, int32_t warm, double* h_z, double* h_U_t, int32_t* h_status,
                         int32_t* h_iters) {
     if (!q) return fail("rtmpc_qp_solve_host: null handle");
+    if (wrong_device(q->device, "rtmpc_qp_solve_host")) return -1;
     if (B <= 0) return 0;
     if (ensure_staging(q, B)) return -1;
     const QPDev& P = q->dev;
@@ -389,7 +401,7 @@ int rtmpc_qp_warm_reset(rtmpc_qp* q) {
 struct rtmpc_loop {
     LoopDev dev;
     std::vector<void*> allocs;
-    int B = 0, t = 0;
+    int B = 0, t = 0, device = 0;
     // scratch of rtmpc_loop_rollout
     double *r_U = nullptr, *r_ref = nullptr;
     int *r_status = nullptr, *r_iters = nullptr, *r_inst_t = nullptr, *r_pending = nullptr, *r_npend = nullptr;
@@ -423,6 +435,7 @@ int rtmpc_loop_create(const rtmpc_loop_desc* d, int32_t B, rtmpc_loop** out) {
     if (!d->A || !d->B || !d->K) return fail("rtmpc_loop_create: A, B, K required");
     rtmpc_loop* l = new rtmpc_loop();
     l->B = B;
+    if (cudaGetDevice(&l->device) != cudaSuccess) { delete l; return fail("rtmpc_loop_create: no CUDA device"); }
     LoopDev& L = l->dev;
     std::memset(&L, 0, sizeof(L));
     L.nx = d->nx; L.nu = d->nu; L.N = d->N; L.actuator = d->actuator; L.plant = d->plant; L.nz_rows = d->nz_rows;
@@ -506,6 +519,7 @@ void rtmpc_loop_destroy(rtmpc_loop* l) {
 
 int rtmpc_loop_reset(rtmpc_loop* l, const double* h_x0) {
     if (!l || !h_x0) return fail("rtmpc_loop_reset: null argument");
+    if (wrong_device(l->device, "rtmpc_loop_reset")) return -1;
     LoopDev& L = l->dev;
     const size_t B = l->B, nx = L.nx, nu = L.nu;
     CU(cudaMemcpy(L.x, h_x0, B * nx * sizeof(double), cudaMemcpyHostToDevice));
@@ -538,6 +552,7 @@ int rtmpc_loop_step(rtmpc_loop* l, const double* d_U_t, const int32_t* d_status,
                     const double* d_w, const double* d_p_loss, uint64_t seed, int64_t id_offset, double* d_traj_x,
                     int64_t traj_stride, void* stream) {
     if (!l || !d_U_t) return fail("rtmpc_loop_step: null argument");
+    if (wrong_device(l->device, "rtmpc_loop_step")) return -1;
     if ((d_theta == nullptr) != (d_gamma == nullptr)) return fail("rtmpc_loop_step: theta and gamma must be given together");
     const int threads = 128;
     const int blocks = (l->B + threads - 1) / threads;
@@ -565,6 +580,8 @@ int rtmpc_loop_rollout(rtmpc_loop* l, rtmpc_qp* q, rtmpc_qp* q1, int32_t T, cons
                        const double* d_p_loss, uint64_t seed, int64_t id_offset, double* d_traj_x, int64_t traj_stride,
                        uint64_t* d_stats, void* stream) {
     if (!l || !q) return fail("rtmpc_loop_rollout: null handle");
+    if (wrong_device(l->device, "rtmpc_loop_rollout") || wrong_device(q->device, "rtmpc_loop_rollout") ||
+        (q1 && wrong_device(q1->device, "rtmpc_loop_rollout"))) return -1;
     if (T <= 0) return 0;
     if ((d_theta == nullptr) != (d_gamma == nullptr)) return fail("rtmpc_loop_rollout: theta and gamma must be given together");
     const QPDev& P = q->dev;
@@ -684,14 +701,14 @@ int rtmpc_support_sweep(const double* d_V, int32_t nv, int32_t dim, const double
     typedef void (*sweep_fn)(const double*, int, int, const double*, long long, double*);
     static const sweep_fn fns[4] = {support_sweep_kernel<4, 1>, support_sweep_kernel<4, 2>, support_sweep_kernel<2, 3>,
                                     support_sweep_kernel<2, 4>};
-    static bool attr_set = false;
-    if (!attr_set) {
-        for (int i = 0; i < 4; ++i)
-            CU(cudaFuncSetAttribute((const void*)fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
     int dev = 0, sms = 0;
     CU(cudaGetDevice(&dev));
+    static std::atomic<unsigned long long> configured{0};       // function attributes are per device
+    if (dev >= 64 || !((configured.load() >> dev) & 1ull)) {
+        for (int i = 0; i < 4; ++i)
+            CU(cudaFuncSetAttribute((const void*)fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (dev < 64) configured.fetch_or(1ull << dev);
+    }
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     // one block per SM stages the vertices once; a warp takes 8 * RT directions per trip
     const int threads = 512;
@@ -710,9 +727,17 @@ namespace {
 struct HostStage {
     void* p = nullptr;
     size_t cap = 0;
+    int dev = -1;
     cudaError_t need(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        int cur = 0;
+        cudaError_t e0 = cudaGetDevice(&cur);
+        if (e0 != cudaSuccess) return e0;
+        if (bytes <= cap && cur == dev) return cudaSuccess;
+        if (p) {
+            // (a buffer that lives on another device is released there)
+            if (dev != cur) { cudaSetDevice(dev); cudaFree(p); cudaSetDevice(cur); } else cudaFree(p);
+        }
+        dev = cur;
         p = nullptr; cap = 0;
         const cudaError_t e = cudaMalloc(&p, bytes + bytes / 4);
         if (e == cudaSuccess) cap = bytes + bytes / 4;

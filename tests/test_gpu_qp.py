@@ -289,3 +289,23 @@ def test_cartpole_hard_cases_after_reference_jumps():
     assert np.array_equal(st2, g["status"]), np.bincount(st2, minlength=4)
     assert (it2 & 0xFFF)[ok].min() >= 1
     assert np.abs(z2[ok] - z[ok]).max() <= TOL_TIGHT * max(1.0, np.abs(z[ok]).max())
+
+
+def test_handles_are_bound_to_their_device():
+    """A handle used while another device is current fails loudly instead of touching foreign memory."""
+    import torch
+    from rtmpc_b200 import _lib
+    from rtmpc_b200.qp import BatchedQP
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = H.load("sets_di.npz")
+    qp = BatchedQP(H.spec_tube_tracking(s), Kss=s["K"])
+    L = _lib.lib()
+    try:
+        _lib.check(L.rtmpc_set_device(1), "rtmpc_set_device")
+        with pytest.raises(_lib.RtmpcError, match="belongs to device 0"):
+            qp.solve_host(np.zeros((1, 2)), np.zeros((1, 2)))
+    finally:
+        _lib.check(L.rtmpc_set_device(0), "rtmpc_set_device")
+    _, _, st, _ = qp.solve_host(np.zeros((1, 2)), np.zeros((1, 2)))
+    assert st[0] == 0
