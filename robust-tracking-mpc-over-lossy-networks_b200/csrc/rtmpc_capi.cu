@@ -501,7 +501,7 @@ int rtmpc_loop_create(const rtmpc_loop_desc* d, int32_t B, rtmpc_loop** out) {
     rc |= lalloc(l, (size_t)B, &l->r_iters);
     rc |= lalloc(l, (size_t)B, &l->r_inst_t);
     rc |= lalloc(l, (size_t)B, &l->r_pending);
-    rc |= lalloc(l, (size_t)1, &l->r_npend);
+    rc |= lalloc(l, (size_t)B + 2, &l->r_npend);      // [instances parked by a launch, next ticket, done[B]]
     if (rc) { rtmpc_loop_destroy(l); return -1; }
     if (cudaMallocHost(&l->h_npend, sizeof(int)) != cudaSuccess) { rtmpc_loop_destroy(l); return fail("cudaMallocHost"); }
     *out = l;
@@ -616,14 +616,14 @@ int rtmpc_loop_rollout(rtmpc_loop* l, rtmpc_qp* q, rtmpc_qp* q1, int32_t T, cons
     a.seed = seed; a.id_offset = id_offset; a.traj = d_traj_x; a.traj_stride = traj_stride;
     a.warm = l->r_warm; a.warm1 = l->r_warm1; a.two = q1 ? 1 : 0;
     a.U = l->r_U; a.z = l->r_z; a.z_stride = l->r_z_stride; a.status = l->r_status; a.iters = l->r_iters;
-    a.inst_t = l->r_inst_t; a.pending = l->r_pending; a.ref_pending = l->r_ref; a.n_pending = l->r_npend;
+    a.inst_t = l->r_inst_t; a.pending = l->r_pending; a.ref_pending = l->r_ref; a.n_pending = l->r_npend; a.next = l->r_npend + 1; a.done = l->r_npend + 2; a.quantum = 0;
     a.stats = reinterpret_cast<unsigned long long*>(d_stats);
     // every instance starts at the loop's common time
     std::vector<int> t0(B, l->t);
     CU(cudaMemcpyAsync(l->r_inst_t, t0.data(), B * sizeof(int), cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(l->r_pending, 0, B * sizeof(int), s));
     for (int round = 0;; ++round) {
-        CU(cudaMemsetAsync(l->r_npend, 0, sizeof(int), s));
+        CU(cudaMemsetAsync(l->r_npend, 0, ((size_t)B + 2) * sizeof(int), s));
         CU(rollout_launch(P, P1, l->dev, q->as_wpb, q->num_sms, max_smem, a, s));
         g_launches.fetch_add(1);
         CU(cudaMemcpyAsync(l->h_npend, l->r_npend, sizeof(int), cudaMemcpyDeviceToHost, s));

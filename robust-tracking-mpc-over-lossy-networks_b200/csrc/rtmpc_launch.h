@@ -62,6 +62,11 @@ struct RolloutArgs {
     int *inst_t, *pending;        // [B] per-instance time; 1 = current step solved by the interior-point kernel
     double* ref_pending;          // [B * nx] reference of the step a parked instance waits at
     int* n_pending;               // instances parked by this launch
+    // time slicing: a ticket is (instance, chunk of `quantum` control steps); warps draw tickets from `next`, a ticket
+    // waits for its instance's previous one through `done` (both zeroed before every launch).  quantum <= 0: whole rollouts
+    int* next;
+    int* done;
+    int quantum;
     unsigned long long* stats;    // [8] status counts[4], IPM iterations, active-set steps, rounds, flops (or NULL)
 };
 bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err);

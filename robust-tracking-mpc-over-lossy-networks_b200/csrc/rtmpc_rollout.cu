@@ -8,6 +8,8 @@
 // An instance whose solve has to be handed to the interior-point kernel parks itself (inst_t, pending,
 // ref_pending); the host runs that kernel on the parked instances and relaunches, which resumes them.
 #include "rtmpc_as.cuh"
+#include <cstdlib>
+
 #include "rtmpc_launch.h"
 #include "rtmpc_loop.cuh"
 
@@ -26,6 +28,12 @@ __host__ __device__ inline int rollout_warp_doubles(const QPDev& P0, const QPDev
 
 // P0: the controller's problem; P1: the "packet received" problem of ExtendedTubeTrackingMPC, chosen per step and
 // instance on gamma_{t-1} (TubeTrackingMPC.py:307-349); P1 == P0 for the single-problem controllers.
+__device__ __forceinline__ int rollout_take_next(int* next, int lane) {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(next, 1);
+    return __shfl_sync(RTMPC_FULL_MASK, v, 0);
+}
+
 template <int R2, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
@@ -46,48 +54,67 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
     double* scratch = wbase + rollout_fixed_doubles(P0, P1, two);
     const bool ext = L.actuator == RTMPC_ACT_EXTENDED;
 
+    // Time slicing.  An instance is a chain of T dependent steps, so B chains on S warp slots take ceil(B / S) chain
+    // lengths when every warp keeps its chain to the end (4096 chains on 2368 slots: 2, with the slots of the second round
+    // 73 % used).  Instead a warp runs a chain for `quantum` steps, puts its state back and draws the next ticket
+    // (instance, chunk) from a global counter; all slots stay busy until the work runs out (1.73 chain lengths).  A ticket
+    // waits for the previous ticket of its instance (`done`), which an earlier draw - a warp that is running - holds.
+    // State written by one SM is read by another: these loads go to L2 (__ldcg), the hand-over is fence + flag.
+    const int Q = a.quantum;
+    const int nchunks = Q > 0 ? (a.T - a.t0 + Q - 1) / Q : 1;
+    const long long ntickets = (long long)a.B * nchunks;
+    const int first_wave = gridDim.x * wpb;       // the first tickets are dealt statically: consecutive instances on different SMs
 #pragma unroll 1
-    // consecutive instances go to different SMs, so a last partial round is spread over all of them
-    for (int inst = warp * gridDim.x + blockIdx.x; inst < a.B; inst += gridDim.x * wpb) {
-        int t = a.inst_t[inst];
-        if (t >= a.T) continue;
-        bool have = a.pending[inst] != 0;       // this step was solved by the interior-point kernel
+    for (long long ticket = warp * gridDim.x + blockIdx.x; ticket < ntickets;
+         ticket = (long long)first_wave + rollout_take_next(a.next, lane)) {
+        const int inst = (int)(ticket % a.B), chunk = (int)(ticket / a.B);
+        if (chunk > 0) {
+            if (lane == 0) while (*reinterpret_cast<volatile int*>(a.done + inst) < chunk) __nanosleep(128);
+            __syncwarp();
+            __threadfence();
+        }
+        int t = __ldcg(a.inst_t + inst);
+        const int t_stop = Q > 0 ? min(a.T, a.t0 + (chunk + 1) * Q) : a.T;
+        bool have = __ldcg(a.pending + inst) != 0;       // this step was solved by the interior-point kernel ...
+        const bool parked = have && __ldcg(a.status + inst) <= RTMPC_FALLBACK;     // ... or is still waiting for it
+        if (t < t_stop && !parked) {
         unsigned n_status[4] = {0, 0, 0, 0}, n_ipm = 0, n_steps = 0, n_rounds = 0;
         unsigned long long n_flops = 0;
         double* traj_b = a.traj ? a.traj + (size_t)inst * a.traj_stride : nullptr;
         const double p = a.p_loss ? a.p_loss[inst] : 0.0;
         // ---- state, payload and warm-start records move on chip for the whole rollout -------------------
         if (lane < nx) {
-            S.x(lane) = L.x[(size_t)inst * nx + lane];
-            S.x_nom(lane) = L.x_nom[(size_t)inst * nx + lane];
-            S.x_hat(lane) = L.x_hat[(size_t)inst * nx + lane];
+            S.x(lane) = __ldcg(L.x + (size_t)inst * nx + lane);
+            S.x_nom(lane) = __ldcg(L.x_nom + (size_t)inst * nx + lane);
+            S.x_hat(lane) = __ldcg(L.x_hat + (size_t)inst * nx + lane);
             // x_nom_0 of a step the interior-point kernel solved: that kernel wrote z with its problem's own stride
-            const int zs = (two && L.gamma_last[inst] == 1) ? P1.nz : P0.nz;
-            x0_s[lane] = (have && ext) ? a.z[(size_t)inst * zs + lane] : 0.0;
+            const int zs = (two && __ldcg(L.gamma_last + inst) == 1) ? P1.nz : P0.nz;
+            x0_s[lane] = (have && ext) ? __ldcg(a.z + (size_t)inst * zs + lane) : 0.0;
         }
-        if (lane < nu) S.u_last(lane) = L.u_last[(size_t)inst * nu + lane];
+        if (lane < nu) S.u_last(lane) = __ldcg(L.u_last + (size_t)inst * nu + lane);
         for (int i = lane; i < usz; i += 32) {
-            S.buf()[i] = L.buf[(size_t)inst * usz + i];
-            U_s[i] = a.U[(size_t)inst * usz + i];
+            S.buf()[i] = __ldcg(L.buf + (size_t)inst * usz + i);
+            U_s[i] = __ldcg(a.U + (size_t)inst * usz + i);
         }
-        for (int i = lane; i < P0.npad + 1; i += 32) warm0_s[i] = a.warm[(size_t)inst * (P0.npad + 1) + i];
-        if (two) for (int i = lane; i < P1.npad + 1; i += 32) warm1_s[i] = a.warm1[(size_t)inst * (P1.npad + 1) + i];
+        for (int i = lane; i < P0.npad + 1; i += 32) warm0_s[i] = __ldcg(a.warm + (size_t)inst * (P0.npad + 1) + i);
+        if (two) for (int i = lane; i < P1.npad + 1; i += 32) warm1_s[i] = __ldcg(a.warm1 + (size_t)inst * (P1.npad + 1) + i);
         if (lane == 0) {
-            S.err_acc() = L.err_acc[inst]; S.tube_max() = L.tube_max[inst];
-            S.q_t() = L.q_t[inst]; S.s_t() = L.s_t[inst]; S.Theta() = L.Theta[inst]; S.alive() = L.alive[inst];
-            S.last_loss() = L.last_loss[inst]; S.gamma_last() = L.gamma_last[inst];
+            S.err_acc() = __ldcg(L.err_acc + inst); S.tube_max() = __ldcg(L.tube_max + inst);
+            S.q_t() = __ldcg(L.q_t + inst); S.s_t() = __ldcg(L.s_t + inst); S.Theta() = __ldcg(L.Theta + inst);
+            S.alive() = __ldcg(L.alive + inst);
+            S.last_loss() = __ldcg(L.last_loss + inst); S.gamma_last() = __ldcg(L.gamma_last + inst);
         }
         __syncwarp();
 #pragma unroll 1
-        for (; t < a.T; ++t) {
+        for (; t < t_stop; ++t) {
             if (!S.alive()) { t = a.T; break; }
             const int k = t - a.t0;
             const double* ref_t = a.ref ? a.ref + (size_t)k * a.ref_stride_t + (size_t)inst * a.ref_stride_b : nullptr;
             int status;
             if (have) {
                 have = false;
-                status = a.status[inst];
-                const int it = a.iters[inst];
+                status = __ldcg(a.status + inst);
+                const int it = __ldcg(a.iters + inst);
                 n_ipm += it & 0xFFF;
                 n_rounds += (it >> 24) & 0xF;
                 if (lane == 0) a.pending[inst] = 0;
@@ -156,7 +183,11 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
                 if (n_flops) atomicAdd(a.stats + 7, n_flops);
             }
         }
+        }   // (ticket had work)
+        // hand the instance on: everything this warp wrote is visible before the flag moves
+        __threadfence();
         __syncwarp();
+        if (Q > 0 && lane == 0) *reinterpret_cast<volatile int*>(a.done + inst) = chunk + 1;
     }
 }
 
@@ -187,9 +218,20 @@ cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, in
     const size_t per_warp = (size_t)rollout_warp_doubles(P, P1, a.two != 0) * sizeof(double);
     while (wpb > 1 && per_warp * wpb > (size_t)max_smem) --wpb;
     int warps = balanced_warps(a.B, num_sms, wpb);
+    RolloutArgs b = a;
+    // more chains than warp slots: slice them (see the kernel) and use every slot
+    static const int env_q = getenv("RTMPC_RO_QUANTUM") ? atoi(getenv("RTMPC_RO_QUANTUM")) : 25;
+    if (env_q > 0 && (long long)a.B > (long long)num_sms * wpb && a.T - a.t0 >= 2 * env_q) {
+        b.quantum = env_q;
+        warps = wpb;
+    }
+    if (const char* e = getenv("RTMPC_RO_WARPS")) {            // tuning knob: warps per block of the rollout kernel
+        const int v = atoi(e);
+        if (v >= 1 && v <= wpb) warps = v;
+    }
     int blocks = (a.B + warps - 1) / warps;
     if (blocks > num_sms) blocks = num_sms;
-    kc->fn<<<blocks, warps * 32, per_warp * warps, stream>>>(P, P1, L, a);
+    kc->fn<<<blocks, warps * 32, per_warp * warps, stream>>>(P, P1, L, b);
     return cudaGetLastError();
 }
 
