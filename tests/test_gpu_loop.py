@@ -307,3 +307,39 @@ def test_full_size_baseline_config_properties():
         else:
             _, e, h = oq.params(x, bench.REF)
             assert not rq.is_feasible(oq.E, e, oq.G, h)
+
+
+@pytest.mark.parametrize("kind,step_cap", [("tube", 0), ("extended", 0), ("tube", 2)])
+def test_time_sliced_rollout_is_bit_identical_to_whole_chains(kind, step_cap):
+    """More instances than warp slots: the rollout kernel slices the chains into 25-step tickets handed between warps
+    (and SMs).  The same instances run as small batches (fewer instances than slots: every warp keeps its chain) must
+    give the same bits - also for the two-problem variant and with instances parked for the interior-point kernel."""
+    import bench
+    from rtmpc_b200.rollout import RemoteLoop
+    s = H.load("sets_cp.npz")
+    mpc, Z = bench.build_controller(extended=(kind == "extended"))
+    B, T = 3072, 60                       # 148 SMs x 16 warps = 2368 slots < 3072; 60 steps = three tickets per chain
+    p = np.array([0.1 * (i % 10) for i in range(B)])
+    mpc._prob.set_step_cap(step_cap)
+    try:
+        big = RemoteLoop(mpc, B, kind=kind, w_half=bench.HW, Z=Z)
+        big.reset()
+        tr = big.run(T, bench.REF, p_loss=p, seed=11, record=True).cpu().numpy()
+        st_big = big.stats.cpu().numpy()
+        xh, sT = big.x_hat.cpu().numpy(), big.s_t.cpu().numpy()
+        if step_cap:
+            assert st_big[4] > 0                                     # interior-point iterations: instances did park
+        parts, stats = [], np.zeros(4, np.int64)
+        for off in range(0, B, 1024):
+            sub = RemoteLoop(mpc, 1024, kind=kind, w_half=bench.HW, Z=Z)
+            sub.reset()
+            parts.append((sub.run(T, bench.REF, p_loss=p[off:off + 1024], seed=11, id_offset=off, record=True).cpu().numpy(),
+                          sub.x_hat.cpu().numpy(), sub.s_t.cpu().numpy()))
+            stats += sub.stats.cpu().numpy()[:4].astype(np.int64)
+        assert np.array_equal(tr, np.concatenate([q[0] for q in parts]))
+        assert np.array_equal(xh, np.concatenate([q[1] for q in parts]))
+        assert np.array_equal(sT, np.concatenate([q[2] for q in parts]))
+        assert np.array_equal(st_big[:4].astype(np.int64), stats)
+        assert st_big[:4].sum() == B * T or kind == "extended"
+    finally:
+        mpc._prob.set_step_cap(0)
