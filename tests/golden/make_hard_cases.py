@@ -9,6 +9,10 @@ interior-point accurate (the flat Hessian turns a 1e-9 relative residual into ~1
 an independent KKT check instead:
 
     python tests/golden/make_hard_cases.py gpurun_out/nonoptimal.npy        # -> tests/golden/hard_cp.npz
+
+(The committed fixture was made from a capture with the kernel as of commit 1d150b7, i.e. before the refactorise-and-restart
+safeguard existed; with today's kernel the capture tool finds next to nothing, which is the point.  The fixture's content
+does not depend on the kernel: states, references and the ORACLE's solutions.)
 """
 import os
 import sys
