@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTMPC_ABI_VERSION 2
+#define RTMPC_ABI_VERSION 3
 
 /* per-instance solver status (replaces cvxpy's `prob.status` string, TubeTrackingMPC.py:185) */
 #define RTMPC_OPTIMAL            0   /* KKT-certified active-set point                          */
@@ -89,6 +89,24 @@ const char* rtmpc_last_error(void);                 /* thread-local text of the 
 int         rtmpc_device_count(void);
 int         rtmpc_set_device(int device);
 
+/*
+ * Launch tuning, process-wide (nothing is read from the environment; results never depend on these, only speed):
+ *   RTMPC_TUNE_ROLLOUT_QUANTUM  control steps a warp runs one closed loop for before it hands the loop's state on and
+ *                               draws the next (instance, chunk) ticket (rtmpc_loop_rollout; default 25).  0: every warp
+ *                               keeps its instance for the whole rollout.  Time slicing needs all thread blocks of the
+ *                               launch resident at once: the library launches it cooperatively and falls back to 0 by
+ *                               itself when the device / context cannot guarantee that (SM-limited MPS, green contexts).
+ *   RTMPC_TUNE_ROLLOUT_WARPS    warps per thread block of the rollout kernel (0: automatic)
+ *   RTMPC_TUNE_AS_WARPS         upper bound on the warps per thread block of the active-set kernel of rtmpc_qp_solve
+ *                               (0: automatic)
+ * A negative value restores the default.  rtmpc_get_tuning returns the value in force (-1: unknown knob).
+ */
+#define RTMPC_TUNE_ROLLOUT_QUANTUM 0
+#define RTMPC_TUNE_ROLLOUT_WARPS   1
+#define RTMPC_TUNE_AS_WARPS        2
+int     rtmpc_set_tuning(int32_t knob, int32_t value);
+int32_t rtmpc_get_tuning(int32_t knob);
+
 /* QP object: replaces `generate_optimization_problem` (TubeTrackingMPC.py:104-156 and siblings) */
 int  rtmpc_qp_create(const rtmpc_qp_desc* desc, rtmpc_qp** out);
 void rtmpc_qp_destroy(rtmpc_qp* qp);
@@ -109,7 +127,9 @@ void rtmpc_qp_destroy(rtmpc_qp* qp);
  *   d_z      [B*nz]        un-condensed solution [x_0..x_N | u_0..u_{N-1} | x_bar | u_bar], or NULL
  *   d_U_t    [B*(N+1)*nu]  packet payload, time-major: U_t[b][k][:] ; last column u_bar + K x_bar
  *                          (only u_0..u_{N-1} are written when the variant has no steady state)
- *   d_status [B] (may be NULL)
+ *   d_status [B] (may be NULL).  With d_sel, entries of unselected instances are left as they are, except that a
+ *            stale value <= RTMPC_FALLBACK_STATUS (uninitialised memory) is replaced by -1: the hand-over to the
+ *            interior-point kernel goes through this array
  *   d_iters  [B] (may be NULL): bits 0-11 interior-point iterations, bits 12-23 active-set steps
  *            (rows added + rows dropped), bits 24-27 certification / endgame rounds (saturating), bits 28-30
  *            diagnostics: why the active-set kernel last refactorised or gave up (0 = it never did)
@@ -171,8 +191,12 @@ int  rtmpc_loop_create(const rtmpc_loop_desc* desc, int32_t B, rtmpc_loop** out)
 void rtmpc_loop_destroy(rtmpc_loop* loop);
 
 /* (re)initialise all B instances: x = x_nom = x_hat = x0[b], t = 0, q_t = s_t = 0
- * (constructors of SmartActuator.py:13-24,129-144 and Estimator.py:11-26). h_x0 is [B*nx] on the host. */
+ * (constructors of SmartActuator.py:13-24,129-144 and Estimator.py:11-26).
+ * rtmpc_loop_reset:        h_x0 is [B*nx] on the HOST; returns when the state is in place (waits for the default stream
+ *                          only, never for the whole device).
+ * rtmpc_loop_reset_device: d_x0 is [B*nx] on the DEVICE (NULL: all zeros); enqueued on `stream`, no synchronisation. */
 int rtmpc_loop_reset(rtmpc_loop* loop, const double* h_x0);
+int rtmpc_loop_reset_device(rtmpc_loop* loop, const double* d_x0, void* stream);
 
 /* device views of the per-instance state, for the host classes and the tests */
 double*  rtmpc_loop_x(rtmpc_loop* loop);        /* [B*nx] plant state                            */
@@ -227,7 +251,9 @@ int rtmpc_loop_step(rtmpc_loop* loop, const double* d_U_t, const int32_t* d_stat
  *   d_stats  [8] uint64 or NULL, accumulated: solves by status [4], interior-point iterations,
  *            active-set steps, certification rounds, algorithmic flops of the active-set method
  * Instances the active-set method hands over are solved by the interior-point kernel between
- * relaunches; the call synchronises `stream` before it returns.
+ * relaunches; the call synchronises `stream` before it returns (it has to read how many instances were handed over;
+ * nothing else is staged through the host).  With more instances than resident warps the loops are time-sliced
+ * (RTMPC_TUNE_ROLLOUT_QUANTUM above); results are identical either way.
  */
 int rtmpc_loop_rollout(rtmpc_loop* loop, rtmpc_qp* qp, rtmpc_qp* qp_received, int32_t T, const double* d_ref, int64_t ref_stride_t,
                        int64_t ref_stride_b, const int32_t* d_theta, const int32_t* d_gamma, const double* d_w,

@@ -1,6 +1,4 @@
 // Instantiations and launcher of the dual active-set kernel (main path of the QP solve).
-#include <cstdlib>
-
 #include "rtmpc_as.cuh"
 #include "rtmpc_launch.h"
 
@@ -15,9 +13,9 @@ static const AsChoice kAs[] = {
     {12, 16, as_solve_kernel<12, 16>}, {16, 16, as_solve_kernel<16, 16>},
 };
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
+Tuning& tuning() {
+    static Tuning t;
+    return t;
 }
 
 static const AsChoice* pick(int mpad) {
@@ -41,8 +39,6 @@ bool as_configure(const QPDev& P, int max_smem, int* wpb_out, size_t* smem_out, 
     const size_t per_warp = (size_t)as_warp_doubles(P) * sizeof(double);
     int wpb = (int)((size_t)max_smem / per_warp);
     if (wpb > kc->maxw) wpb = kc->maxw;
-    // tuning knob: fewer resident warps per SM (more L1 per warp); used by tools/gpu_as_knobs.py
-    if (env_int("RTMPC_AS_WPB", 0) > 0 && env_int("RTMPC_AS_WPB", 0) < wpb) wpb = env_int("RTMPC_AS_WPB", 0);
     if (wpb < 1) return false;
     *err = cudaFuncSetAttribute((const void*)kc->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     *wpb_out = wpb;
@@ -53,6 +49,7 @@ bool as_configure(const QPDev& P, int max_smem, int* wpb_out, size_t* smem_out, 
 cudaError_t as_launch(const QPDev& P, int wpb, size_t smem, int num_sms, const QPLaunch& a) {
     const AsChoice* kc = pick(P.mpad);
     // spread the instances over all SMs first, then fill the warps of each CTA
+    if (tuning().as_warps > 0 && tuning().as_warps < wpb) wpb = tuning().as_warps;   // RTMPC_TUNE_AS_WARPS
     int warps = balanced_warps(a.B, num_sms, wpb);
     int blocks = (a.B + warps - 1) / warps;
     if (blocks > num_sms) blocks = num_sms;

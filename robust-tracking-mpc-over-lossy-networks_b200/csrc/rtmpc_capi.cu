@@ -66,6 +66,21 @@ static int upload(rtmpc_qp* q, const T* src, size_t count, const T** dst) {
     return 0;
 }
 
+// An unselected instance whose status slot happens to hold the transient hand-over mark (stale or uninitialised caller
+// memory) must not be picked up by the interior-point launch that follows the active-set launch.
+__global__ void clear_stale_handover_kernel(int B, const int* __restrict__ sel, int sel_value, int* __restrict__ status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && sel[b] != sel_value && status[b] <= RTMPC_FALLBACK_STATUS) status[b] = -1;
+}
+
+// start of a rollout: every instance at the loop's common time, nothing pending, counters / ticket flags cleared
+__global__ void rollout_prepare_kernel(int B, int t, int* __restrict__ inst_t, int* __restrict__ pending,
+                                       int* __restrict__ npend) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) { inst_t[b] = t; pending[b] = 0; npend[2 + b] = 0; }
+    if (b < 2) npend[b] = 0;
+}
+
 extern "C" {
 
 int rtmpc_abi_version(void) { return RTMPC_ABI_VERSION; }
@@ -80,6 +95,25 @@ int rtmpc_device_count(void) {
 int rtmpc_set_device(int device) {
     CU(cudaSetDevice(device));
     return 0;
+}
+
+int rtmpc_set_tuning(int32_t knob, int32_t value) {
+    Tuning& t = tuning();
+    switch (knob) {
+        case RTMPC_TUNE_ROLLOUT_QUANTUM: t.rollout_quantum = value < 0 ? 25 : value; return 0;
+        case RTMPC_TUNE_ROLLOUT_WARPS: t.rollout_warps = value < 0 ? 0 : value; return 0;
+        case RTMPC_TUNE_AS_WARPS: t.as_warps = value < 0 ? 0 : value; return 0;
+        default: return fail("rtmpc_set_tuning: unknown knob");
+    }
+}
+int32_t rtmpc_get_tuning(int32_t knob) {
+    const Tuning& t = tuning();
+    switch (knob) {
+        case RTMPC_TUNE_ROLLOUT_QUANTUM: return t.rollout_quantum;
+        case RTMPC_TUNE_ROLLOUT_WARPS: return t.rollout_warps;
+        case RTMPC_TUNE_AS_WARPS: return t.as_warps;
+        default: return -1;
+    }
 }
 
 int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
@@ -99,8 +133,11 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
     if (mpad < 0) return fail("rtmpc_qp_create: too many rows for the compiled kernel set (mpad <= 1024)");
     if (d->nss > 0 && !d->Kss) return fail("rtmpc_qp_create: Kss required when nss > 0");
     rtmpc_qp* q = new rtmpc_qp();
-    CU(cudaGetDevice(&q->device));
-    CU(cudaDeviceGetAttribute(&q->num_sms, cudaDevAttrMultiProcessorCount, q->device));
+    {
+        cudaError_t e0 = cudaGetDevice(&q->device);
+        if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&q->num_sms, cudaDevAttrMultiProcessorCount, q->device);
+        if (e0 != cudaSuccess) { delete q; return fail("rtmpc_qp_create: no usable CUDA device", e0); }
+    }
     QPDev& P = q->dev;
     std::memset(&P, 0, sizeof(P));
     P.nx = d->nx; P.nu = d->nu; P.N = d->N; P.n = d->n; P.npad = d->npad; P.m = d->m; P.mpad = mpad;
@@ -248,7 +285,10 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
     if (P.nss > 0 && !P.Kss) { rtmpc_qp_destroy(q); return fail("rtmpc_qp_create: Kss required when nss > 0"); }
 
     int max_smem = 0;
-    CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, q->device));
+    if (cudaError_t e1 = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, q->device)) {
+        rtmpc_qp_destroy(q);
+        return fail("rtmpc_qp_create: cudaDeviceGetAttribute", e1);
+    }
     cudaError_t e = cudaSuccess;
     if (!ipm_configure(P, max_smem, &q->ipm_wpb, &q->ipm_smem, &e)) {
         rtmpc_qp_destroy(q);
@@ -323,6 +363,11 @@ int rtmpc_qp_solve(rtmpc_qp* q, int32_t B, const double* d_x_init, const double*
             q->tmp_cap = B;
         }
         a.status = q->s_tmp_status;
+    }
+    if (d_sel) {
+        clear_stale_handover_kernel<<<(B + 255) / 256, 256, 0, a.stream>>>(B, d_sel, sel_value, a.status);
+        g_launches.fetch_add(1);
+        CU(cudaGetLastError());
     }
     CU(as_launch(q->dev, q->as_wpb, q->as_smem, q->num_sms, a));
     // instances the active-set kernel handed over (status RTMPC_FALLBACK); exits at once when there are none
@@ -517,19 +562,37 @@ void rtmpc_loop_destroy(rtmpc_loop* l) {
     delete l;
 }
 
+int rtmpc_loop_reset_device(rtmpc_loop* l, const double* d_x0, void* stream) {
+    if (!l) return fail("rtmpc_loop_reset_device: null handle");
+    if (wrong_device(l->device, "rtmpc_loop_reset_device")) return -1;
+    LoopDev& L = l->dev;
+    const size_t B = l->B, nx = L.nx;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d_x0) CU(cudaMemcpyAsync(L.x, d_x0, B * nx * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    else CU(cudaMemsetAsync(L.x, 0, B * nx * sizeof(double), s));
+    const int threads = 128;
+    loop_reset_kernel<<<(int)((B + threads - 1) / threads), threads, 0, s>>>(L, (int)B, l->r_warm, l->r_warm_stride, l->r_warm1,
+                                                                              l->r_warm1_stride);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    l->t = 0;
+    return 0;
+}
+
 int rtmpc_loop_reset(rtmpc_loop* l, const double* h_x0) {
     if (!l || !h_x0) return fail("rtmpc_loop_reset: null argument");
     if (wrong_device(l->device, "rtmpc_loop_reset")) return -1;
     LoopDev& L = l->dev;
-    const size_t B = l->B, nx = L.nx, nu = L.nu;
+    const size_t B = l->B, nx = L.nx;
+    // host buffer in: the copy is synchronous with respect to the host (pageable memory), the kernel runs on the
+    // default stream and only that stream is waited for - callers may continue on any stream afterwards
     CU(cudaMemcpy(L.x, h_x0, B * nx * sizeof(double), cudaMemcpyHostToDevice));
-    (void)nu;
     const int threads = 128;
     loop_reset_kernel<<<(int)((B + threads - 1) / threads), threads>>>(L, (int)B, l->r_warm, l->r_warm_stride, l->r_warm1,
                                                                         l->r_warm1_stride);
     g_launches.fetch_add(1);
     CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());        // callers may continue on any stream
+    CU(cudaStreamSynchronize(nullptr));
     l->t = 0;
     return 0;
 }
@@ -618,12 +681,12 @@ int rtmpc_loop_rollout(rtmpc_loop* l, rtmpc_qp* q, rtmpc_qp* q1, int32_t T, cons
     a.U = l->r_U; a.z = l->r_z; a.z_stride = l->r_z_stride; a.status = l->r_status; a.iters = l->r_iters;
     a.inst_t = l->r_inst_t; a.pending = l->r_pending; a.ref_pending = l->r_ref; a.n_pending = l->r_npend; a.next = l->r_npend + 1; a.done = l->r_npend + 2; a.quantum = 0;
     a.stats = reinterpret_cast<unsigned long long*>(d_stats);
-    // every instance starts at the loop's common time
-    std::vector<int> t0(B, l->t);
-    CU(cudaMemcpyAsync(l->r_inst_t, t0.data(), B * sizeof(int), cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(l->r_pending, 0, B * sizeof(int), s));
+    // every instance starts at the loop's common time (filled on the device: nothing is staged on the host)
+    rollout_prepare_kernel<<<(int)((B + 255) / 256), 256, 0, s>>>((int)B, l->t, l->r_inst_t, l->r_pending, l->r_npend);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
     for (int round = 0;; ++round) {
-        CU(cudaMemsetAsync(l->r_npend, 0, ((size_t)B + 2) * sizeof(int), s));
+        if (round > 0) CU(cudaMemsetAsync(l->r_npend, 0, ((size_t)B + 2) * sizeof(int), s));
         CU(rollout_launch(P, P1, l->dev, q->as_wpb, q->num_sms, max_smem, a, s));
         g_launches.fetch_add(1);
         CU(cudaMemcpyAsync(l->h_npend, l->r_npend, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -33,6 +33,14 @@ inline int balanced_warps(int B, int num_sms, int wpb) {
     return best;
 }
 
+// Process-wide launch tuning (rtmpc_set_tuning, include/rtmpc.h); never read from the environment.
+struct Tuning {
+    int rollout_quantum = 25;   // control steps per ticket of the time-sliced rollout; 0: whole chains per warp
+    int rollout_warps = 0;      // warps per CTA of the rollout kernel; 0: automatic
+    int as_warps = 0;           // cap on the warps per CTA of the active-set solve kernel; 0: automatic
+};
+Tuning& tuning();
+
 // interior-point kernel: picks the instantiation for (n, mpad); returns false if none fits
 bool ipm_configure(const QPDev& P, int max_smem, int* wpb, size_t* smem, cudaError_t* err);
 cudaError_t ipm_launch(const QPDev& P, int wpb, size_t smem, int num_sms, const QPLaunch& a);

@@ -8,7 +8,7 @@
 //   RobustEstimator.update_estimate                                                      Estimator.py:113-156
 //   plant step x+ = A x + B u + w                                                        Results/results_linear_system.py:248
 // O(1) equivalents of the reference's O(t) bookkeeping (checked against the literal restatement
-// in oracle/ref_loop.py by tests/test_loop_*.py):
+// in oracle/ref_loop.py by tests/test_oracle_loop.py and, on the reference's own sequences, tests/test_reference_pin.py):
 //   * Theta_t = theta_t * prod(theta[q_t+1 .. t])  ==  theta_t && (last lost step <= q_t)
 //   * the estimator's `controlSequences[s_t]` is by construction the actuator's current buffer.
 #pragma once
@@ -663,6 +663,12 @@ __global__ void estimator_update_kernel(EstArgs e, int B) {
     double base[LOOP_MAX_NX], uh[LOOP_MAX_NU];
     if (e.gamma[b] == 1) {
         const int s_t = e.pkt_s[b];
+        if (s_t < 0 || s_t >= e.n_hist) {
+            // the packet names a sequence that was never stored (Estimator.py:55 would raise IndexError): poison the
+            // estimate instead of reading out of bounds
+            for (int i = 0; i < nx; ++i) e.x_hat[(size_t)b * nx + i] = __longlong_as_double(0x7ff8000000000000LL);
+            return;
+        }
         const double* sq = e.hist + ((size_t)s_t * B + b) * seq;
         const int kk = e.t - s_t;
         for (int k = 0; k < nx; ++k) base[k] = e.pkt_x[(size_t)b * nx + k];

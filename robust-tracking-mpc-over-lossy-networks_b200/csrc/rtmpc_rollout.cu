@@ -8,7 +8,6 @@
 // An instance whose solve has to be handed to the interior-point kernel parks itself (inst_t, pending,
 // ref_pending); the host runs that kernel on the parked instances and relaunches, which resumes them.
 #include "rtmpc_as.cuh"
-#include <cstdlib>
 
 #include "rtmpc_launch.h"
 #include "rtmpc_loop.cuh"
@@ -211,6 +210,11 @@ bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err) {
     return *err == cudaSuccess;
 }
 
+// Time slicing makes warps wait for tickets held by warps of OTHER CTAs, which is only safe when every CTA of the grid
+// is resident at the same time.  The sliced launch is therefore a cooperative launch (the runtime refuses it instead of
+// letting it hang when the grid cannot be co-resident: SM-limited MPS / green contexts) with the grid clamped to what
+// the occupancy calculator says fits; when the device or context cannot give that guarantee the rollout runs with
+// whole chains per warp (quantum 0: no cross-CTA waits, same results bit for bit).
 cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, int wpb, int num_sms, int max_smem,
                            const RolloutArgs& a, cudaStream_t stream) {
     const RoChoice* kc = pick(P.mpad);
@@ -219,18 +223,38 @@ cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, in
     while (wpb > 1 && per_warp * wpb > (size_t)max_smem) --wpb;
     int warps = balanced_warps(a.B, num_sms, wpb);
     RolloutArgs b = a;
+    const Tuning& tn = tuning();
     // more chains than warp slots: slice them (see the kernel) and use every slot
-    static const int env_q = getenv("RTMPC_RO_QUANTUM") ? atoi(getenv("RTMPC_RO_QUANTUM")) : 25;
-    if (env_q > 0 && (long long)a.B > (long long)num_sms * wpb && a.T - a.t0 >= 2 * env_q) {
-        b.quantum = env_q;
-        warps = wpb;
-    }
-    if (const char* e = getenv("RTMPC_RO_WARPS")) {            // tuning knob: warps per block of the rollout kernel
-        const int v = atoi(e);
-        if (v >= 1 && v <= wpb) warps = v;
-    }
+    const int q = tn.rollout_quantum;
+    bool sliced = q > 0 && (long long)a.B > (long long)num_sms * wpb && a.T - a.t0 >= 2 * q;
+    if (sliced) warps = wpb;
+    if (tn.rollout_warps >= 1 && tn.rollout_warps <= wpb) warps = tn.rollout_warps;      // RTMPC_TUNE_ROLLOUT_WARPS
     int blocks = (a.B + warps - 1) / warps;
     if (blocks > num_sms) blocks = num_sms;
+    const size_t smem = per_warp * warps;
+    if (sliced) {
+        int dev = 0, coop = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kc->fn, warps * 32, smem);
+        if (e != cudaSuccess) return e;
+        const long long fit = (long long)per_sm * num_sms;
+        if (coop && fit >= 1) {
+            if (blocks > fit) blocks = (int)fit;
+            b.quantum = q;
+            QPDev p0 = P, p1 = P1;
+            LoopDev ld = L;
+            void* args[] = {&p0, &p1, &ld, &b};
+            e = cudaLaunchCooperativeKernel((const void*)kc->fn, dim3(blocks), dim3(warps * 32), args, smem, stream);
+            if (e == cudaSuccess) return cudaGetLastError();
+            if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorNotSupported) return e;
+            (void)cudaGetLastError();            // co-residency refused: fall through to whole chains
+        }
+        b.quantum = 0;
+        warps = balanced_warps(a.B, num_sms, wpb);
+        blocks = (a.B + warps - 1) / warps;
+        if (blocks > num_sms) blocks = num_sms;
+    }
     kc->fn<<<blocks, warps * 32, per_warp * warps, stream>>>(P, P1, L, b);
     return cudaGetLastError();
 }

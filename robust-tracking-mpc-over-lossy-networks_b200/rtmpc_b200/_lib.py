@@ -14,10 +14,10 @@ LIB_PATH = os.path.join(_HERE, "librtmpc_b200.so")
 
 # every symbol include/rtmpc.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "rtmpc_abi_version", "rtmpc_last_error", "rtmpc_device_count", "rtmpc_set_device",
+    "rtmpc_abi_version", "rtmpc_last_error", "rtmpc_device_count", "rtmpc_set_device", "rtmpc_set_tuning", "rtmpc_get_tuning",
     "rtmpc_qp_create", "rtmpc_qp_destroy", "rtmpc_qp_solve", "rtmpc_qp_solve_host", "rtmpc_launch_count",
     "rtmpc_qp_warm_stride", "rtmpc_qp_rows", "rtmpc_qp_warm_reset", "rtmpc_qp_set_method", "rtmpc_qp_set_work_counter", "rtmpc_qp_set_step_cap",
-    "rtmpc_loop_create", "rtmpc_loop_destroy", "rtmpc_loop_reset", "rtmpc_loop_x", "rtmpc_loop_x_nom",
+    "rtmpc_loop_create", "rtmpc_loop_destroy", "rtmpc_loop_reset", "rtmpc_loop_reset_device", "rtmpc_loop_x", "rtmpc_loop_x_nom",
     "rtmpc_loop_x_hat", "rtmpc_loop_q_t", "rtmpc_loop_s_t", "rtmpc_loop_Theta", "rtmpc_loop_alive",
     "rtmpc_loop_err_acc", "rtmpc_loop_tube_max", "rtmpc_loop_u", "rtmpc_loop_gamma", "rtmpc_loop_time",
     "rtmpc_loop_step", "rtmpc_loop_rollout",
@@ -27,7 +27,8 @@ EXPORTS = [
 
 OPTIMAL, MAX_ITER, INFEASIBLE, OPTIMAL_INACCURATE = 0, 1, 2, 3
 METHOD_ACTIVE_SET, METHOD_INTERIOR_POINT = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
+TUNE_ROLLOUT_QUANTUM, TUNE_ROLLOUT_WARPS, TUNE_AS_WARPS = 0, 1, 2
 ACT_SMART, ACT_CONSISTENT, ACT_EXTENDED = 0, 1, 2
 PLANT_LINEAR, PLANT_CARTPOLE = 0, 1
 
@@ -74,6 +75,9 @@ def lib():
     L.rtmpc_last_error.restype = C.c_char_p
     L.rtmpc_device_count.restype = C.c_int
     L.rtmpc_set_device.argtypes = [C.c_int]
+    L.rtmpc_set_tuning.argtypes = [C.c_int32, C.c_int32]
+    L.rtmpc_get_tuning.argtypes = [C.c_int32]
+    L.rtmpc_get_tuning.restype = C.c_int32
     L.rtmpc_qp_create.argtypes = [C.POINTER(QPDesc), C.POINTER(vp)]
     L.rtmpc_qp_destroy.argtypes = [vp]
     L.rtmpc_qp_destroy.restype = None
@@ -92,6 +96,7 @@ def lib():
     L.rtmpc_loop_destroy.argtypes = [vp]
     L.rtmpc_loop_destroy.restype = None
     L.rtmpc_loop_reset.argtypes = [vp, vp]
+    L.rtmpc_loop_reset_device.argtypes = [vp, vp, vp]
     for name in ("x", "x_nom", "x_hat", "q_t", "s_t", "Theta", "alive", "err_acc", "tube_max", "u", "gamma"):
         f = getattr(L, "rtmpc_loop_" + name)
         f.argtypes = [vp]
@@ -116,6 +121,16 @@ def lib():
 def check(rc, what=""):
     if rc != 0:
         raise RtmpcError(f"{what} failed: {lib().rtmpc_last_error().decode()}")
+
+
+def set_tuning(knob, value):
+    """Process-wide launch tuning (``rtmpc_set_tuning``): ``knob`` one of TUNE_ROLLOUT_QUANTUM / TUNE_ROLLOUT_WARPS /
+    TUNE_AS_WARPS; a negative value restores the default.  Results never depend on it."""
+    check(lib().rtmpc_set_tuning(int(knob), int(value)), "rtmpc_set_tuning")
+
+
+def get_tuning(knob):
+    return int(lib().rtmpc_get_tuning(int(knob)))
 
 
 def require_cuda():

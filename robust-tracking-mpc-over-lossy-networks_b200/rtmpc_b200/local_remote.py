@@ -63,7 +63,7 @@ class SmartActuator:
         else:
             U = U_t
             N = U.shape[1] - 1
-        Ud = U if torch.is_tensor(U) else _t64(U, self._dev)
+        Ud = U.to(self._dev, torch.float64) if torch.is_tensor(U) else _t64(U, self._dev)
         if self._buf is None:
             self._N = N
             self._buf = torch.zeros(self._Bn, N + 1, self._nu, device=self._dev, dtype=torch.float64)
@@ -194,7 +194,7 @@ class Estimator:
         if self._single:
             U = _t64(np.asarray(Ut, float).T.reshape(1, self._N + 1, self._nu), self._dev)
         else:
-            U = Ut if torch.is_tensor(Ut) else _t64(Ut, self._dev)
+            U = Ut.to(self._dev, torch.float64) if torch.is_tensor(Ut) else _t64(Ut, self._dev)
         self._hist[self._n_hist].copy_(U.reshape(self._Bn, self._N + 1, self._nu))
         self._n_hist += 1
 

@@ -76,19 +76,28 @@ class BatchedQP:
         self.rows = int(L.rtmpc_qp_rows(h))          # rows the kernels work on (padded)
         self._Kss = Kss
         self._max_iter = max_iter
+        self._method = "active_set"
+        self._step_cap = 0
 
     def with_rows(self, min_rows):
         """The same problem padded to at least ``min_rows`` rows (two problems one rollout switches between)."""
-        return self if self.rows >= min_rows else BatchedQP(self.spec, Kss=self._Kss, max_iter=self._max_iter, min_rows=min_rows)
+        if self.rows >= min_rows:
+            return self
+        q = BatchedQP(self.spec, Kss=self._Kss, max_iter=self._max_iter, min_rows=min_rows)
+        q.set_method(self._method)          # the handle's settings travel with it
+        q.set_step_cap(self._step_cap)
+        return q
 
     def set_method(self, method):
         """'active_set' (default: dual active-set kernel, interior point as fallback) or 'interior_point'."""
         m = {"active_set": _lib.METHOD_ACTIVE_SET, "interior_point": _lib.METHOD_INTERIOR_POINT}[method]
         _lib.check(self._L.rtmpc_qp_set_method(self._h, m), "rtmpc_qp_set_method")
+        self._method = method
 
     def set_step_cap(self, max_steps):
         """Active-set steps after which an instance goes to the interior-point kernel (<= 0: default)."""
         _lib.check(self._L.rtmpc_qp_set_step_cap(self._h, int(max_steps)), "rtmpc_qp_set_step_cap")
+        self._step_cap = int(max_steps)
 
     def set_work_counter(self, counter):
         """uint64 device tensor (1 element) accumulating the active-set kernel's algorithmic flops, or None."""

@@ -104,10 +104,17 @@ class RemoteLoop:
             self._h = None
 
     def reset(self, x0=None):
-        x0 = np.zeros((self.B, self.nx)) if x0 is None else np.broadcast_to(np.asarray(x0, float).reshape(-1, self.nx),
-                                                                              (self.B, self.nx))
-        x0 = _lib.f64(x0)
-        _lib.check(self.L.rtmpc_loop_reset(self._h, _lib.ptr(x0)), "rtmpc_loop_reset")
+        """x = x_nom = x_hat = x0 ([nx] or [B, nx]; None: zeros), t = 0.  A host array goes through ``rtmpc_loop_reset``
+        (returns when the state is in place); a CUDA tensor or None through ``rtmpc_loop_reset_device`` (enqueued on the
+        current stream, nothing synchronises)."""
+        if x0 is None or torch.is_tensor(x0):
+            if x0 is not None:
+                x0 = x0.to(self.dev, torch.float64).reshape(-1, self.nx).expand(self.B, self.nx).contiguous()
+            _lib.check(self.L.rtmpc_loop_reset_device(self._h, _lib.ptr(x0), torch.cuda.current_stream().cuda_stream),
+                       "rtmpc_loop_reset_device")
+        else:
+            x0 = _lib.f64(np.broadcast_to(np.asarray(x0, float).reshape(-1, self.nx), (self.B, self.nx)))
+            _lib.check(self.L.rtmpc_loop_reset(self._h, _lib.ptr(x0)), "rtmpc_loop_reset")
         self.iters_total.zero_()
         self.status_count.zero_()
         self.stats.zero_()
@@ -136,15 +143,18 @@ class RemoteLoop:
                                         warm=self.warm)
             x_nom0, stride = None, 0
         if stats:
-            self.accumulate_iters()
-            self.status_count += torch.bincount(self.status, minlength=4)[:4]
+            # instances whose controller already returned None take no further steps (loop_step_begin) and are not
+            # counted again - the persistent rollout stops solving them altogether
+            live = self.alive != 0
+            self.accumulate_iters(live)
+            self.status_count += torch.bincount(self.status[live].clamp(min=0), minlength=4)[:4]
         _lib.check(self.L.rtmpc_loop_step(self._h, p(self.U), p(self.status), p(x_nom0), stride, p(ref_d), p(theta),
                                           p(gamma), p(w), p(p_loss), int(seed), int(id_offset), p(traj),
                                           0 if traj is None else traj.shape[1] * traj.shape[2], stream),
                    "rtmpc_loop_step")
 
-    def accumulate_iters(self):
-        it = self.iters
+    def accumulate_iters(self, live=None):
+        it = self.iters if live is None else self.iters[live]
         self.iters_total += torch.stack(((it & 0xFFF).sum(), ((it >> 12) & 0xFFF).sum(), ((it >> 24) & 0xF).sum()))
 
     def run(self, T, ref, p_loss=None, theta=None, gamma=None, w=None, seed=0, id_offset=0, record=False, stats=True,
@@ -173,16 +183,23 @@ class RemoteLoop:
             theta = torch.as_tensor(np.ascontiguousarray(theta), device=self.dev).to(torch.int32).contiguous()
             gamma = torch.as_tensor(np.ascontiguousarray(gamma), device=self.dev).to(torch.int32).contiguous()
             w = None if w is None else torch.as_tensor(np.ascontiguousarray(w), device=self.dev, dtype=f64).contiguous()
-        elif p_loss is not None:
-            p_loss = torch.as_tensor(np.array(np.broadcast_to(p_loss, (self.B,)), dtype=float), device=self.dev, dtype=f64)
         else:
-            p_loss = torch.zeros(self.B, device=self.dev, dtype=f64)
+            p_loss = self._p_loss(p_loss)
         for k in range(T):
             if theta is not None:
                 self.step(ref_d[k], theta[k], gamma[k], None if w is None else w[k], traj=traj, stats=stats)
             else:
                 self.step(ref_d[k], p_loss=p_loss, seed=seed, id_offset=id_offset, traj=traj, stats=stats)
         return traj
+
+    def _p_loss(self, p_loss):
+        """Loss probability per instance as a contiguous FP64 device vector [B] (scalar / host array / tensor of any
+        dtype or device; None: no losses)."""
+        if p_loss is None:
+            return torch.zeros(self.B, device=self.dev, dtype=torch.float64)
+        if not torch.is_tensor(p_loss):
+            p_loss = torch.as_tensor(np.asarray(p_loss, dtype=float))
+        return p_loss.to(self.dev, torch.float64).reshape(-1).expand(self.B).contiguous()
 
     def _run_fused(self, T, ref, p_loss, theta, gamma, w, seed, id_offset, record):
         f64 = torch.float64
@@ -210,11 +227,8 @@ class RemoteLoop:
             gamma = torch.as_tensor(np.ascontiguousarray(gamma), device=self.dev).to(torch.int32).contiguous()
             w = None if w is None else torch.as_tensor(np.ascontiguousarray(w), device=self.dev, dtype=f64).contiguous()
             p_loss = None
-        elif p_loss is not None:
-            if not torch.is_tensor(p_loss):
-                p_loss = torch.as_tensor(np.array(np.broadcast_to(p_loss, (B,)), dtype=float), device=self.dev, dtype=f64)
         else:
-            p_loss = torch.zeros(B, device=self.dev, dtype=f64)
+            p_loss = self._p_loss(p_loss)
         p = _lib.ptr
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(self.L.rtmpc_loop_rollout(self._h, self.mpc._prob._h, recv, int(T), p(ref_d), st, sb, p(theta), p(gamma), p(w),

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_no_cpu_fallback():
     L = _lib.lib()
-    assert L.rtmpc_abi_version() == _lib.ABI_VERSION == 2
+    assert L.rtmpc_abi_version() == _lib.ABI_VERSION == 3
     if L.rtmpc_device_count() <= 0:
         with pytest.raises(_lib.RtmpcError):
             _lib.require_cuda()
