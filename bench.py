@@ -249,6 +249,10 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
+    if args.rollout_warps:
+        _lib.set_tuning(_lib.TUNE_ROLLOUT_WARPS, args.rollout_warps)
+    if args.rollout_quantum >= 0:
+        _lib.set_tuning(_lib.TUNE_ROLLOUT_QUANTUM, args.rollout_quantum)
     wl = WORKLOADS[args.workload]
     SEED = wl["seed"]
     mpc, Z = build_controller(extended=wl["extended"])
@@ -259,7 +263,7 @@ def run_gpu_arm(args):
     ref_d = torch.as_tensor(np.tile(REF, (B, 1)), device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)    # > 126 MB L2
     n, m = mpc._prob.n, mpc._prob.m
-    kernel_name = "rollout_kernel<%d,16>" % ((mpc._prob.rows + 63) // 64)
+    kernel_name = mpc._prob.rollout_kernel           # the instantiation rtmpc_loop_rollout launches (from the library)
     f_it = ipm_flops_per_iteration(n, m)
     stream = torch.cuda.current_stream()
 
@@ -351,6 +355,12 @@ def run_gpu_arm(args):
                       "rtmpc_loop_reset + rtmpc_loop_rollout; trajectories [B,T+1,nx] and tracking errors copied "
                       "back to pinned host memory, wall clock"}
 
+    extra, gather = {}, {}
+    if not args.no_extra:
+        del loop
+        extra = extra_workloads(args, torch, dist, D, RemoteLoop, dev, rank, world, fp64_peak)
+        gather = trajectory_all_gather(torch, dist, D, RemoteLoop, dev, rank, world, mpc, Z, ids0, p_loss, ref_d)
+
     if rank == 0:
         peaks, traffic = {}, None
         try:
@@ -379,7 +389,9 @@ def run_gpu_arm(args):
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA; no tcgen05 kind for f64)", "kernel": kernel_name + " (dual active-set QP + closed-loop step, one warp per instance for all T steps; ipm_solve_kernel on handed-over instances)",
+            "roofline": {"bound": "tensor", "pipe": "fp64 FMA pipe (the QP kernel issues DFMA only - no tensor-core instruction; tcgen05 has no f64 "
+                                                     "kind; 'tensor' = the compute roof of the bench schema, its denominator is a DMMA DGEMM)",
+                         "kernel": kernel_name + " (dual active-set QP + closed-loop step, one warp per instance for all T steps; ipm_solve_kernel on handed-over instances)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure; "
@@ -392,14 +404,144 @@ def run_gpu_arm(args):
                          "mean_active_set_steps_per_solve": float(iters_sum[1]) / solves},
             "cpu_baseline": {"value": cpu_value, "unit": "solves/s", "cores": cores, "kind": "port",
                              "sample": f"{cpu_n} QP solves of the same workload (states of the golden closed-loop runs at "
-                                       "loss 0/0.3/0.6/0.9), oracle IPM + certified polish, one process per core"},
+                                       "loss 0/0.3/0.6/0.9), oracle IPM + certified polish, one process per core",
+                             "same_config": False,
+                             "caveat": "a numpy interior-point port of the reference's QP on sampled states (the reference's cvxpy + "
+                                       "Clarabel stack is not installable offline), not closed loops and not Clarabel: a reported "
+                                       "baseline, not a like-for-like ratio; it does not grow with --gpus"},
             "checks": {"status_counts[optimal,max_iter,infeasible,inaccurate]": status_all.tolist(),
                        "max_tube_violation": tube_max, "mean_tracking_error": float(err_all.mean().item()),
-                       "stats_all_gather_ms": gather_ms},
+                       "stats_all_gather_ms": gather_ms, **gather},
+            "extra_workloads": extra,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def timed_rollouts(torch, D, loop, T, ref_vec, p_loss, seed, ids0, steps, warmup, flush, barrier):
+    """`steps` device-timed rollouts of an already built loop (L2 flushed between them); returns (ms max over ranks, stats)."""
+    stream = torch.cuda.current_stream()
+    for wi in range(warmup):
+        loop.reset()
+        loop.run(T, ref_vec, p_loss=p_loss, seed=seed + 1000 + wi, id_offset=ids0, fused=True)
+    barrier()
+    total_ms, stats = 0.0, np.zeros(8, np.int64)
+    for k in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        loop.reset()
+        e0.record(stream)
+        loop.run(T, ref_vec, p_loss=p_loss, seed=seed + k, id_offset=ids0, fused=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        stats += loop.stats.cpu().numpy().astype(np.int64)
+    barrier()
+    t_ms = float(D.all_reduce_max(torch.tensor([total_ms], device=loop.dev, dtype=torch.float64)).item())
+    stats = D.all_reduce_sum(torch.as_tensor(stats, device=loop.dev)).cpu().numpy()
+    return t_ms, stats
+
+
+def extra_workloads(args, torch, dist, D, RemoteLoop, dev, rank, world, fp64_peak):
+    """BASELINE.json configs[2..4] in the same process, after the headline's timed region (so that the driver's BENCH / SCALE
+    records carry them): c3 = extended variant, 65 536 instances in total split over the ranks (STRONG scaling: total work
+    fixed as N grows); c4 = analytic cartpole plant, 32 768 instances per GPU (configs[3]'s 262 144 on 8 GPUs, weak);
+    c5 = support sweep over 10^6 directions split over the ranks (strong).  Same timing rules as the headline (warm-up,
+    L2 flush, CUDA events, max over ranks), 2 timed steps each."""
+    from rtmpc_b200 import _lib
+    out = {}
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    steps, warmup = 2, 1
+    for name, total, per_gpu, scaling in (("c3", 65536, None, "strong"), ("c4", None, 32768, "weak")):
+        wl = WORKLOADS[name]
+        mpc, Z = build_controller(extended=wl["extended"])
+        if total is not None:
+            ids0, B = D.shard(total, rank, world)
+        else:
+            B = per_gpu
+            ids0, _ = D.shard(B * world, rank, world)
+        loop = RemoteLoop(mpc, B, kind=wl["kind"], plant=wl["plant"], w_half=HW if wl["plant"] == "linear" else None, Z=Z)
+        p_loss = torch.as_tensor(np.array([0.1 * ((ids0 + i) % 10) for i in range(B)]), device=dev)
+        ref_vec = torch.as_tensor(REF.copy(), device=dev)
+        t_ms, st = timed_rollouts(torch, D, loop, T_STEPS, ref_vec, p_loss, wl["seed"], ids0, steps, warmup, flush, barrier)
+        n_inst = total if total is not None else B * world
+        solves = n_inst * T_STEPS * steps
+        flops = int(st[7]) + ipm_flops_per_iteration(mpc._prob.n, mpc._prob.m) * int(st[4])
+        ach = flops / (t_ms * 1e-3) / 1e12 / world            # per GPU
+        out[name] = {"workload": wl["text"], "instances_total": int(n_inst), "instances_per_gpu": int(B), "scaling": scaling,
+                     "value": solves / (t_ms * 1e-3), "unit": "solves/s", "ms_per_step": t_ms / steps, "steps": steps,
+                     "warmup": warmup, "kernel": mpc._prob.rollout_kernel,
+                     "roofline": {"achieved_tflops_per_gpu": ach, "peak": fp64_peak, "frac": (ach / fp64_peak) if fp64_peak else None},
+                     "status_counts[optimal,max_iter,infeasible,inaccurate]": [int(v) for v in st[:4]],
+                     "mean_active_set_steps_per_solve": float(st[5]) / max(solves, 1),
+                     "max_tube_violation": float(D.all_reduce_max(loop.tube_max.max().reshape(1)).item())}
+        del loop, mpc
+    # c5: support sweep, 10^6 directions in total
+    from rtmpc_b200 import polytope as pc
+    s = load_sets()
+    Mtot = 1_000_000
+    off, M = D.shard(Mtot, rank, world)
+    dirs = torch.as_tensor(support_directions(s, Mtot)[off:off + M], device=dev)
+    V_h = np.ascontiguousarray(pc.extreme(pc.Polytope(s["Z_A"], s["Z_b"], normalize=False)))
+    V = torch.as_tensor(V_h, device=dev)
+    res = torch.empty(M, device=dev, dtype=torch.float64)
+    L = _lib.lib()
+    stream = torch.cuda.current_stream()
+    sweep = lambda: _lib.check(L.rtmpc_support_sweep(_lib.ptr(V), V.shape[0], V.shape[1], _lib.ptr(dirs), M, _lib.ptr(res),   # noqa: E731
+                                                    stream.cuda_stream), "rtmpc_support_sweep")
+    sweep()
+    barrier()
+    total_ms = 0.0
+    for k in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); sweep(); e1.record(stream)
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e1)
+    barrier()
+    t_ms = float(D.all_reduce_max(torch.tensor([total_ms], device=dev, dtype=torch.float64)).item())
+    fl = 2.0 * V.shape[1] * V.shape[0] * M * steps / (total_ms * 1e-3) / 1e12      # this rank's kernel
+    out["c5"] = {"workload": "support-function sweep h_Z(a), 10^6 directions in total split over the ranks, Z = cartpole tube "
+                             f"({V.shape[0]} vertices in {V.shape[1]}-D)", "directions_total": Mtot, "scaling": "strong",
+                 "value": Mtot * steps / (t_ms * 1e-3), "unit": "directions/s", "ms_per_step": t_ms / steps, "steps": steps,
+                 "warmup": 1, "kernel": "support_sweep_kernel",
+                 "roofline": {"achieved_tflops_per_gpu": fl, "peak": fp64_peak, "frac": (fl / fp64_peak) if fp64_peak else None}}
+    return out
+
+
+def trajectory_all_gather(torch, dist, D, RemoteLoop, dev, rank, world, mpc, Z, ids0, p_loss, ref_d):
+    """north_star / SURVEY 8(e): the one collective of the path - an all-gather of the state trajectories [B/G, T+1, nx]
+    (and of the per-instance statistics) AFTER the rollouts.  One recorded rollout of the headline workload, then the
+    gather timed with CUDA events (second call: the first one pays NCCL's connection set-up)."""
+    B = p_loss.shape[0]
+    loop = RemoteLoop(mpc, B, kind="tube", plant="linear", w_half=HW, Z=Z)
+    loop.reset()
+    traj = loop.run(T_STEPS, ref_d[0], p_loss=p_loss, seed=SEED, id_offset=ids0, record=True, fused=True)
+    out = {"trajectory_all_gather_bytes_per_rank": int(traj.numel() * 8)}
+    if world == 1:
+        out.update(trajectory_all_gather_ms=0.0, trajectory_all_gather_gbs=None, trajectory_checksum=float(traj.sum().item()))
+        return out
+    D.all_gather_instances(traj, B * world)                   # connection set-up
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    allt = D.all_gather_instances(traj, B * world)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = float(D.all_reduce_max(torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)).item())
+    recv = traj.numel() * 8 * (world - 1)                     # bytes every rank receives
+    out.update(trajectory_all_gather_ms=ms, trajectory_all_gather_gbs=recv / (ms * 1e-3) / 1e9,
+               trajectory_all_gather_shape=list(allt.shape), trajectory_checksum=float(allt.sum().item()))
+    return out
 
 
 def support_directions(s, M, seed=1):
@@ -547,6 +689,13 @@ def main():
     ap.add_argument("--cpu-solves", type=int, default=8192, dest="cpu_solves",
                     help="QP solves of the CPU arm per step (bounded sample of the workload, ~10 s on 16 cores)")
     ap.add_argument("--no-e2e", action="store_true", dest="no_e2e")
+    ap.add_argument("--no-extra", action="store_true", dest="no_extra",
+                    help="skip the extra_workloads object (BASELINE configs[2..4] measured after the headline) and the "
+                         "trajectory all-gather")
+    ap.add_argument("--rollout-warps", type=int, default=0, dest="rollout_warps",
+                    help="development: rtmpc_set_tuning(RTMPC_TUNE_ROLLOUT_WARPS) (0 = the library's choice)")
+    ap.add_argument("--rollout-quantum", type=int, default=-1, dest="rollout_quantum",
+                    help="development: rtmpc_set_tuning(RTMPC_TUNE_ROLLOUT_QUANTUM) (-1 = the library's default)")
     ap.add_argument("--instances", type=int, default=B_PER_GPU, help="closed-loop instances per GPU (BASELINE configs[1]: 4096; configs[2] = --workload c3 --instances 8192 on 8 GPUs, "
                          "configs[3] = --workload c4 --instances 32768 on 8 GPUs)")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"],

@@ -43,9 +43,10 @@ constexpr int RTMPC_FALLBACK = RTMPC_FALLBACK_STATUS;
 constexpr int AS_STALL = 7;
 
 // per-warp shared memory, in doubles: M (one row per working-set slot), zu, z, v, coef, 16 parameters, slot lists
-// (2*npad ints).  Kept as small as possible: what the warps do not take is L1 for the shared tables.
+// (2*npad ints).  Kept as small as possible: what the warps do not take is L1 for the shared tables, and
+// the L1 / shared split moves in steps (.., 100, 132, .. KB): 16 warps of the cartpole problem fit the 100 KB step.
 __host__ __device__ inline int as_ms(const QPDev& P) { return P.npad + 2; }
-__host__ __device__ inline int as_mrows(const QPDev& P) { return P.npad; }      // one row per slot (<= n rows in the working set), padded to 4
+__host__ __device__ inline int as_mrows(const QPDev& P) { return P.n; }      // one row per slot (<= n rows in the working set; the row stride is even)
 __host__ __device__ inline int as_warp_doubles(const QPDev& P) {
     return as_mrows(P) * as_ms(P) + 4 * P.npad + 16 + P.npad + 4;
 }
@@ -82,6 +83,31 @@ __device__ __forceinline__ ASWarp as_carve(double* base, const QPDev& P) {
 }
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+// 16-byte read-only loads with an L1 policy.  The shared tables (1.3 MB for the cartpole) go through a ~118 KB L1 that
+// 16 warps at different points of their solves compete for; what is streamed once per use should not evict what every
+// warp re-reads every control step.  0: default, 1: no_allocate, 2: evict_first, 3: evict_last.
+template <int HINT>
+__device__ __forceinline__ double2 ld2_hint(const double* p) {
+    double2 v;
+    if (HINT == 1) asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    else if (HINT == 2) asm volatile("ld.global.nc.L1::evict_first.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    else if (HINT == 3) asm volatile("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    else v = *reinterpret_cast<const double2*>(p);
+    return v;
+}
+#ifndef RTMPC_HINT_GT
+#define RTMPC_HINT_GT 1        // columns of G' (certification): streamed
+#endif
+#ifndef RTMPC_HINT_W
+#define RTMPC_HINT_W 0         // rows of W (active-set steps)
+#endif
+#ifndef RTMPC_HINT_SETUP
+#define RTMPC_HINT_SETUP 0     // ExT / TrT (row values at z_u, every solve)
+#endif
+#ifndef RTMPC_HINT_UX
+#define RTMPC_HINT_UX 0        // UxT (certification)
+#endif
+__device__ __forceinline__ double2 ld2_stream(const double* p) { return ld2_hint<RTMPC_HINT_GT>(p); }
 
 // steps: rows added + dropped; rounds: certifications; rows: rows of W streamed; sq: sum of na^2 over the
 // small dense operations (mat-vec, bordering, downdate).  Algorithmic flops are derived from these.
@@ -168,12 +194,13 @@ static __device__ __noinline__ double as_matvec(int Mo, int ms, int hi, int lane
 
 // M grows by slot s:  [[M + r r'/kappa, -r/kappa], [-r'/kappa, 1/kappa]]   (r in rv, zero on free slots;
 // hi = even number of slots covering every occupied one and s)
-static __device__ __noinline__ void as_border(int Mo, int rvo, int ms, int hi, int lane, int s, double r_own, double kappa) {
+// (nr = rows of M: hi is a multiple of 4 and may reach past them; those slots are never occupied)
+static __device__ __noinline__ void as_border(int Mo, int rvo, int ms, int hi, int nr, int lane, int s, double r_own, double kappa) {
     extern __shared__ __align__(16) double as_smem[];
     double* M = as_smem + Mo;
     const double* rv = as_smem + rvo;
     const double ik = __drcp_rn(kappa);
-    if (lane < hi) {
+    if (lane < hi && lane < nr) {
         double* row = M + lane * ms;
         if (lane == s) {
 #pragma unroll 1
@@ -203,14 +230,14 @@ static __device__ __noinline__ void as_border(int Mo, int rvo, int ms, int hi, i
 }
 
 // slot j leaves:  M <- M - m_j m_j' / M_jj, row and column j cleared (tmp: npad doubles of scratch)
-static __device__ __noinline__ void as_downdate(int Mo, int tmpo, int ms, int hi, int lane, int j) {
+static __device__ __noinline__ void as_downdate(int Mo, int tmpo, int ms, int hi, int nr, int lane, int j) {
     extern __shared__ __align__(16) double as_smem[];
     double* M = as_smem + Mo;
     double* tmp = as_smem + tmpo;
     if (lane < hi) tmp[lane] = M[j * ms + lane];      // (columns between the highest slot and hi hold zeros)
     __syncwarp();
     const double ij = __drcp_rn(tmp[j]);
-    if (lane < hi) {
+    if (lane < hi && lane < nr) {
         double* row = M + lane * ms;
         const double c = (lane == j) ? -1.0 : -row[j] * ij;      // row j: m_j - m_j = 0
         if (c != 0.0) {
@@ -387,14 +414,14 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                         mk &= mk - 1;
 #pragma unroll
                         for (int r2 = 0; r2 < R2; ++r2) {
-                            const double2 g = ld2(Wa + r2 * 64), h = ld2(Wb + r2 * 64);
+                            const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64), h = ld2_hint<RTMPC_HINT_W>(Wb + r2 * 64);
                             e[2 * r2] = fma(cb, h.x, fma(ca, g.x, e[2 * r2]));
                             e[2 * r2 + 1] = fma(cb, h.y, fma(ca, g.y, e[2 * r2 + 1]));
                         }
                     } else {
 #pragma unroll
                         for (int r2 = 0; r2 < R2; ++r2) {
-                            const double2 g = ld2(Wa + r2 * 64);
+                            const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64);
                             e[2 * r2] = fma(ca, g.x, e[2 * r2]);
                             e[2 * r2 + 1] = fma(ca, g.y, e[2 * r2 + 1]);
                         }
@@ -416,7 +443,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 __syncwarp();                 // rv shares coef's storage: every lane is done streaming
                 if (lane < npad) w.rv()[lane] = rr;
                 __syncwarp();
-                as_border(w.Mo(), w.rvo(), ms, as_hi(amask | (1u << s)), lane, s, rr, kappa);
+                as_border(w.Mo(), w.rvo(), ms, as_hi(amask | (1u << s)), as_mrows(P), lane, s, rr, kappa);
                 if (lane == s) { sl.ra = p; sl.sa = sp; sl.lam = lam_p; w.act_row()[s] = p; w.act_sgn()[s] = (int)sp; }
                 as_mark(lane, p, (int)sp, true, actu, actl);
                 amask |= 1u << s;
@@ -426,7 +453,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
             }
             // partial step: the blocking row leaves the working set
             as_mark(lane, w.act_row()[j1], w.act_sgn()[j1], false, actu, actl);
-            as_downdate(w.Mo(), w.vo(), ms, hi, lane, j1);
+            as_downdate(w.Mo(), w.vo(), ms, hi, as_mrows(P), lane, j1);
             amask &= ~(1u << j1);
             cnt.sq += na * na;
         }
@@ -510,7 +537,7 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
         const double* __restrict__ u = P.UxT + (size_t)k * mpad + 2 * lane;
 #pragma unroll
         for (int r2 = 0; r2 < R2; ++r2) {
-            const double2 c = ld2(u + r2 * 64);
+            const double2 c = ld2_hint<RTMPC_HINT_UX>(u + r2 * 64);
             e[2 * r2] = fma(-c.x, xk, e[2 * r2]);
             e[2 * r2 + 1] = fma(-c.y, xk, e[2 * r2 + 1]);
         }
@@ -527,7 +554,7 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
             const double* __restrict__ g2 = P.GT + (size_t)k2 * mpad + 2 * lane;
 #pragma unroll
             for (int r2 = 0; r2 < R2; ++r2) {
-                const double2 a = ld2(g0 + r2 * 64), b = ld2(g1 + r2 * 64), c = ld2(g2 + r2 * 64);
+                const double2 a = ld2_stream(g0 + r2 * 64), b = ld2_stream(g1 + r2 * 64), c = ld2_stream(g2 + r2 * 64);
                 e[2 * r2] = fma(c.x, z2, fma(b.x, z1, fma(a.x, z0, e[2 * r2])));
                 e[2 * r2 + 1] = fma(c.y, z2, fma(b.y, z1, fma(a.y, z0, e[2 * r2 + 1])));
             }
@@ -626,7 +653,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             const size_t o = (size_t)k * mpad + 2 * lane;
 #pragma unroll
             for (int r2 = 0; r2 < R2; ++r2) {
-                const double2 a = ld2(P.ExT + o + r2 * 64), b = ld2(P.TrT + o + r2 * 64);
+                const double2 a = ld2_hint<RTMPC_HINT_SETUP>(P.ExT + o + r2 * 64), b = ld2_hint<RTMPC_HINT_SETUP>(P.TrT + o + r2 * 64);
                 e[2 * r2] = fma(b.x, rk, fma(a.x, xk, e[2 * r2]));
                 e[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, e[2 * r2 + 1]));
             }
@@ -732,7 +759,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                     sl.lam = occ ? fmax(lamv, 0.0) : 0.0;
                     break;
                 }
-                as_downdate(w.Mo(), w.vo(), ms, hi, lane, lm.idx);
+                as_downdate(w.Mo(), w.vo(), ms, hi, as_mrows(P), lane, lm.idx);
                 amask &= ~(1u << lm.idx);
                 cnt.sq += na * na;
             }

@@ -337,6 +337,7 @@ int rtmpc_qp_set_work_counter(rtmpc_qp* q, uint64_t* d_counter) {
 }
 
 int32_t rtmpc_qp_warm_stride(rtmpc_qp* q) { return q ? q->dev.npad + 1 : -1; }
+const char* rtmpc_qp_rollout_kernel(rtmpc_qp* q) { return q ? rollout_kernel_name(q->dev) : ""; }
 int32_t rtmpc_qp_rows(rtmpc_qp* q) { return q ? q->dev.mpad : -1; }
 
 int rtmpc_qp_solve(rtmpc_qp* q, int32_t B, const double* d_x_init, const double* d_ref, const int32_t* d_sel,

@@ -78,6 +78,7 @@ struct RolloutArgs {
     unsigned long long* stats;    // [8] status counts[4], IPM iterations, active-set steps, rounds, flops (or NULL)
 };
 bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err);
+const char* rollout_kernel_name(const QPDev& P);     // instantiation rollout_launch picks for this problem
 cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, int wpb, int num_sms, int max_smem,
                            const RolloutArgs& a, cudaStream_t stream);
 

@@ -17,7 +17,7 @@ namespace rtmpc {
 // per-warp shared memory of the rollout, in doubles:
 //   closed-loop state | packet payload | x_nom_0 of this step's solve | warm-start record of each QP | solver scratch
 __host__ __device__ inline int rollout_fixed_doubles(const QPDev& P0, const QPDev& P1, bool two) {
-    return loop_smem_doubles(P0.N, P0.nu) + (((P0.N + 1) * P0.nu + 1) & ~1) + LOOP_MAX_NX +
+    return loop_smem_doubles(P0.N, P0.nu) + loop_even((P0.N + 1) * P0.nu) + loop_even(P0.nx) +
            ((((P0.npad + 2) >> 1) + 1) & ~1) + (two ? ((((P1.npad + 2) >> 1) + 1) & ~1) : 0);   // every part even (16-byte alignment)
 }
 __host__ __device__ inline int rollout_warp_doubles(const QPDev& P0, const QPDev& P1, bool two) {
@@ -47,8 +47,8 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
     LoopSmemState S;
     S.base = wbase;
     double* U_s = S.base + loop_smem_doubles(P0.N, nu);                  // this step's packet payload
-    double* x0_s = U_s + ((usz + 1) & ~1);                                // x_nom[:,0] of this step's solve
-    int* warm0_s = reinterpret_cast<int*>(x0_s + LOOP_MAX_NX);            // warm-start records
+    double* x0_s = U_s + loop_even(usz);                                  // x_nom[:,0] of this step's solve
+    int* warm0_s = reinterpret_cast<int*>(x0_s + loop_even(nx));          // warm-start records
     int* warm1_s = warm0_s + 2 * ((((P0.npad + 2) >> 1) + 1) & ~1);
     double* scratch = wbase + rollout_fixed_doubles(P0, P1, two);
     const bool ext = L.actuator == RTMPC_ACT_EXTENDED;
@@ -201,6 +201,13 @@ static const RoChoice* pick(int mpad) {
     for (const auto& c : kRo)
         if (c.r2 >= r_need) return &c;
     return nullptr;
+}
+
+const char* rollout_kernel_name(const QPDev& P) {
+    static const char* names[] = {"rollout_kernel<2,24>", "rollout_kernel<5,16>", "rollout_kernel<9,16>", "rollout_kernel<12,16>",
+                                  "rollout_kernel<16,16>"};
+    const RoChoice* kc = pick(P.mpad);
+    return kc ? names[kc - kRo] : "none";
 }
 
 bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err) {

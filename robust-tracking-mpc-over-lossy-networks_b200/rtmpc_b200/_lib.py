@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "librtmpc_b200.so")
 EXPORTS = [
     "rtmpc_abi_version", "rtmpc_last_error", "rtmpc_device_count", "rtmpc_set_device", "rtmpc_set_tuning", "rtmpc_get_tuning",
     "rtmpc_qp_create", "rtmpc_qp_destroy", "rtmpc_qp_solve", "rtmpc_qp_solve_host", "rtmpc_launch_count",
-    "rtmpc_qp_warm_stride", "rtmpc_qp_rows", "rtmpc_qp_warm_reset", "rtmpc_qp_set_method", "rtmpc_qp_set_work_counter", "rtmpc_qp_set_step_cap",
+    "rtmpc_qp_warm_stride", "rtmpc_qp_rows", "rtmpc_qp_rollout_kernel", "rtmpc_qp_warm_reset", "rtmpc_qp_set_method", "rtmpc_qp_set_work_counter", "rtmpc_qp_set_step_cap",
     "rtmpc_loop_create", "rtmpc_loop_destroy", "rtmpc_loop_reset", "rtmpc_loop_reset_device", "rtmpc_loop_x", "rtmpc_loop_x_nom",
     "rtmpc_loop_x_hat", "rtmpc_loop_q_t", "rtmpc_loop_s_t", "rtmpc_loop_Theta", "rtmpc_loop_alive",
     "rtmpc_loop_err_acc", "rtmpc_loop_tube_max", "rtmpc_loop_u", "rtmpc_loop_gamma", "rtmpc_loop_time",
@@ -87,6 +87,8 @@ def lib():
     L.rtmpc_qp_warm_stride.restype = C.c_int32
     L.rtmpc_qp_rows.argtypes = [vp]
     L.rtmpc_qp_rows.restype = C.c_int32
+    L.rtmpc_qp_rollout_kernel.argtypes = [vp]
+    L.rtmpc_qp_rollout_kernel.restype = C.c_char_p
     L.rtmpc_qp_warm_reset.argtypes = [vp]
     L.rtmpc_qp_set_method.argtypes = [vp, C.c_int32]
     L.rtmpc_qp_set_work_counter.argtypes = [vp, vp]

@@ -19,6 +19,7 @@ from . import _lib
 from . import numerics
 from . import sets as up
 from .condense import MPCSpec
+from .packets import as_polytope
 from .polytope import Polytope, reduce as _reduce
 from .qp import BatchedQP
 
@@ -52,10 +53,13 @@ class RegulatorMPC:
         self._last_iters = None
 
     def set_state_constraints(self, X):
-        self._X = X
+        """``RegulatorMPC.py:33-37``.  ``X``: anything with ``.A`` / ``.b`` (a ``polytope.Polytope``, this package's
+        ``Polytope``, ...); rows are brought to unit length the way ``polytope.Polytope`` holds them."""
+        self._X = as_polytope(X)
 
     def set_input_constraints(self, U):
-        self._U = U
+        """``RegulatorMPC.py:39-43``; see ``set_state_constraints``."""
+        self._U = as_polytope(U)
 
     def set_solver(self, solver):
         """Kept for API compatibility (``RegulatorMPC.py:93-94``); the CUDA solver is the only one."""

@@ -103,6 +103,11 @@ class BatchedQP:
         """uint64 device tensor (1 element) accumulating the active-set kernel's algorithmic flops, or None."""
         _lib.check(self._L.rtmpc_qp_set_work_counter(self._h, _lib.ptr(counter)), "rtmpc_qp_set_work_counter")
 
+    @property
+    def rollout_kernel(self):
+        """Name of the rollout-kernel instantiation ``rtmpc_loop_rollout`` launches for this problem."""
+        return self._L.rtmpc_qp_rollout_kernel(self._h).decode()
+
     def warm_reset(self):
         _lib.check(self._L.rtmpc_qp_warm_reset(self._h), "rtmpc_qp_warm_reset")
 
