@@ -171,22 +171,36 @@ def encapsulate_controller_packet(u_nom, x_bar, u_bar, K, q_t, x_nom_0=None):
     return pkt
 
 
-def cartpole_ode_step(x, F, dt=1.0 / 500.0, M=1.0, m=0.1, I=0.001, g=9.8, l=0.5):
+BULLET_POLE_INERTIA = 0.1 * (0.05 ** 2 + 1.0 ** 2) / 12.0      # box 0.05 x 0.05 x 1.0, mass 0.1 (cartpole.urdf:61-72)
+BULLET_LINK_DAMPING = 0.04                                     # pybullet default linearDamping = angularDamping
+
+
+def cartpole_ode_step(x, F, dt=1.0 / 500.0, M=1.0, m=0.1, I=0.001, g=9.8, l=0.5, damping=0.0):
     """Analytic replacement of the PyBullet plant (parameters from
     ``Results/results_nonlinear_system.py:29-37`` and ``cartpole.urdf:37-38,61-63``): semi-implicit
-    Euler at 1/500 s.  State (pos, vel, phi, phidot), phi = 0 upright; linearises to (Ac, Bc)."""
+    Euler at 1/500 s.  State (pos, vel, phi, phidot), phi = 0 upright; linearises to (Ac, Bc).
+    ``damping`` k > 0 adds Bullet's link damping (force ``-m v (k + k|v|)`` on each link's linear velocity, torque
+    ``-I w (k + k|w|)``); ``I = BULLET_POLE_INERTIA`` is what ``loadURDF`` (no ``URDF_USE_INERTIA_FROM_FILE``,
+    ``Results/Cartpole/cartpole.py:14-16``) recomputes from the pole's collision box."""
     pos, vel, phi, om = x
     s, c = np.sin(phi), np.cos(phi)
-    D = (M + m) * (I + m * l * l) - (m * l * c) ** 2
     fe = F + m * l * om * om * s
-    acc = ((I + m * l * l) * fe - (m * l) ** 2 * g * s * c) / D
-    alp = ((M + m) * m * g * l * s - m * l * c * fe) / D
+    ge = m * g * l * s
+    if damping > 0.0:
+        vpx, vpz = vel + l * om * c, -l * om * s
+        kp = damping + damping * np.hypot(vpx, vpz)
+        fpx, fpz = -m * vpx * kp, -m * vpz * kp
+        fe += -M * vel * (damping + damping * abs(vel)) + fpx
+        ge += -I * om * (damping + damping * abs(om)) + fpx * l * c - fpz * l * s
+    D = (M + m) * (I + m * l * l) - (m * l * c) ** 2
+    acc = ((I + m * l * l) * fe - m * l * c * ge) / D
+    alp = ((M + m) * ge - m * l * c * fe) / D
     vel2 = vel + dt * acc
     om2 = om + dt * alp
     return np.array([pos + dt * vel2, vel2, phi + dt * om2, om2])
 
 
-def estimate_model_error(x0s, K, Acl, n_steps, substeps=10, dt=1.0 / 500.0):
+def estimate_model_error(x0s, K, Acl, n_steps, substeps=10, dt=1.0 / 500.0, I=0.001, damping=0.0):
     """``Results/estimate_W_for_Cartpole.py:79-127`` with the analytic plant: for every initial condition hold
     ``u = -K x`` over ``substeps`` physics steps (the script's ``lim_zoh`` counter, ``:96-113``), record
     ``w(k) = x(k) - Acl x(k-1)`` at the control instants (``:104-110``).  Returns w [runs, n_steps, 4] and the final
@@ -201,7 +215,7 @@ def estimate_model_error(x0s, K, Acl, n_steps, substeps=10, dt=1.0 / 500.0):
             u = float(-(K @ x)[0])
             prev = x.copy()
             for _ in range(substeps):
-                x = cartpole_ode_step(x, u, dt=dt)
+                x = cartpole_ode_step(x, u, dt=dt, I=I, damping=damping)
             W[r, k] = x - Acl @ prev
         XF[r] = x
     return W, XF

@@ -128,12 +128,18 @@ CARTPOLE_PARAMS = dict(M=1.0, m=0.1, I=0.001, g=9.8, l=0.5)       # Results/esti
 
 
 def estimate_disturbance_set(A, B, K, n_runs=100, n_steps=400, x0_half=(1.0, 0.5, 0.3, 0.5), seed=456, outlier=0.025,
-                             physics_timestep=1.0 / 500.0, Th=0.02, x0=None):
+                             physics_timestep=1.0 / 500.0, Th=0.02, x0=None, plant="cartpole_bullet"):
     """Batched ``Results/estimate_W_for_Cartpole.py:79-127``: ``n_runs`` random initial conditions in the box
     ``+-x0_half`` (script ``:67-75``), each stabilised for ``n_steps`` control periods (the script's 4000 physics steps)
     by the zero-order-hold LQR law ``u = -K x`` on the nonlinear cartpole (analytic ODE instead of PyBullet, one
     launch for all runs); the model error ``w(k) = x(k) - (A - BK) x(k-1)`` (``:104-110``) is collected and the
     interval that discards the ``outlier`` share of largest absolute values per component is returned (``:123-127``).
+
+    ``plant``: 'cartpole_bullet' (default) simulates what the script's PyBullet call simulates - pole inertia recomputed
+    from the collision box and default link damping 0.04 (see ``rollout.CART_PARAMS_BULLET``); its intervals reproduce the
+    constants the reference hard-codes, ``hw = (1e-4, 2.7e-3, 3e-4, 4.3e-2)`` (``Results/results_linear_system.py:76-91``),
+    to within 0.5 %.  'cartpole' uses the parameters of the linear model itself (model error = linearisation and
+    discretisation only).
 
     Returns ``(intervals [nx, 2], w [n_runs, n_steps, nx], x_final [n_runs, nx])``; ``max |intervals|`` per component
     is the half-width vector ``hw`` the experiment scripts build ``W`` from."""
@@ -152,8 +158,9 @@ def estimate_disturbance_set(A, B, K, n_runs=100, n_steps=400, x0_half=(1.0, 0.5
     n_runs = x0.shape[0]
     Acl = _lib.f64(A - B @ K)
     Kf = _lib.f64(K.reshape(-1))
-    p = CARTPOLE_PARAMS
-    cart = (C.c_double * 8)(p["M"], p["m"], p["I"], p["g"], p["l"], physics_timestep, round(Th / physics_timestep), 0.0)
+    from .rollout import PLANTS
+    cp = PLANTS[plant][1]
+    cart = (C.c_double * 8)(cp[0], cp[1], cp[2], cp[3], cp[4], physics_timestep, round(Th / physics_timestep), cp[7])
     w = np.empty((n_runs, n_steps, 4))
     xf = np.empty((n_runs, 4))
     _lib.check(L.rtmpc_model_error_sweep_host(cart, n_runs, n_steps, _lib.ptr(x0), _lib.ptr(Kf), _lib.ptr(Acl), _lib.ptr(w),

@@ -14,7 +14,15 @@ import torch
 
 from . import _lib
 
-CART_PARAMS = (1.0, 0.1, 0.001, 9.8, 0.5, 1.0 / 500.0, 10.0, 0.0)   # M, m, I, g, l, dt, sub-steps
+CART_PARAMS = (1.0, 0.1, 0.001, 9.8, 0.5, 1.0 / 500.0, 10.0, 0.0)   # M, m, I, g, l, dt, sub-steps, link damping
+# The plant the reference actually simulates (Results/Cartpole/cartpole.py:14-16: loadURDF without
+# URDF_USE_INERTIA_FROM_FILE, default dynamics): Bullet recomputes the pole's inertia from its collision box
+# (m (0.05^2 + 1^2) / 12, cartpole.urdf:61-72) and damps every link with linearDamping = angularDamping = 0.04.
+BULLET_POLE_INERTIA = 0.1 * (0.05 ** 2 + 1.0 ** 2) / 12.0
+BULLET_LINK_DAMPING = 0.04
+CART_PARAMS_BULLET = (1.0, 0.1, BULLET_POLE_INERTIA, 9.8, 0.5, 1.0 / 500.0, 10.0, BULLET_LINK_DAMPING)
+PLANTS = {"linear": (_lib.PLANT_LINEAR, CART_PARAMS), "cartpole": (_lib.PLANT_CARTPOLE, CART_PARAMS),
+          "cartpole_bullet": (_lib.PLANT_CARTPOLE, CART_PARAMS_BULLET)}
 
 
 class _DeviceArray:
@@ -37,7 +45,9 @@ class RemoteLoop:
               with its optimisation problem(s) generated
     kind      'tube' (ConsistentActuator + Estimator), 'extended' (+ RobustEstimator, x_nom_0 in the
               packet, gamma-switched QP) or 'track' (SmartActuator + Estimator, Pezzutto remote MPC)
-    plant     'linear' or 'cartpole' (analytic ODE, 10 sub-steps of 1/500 s, no disturbance)
+    plant     'linear', 'cartpole' (analytic ODE with the parameters of the reference's linear model, 10 sub-steps of
+              1/500 s, no disturbance) or 'cartpole_bullet' (the same ODE with the pole inertia and link damping Bullet
+              uses for the reference's URDF: the plant behind figures/TrackingErrorNonlinear.png)
     """
 
     def __init__(self, mpc, B, kind="tube", plant="linear", w_half=None, Z=None, K_plant=None):
@@ -55,7 +65,7 @@ class RemoteLoop:
         d = _lib.LoopDesc()
         d.nx, d.nu, d.N = self.nx, self.nu, self.N
         d.actuator = {"track": _lib.ACT_SMART, "tube": _lib.ACT_CONSISTENT, "extended": _lib.ACT_EXTENDED}[kind]
-        d.plant = {"linear": _lib.PLANT_LINEAR, "cartpole": _lib.PLANT_CARTPOLE}[plant]
+        d.plant, cart = PLANTS[plant]
         keep = [_lib.f64(A), _lib.f64(Bm), _lib.f64(K), _lib.f64(np.atleast_2d(K_plant)),
                 _lib.f64(np.zeros(self.nx) if w_half is None else w_half)]
         dp = C.POINTER(C.c_double)
@@ -64,7 +74,7 @@ class RemoteLoop:
             Hz, hz = _lib.f64(Z.A), _lib.f64(np.asarray(Z.b).flatten())
             d.nz_rows, d.Hz, d.hz = Hz.shape[0], Hz.ctypes.data_as(dp), hz.ctypes.data_as(dp)
             keep += [Hz, hz]
-        for i, v in enumerate(CART_PARAMS):
+        for i, v in enumerate(cart):
             d.cart_params[i] = v
         h = C.c_void_p()
         _lib.check(self.L.rtmpc_loop_create(C.byref(d), self.B, C.byref(h)), "rtmpc_loop_create")

@@ -39,7 +39,7 @@ from rtmpc_b200.condense import condense              # noqa: E402
 from rtmpc_b200.ipm_data import prepare               # noqa: E402
 
 SIGMA, ALPHA = 1e-6, 1.6
-LADDER = (1e-2, 1e-1, 1.0, 1e1, 1e2, 1e3)
+LADDER = (1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1.0, 1e1, 1e2, 1e3)
 MAX_ITER = 4000
 DGEMM_TFLOPS = 35.8                                   # cuBLAS DGEMM 6144^3 measured on the B200 (BENCH_r01.json)
 
