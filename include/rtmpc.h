@@ -299,6 +299,27 @@ int rtmpc_support_sweep(const double* d_V, int32_t nv, int32_t dim, const double
 int rtmpc_support_sweep_host(const double* h_V, int32_t nv, int32_t dim, const double* h_dirs, int64_t M,
                              double* h_out);
 
+/*
+ * Batched low-dimensional LPs over one shared H-representation (the LPs behind the offline set
+ * pipeline once a set has no tractable vertex representation - utils_polytope.support utils_polytope.py:12-23 inside the
+ * maximal-output-admissible-set iteration :247-268, polytope's subset test, polytope.reduce TubeRegulatorMPC.py:74):
+ *     val[b] = max  obj[b]' x   s.t.  H x <= h  (bound of row relax_row[b] relaxed by relax_by),
+ *                                     extra[b][e][0..dim) x <= extra[b][e][dim]  for e < n_extra,   |x_i| <= box
+ * One warp per LP, dual simplex from the box vertex (csrc/rtmpc_lp.cu).  dim <= 16.
+ *   d_HT [dim*mpad]  H TRANSPOSED (row r, coordinate k at d_HT[k*mpad + r]); d_h [mpad]; rows >= m are ignored
+ *   d_obj [B*dim]; d_relax_row [B] or NULL (-1: no row relaxed); d_extra [B*n_extra*(dim+1)] or NULL
+ *   d_val [B]; d_x [B*dim] or NULL (the optimal vertex); d_iters [B] or NULL (simplex iterations)
+ *   d_status [B]: 0 optimal, 1 iteration limit / singular basis, 2 infeasible (val = -1e300),
+ *                 4 unbounded inside the box (val = +1e300)
+ * rtmpc_lp_solve_host: the same with HOST buffers and H row-major [m*dim]; copies, solves, copies back, synchronises.
+ */
+int rtmpc_lp_solve(const double* d_HT, const double* d_h, int32_t m, int32_t mpad, int32_t dim, const double* d_obj,
+                   const int32_t* d_relax_row, double relax_by, const double* d_extra, int32_t n_extra, int64_t B,
+                   double box, double* d_val, double* d_x, int32_t* d_status, int32_t* d_iters, void* stream);
+int rtmpc_lp_solve_host(const double* h_H, const double* h_h, int32_t m, int32_t dim, const double* h_obj,
+                        const int32_t* h_relax_row, double relax_by, const double* h_extra, int32_t n_extra, int64_t B,
+                        double box, double* h_val, double* h_x, int32_t* h_status, int32_t* h_iters);
+
 /* Model-error sweep for the disturbance set W (Results/estimate_W_for_Cartpole.py:79-127, analytic cartpole ODE instead
  * of PyBullet): B independent runs; run b starts at x0[b], the plant is driven by the zero-order-hold LQR law
  * u_k = -K x_k for T control periods (cart_params as in rtmpc_loop_desc: M, m, I, g, l, dt, substeps), and

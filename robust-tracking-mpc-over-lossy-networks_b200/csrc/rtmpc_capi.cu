@@ -21,6 +21,7 @@ static int fail(const char* what, cudaError_t e = cudaSuccess) {
     if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
     return -1;
 }
+namespace rtmpc { int set_last_error(const char* what, cudaError_t e) { return fail(what, e); } }
 // a handle's arrays live on the device that was current when it was created
 static int wrong_device(int handle_device, const char* who) {
     int cur = -1;

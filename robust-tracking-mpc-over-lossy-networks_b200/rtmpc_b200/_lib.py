@@ -22,7 +22,7 @@ EXPORTS = [
     "rtmpc_loop_err_acc", "rtmpc_loop_tube_max", "rtmpc_loop_u", "rtmpc_loop_gamma", "rtmpc_loop_time",
     "rtmpc_loop_step", "rtmpc_loop_rollout",
     "rtmpc_actuator_process", "rtmpc_estimator_update", "rtmpc_support_sweep", "rtmpc_support_sweep_host",
-    "rtmpc_model_error_sweep", "rtmpc_model_error_sweep_host",
+    "rtmpc_model_error_sweep", "rtmpc_model_error_sweep_host", "rtmpc_lp_solve", "rtmpc_lp_solve_host",
 ]
 
 OPTIMAL, MAX_ITER, INFEASIBLE, OPTIMAL_INACCURATE = 0, 1, 2, 3
@@ -116,6 +116,8 @@ def lib():
     L.rtmpc_support_sweep_host.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int64, vp]
     L.rtmpc_model_error_sweep.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
     L.rtmpc_model_error_sweep_host.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
+    L.rtmpc_lp_solve.argtypes = [vp, vp, i32, i32, i32, vp, vp, C.c_double, vp, i32, C.c_int64, C.c_double, vp, vp, vp, vp, vp]
+    L.rtmpc_lp_solve_host.argtypes = [vp, vp, i32, i32, vp, vp, C.c_double, vp, i32, C.c_int64, C.c_double, vp, vp, vp, vp]
     _lib = L
     return L
 

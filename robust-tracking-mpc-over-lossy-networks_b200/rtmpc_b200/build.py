@@ -6,7 +6,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 OUT = os.path.join(_HERE, "librtmpc_b200.so")
-SOURCES = ["rtmpc_capi.cu", "rtmpc_as.cu", "rtmpc_ipm.cu", "rtmpc_rollout.cu"]
+SOURCES = ["rtmpc_capi.cu", "rtmpc_as.cu", "rtmpc_ipm.cu", "rtmpc_rollout.cu", "rtmpc_lp.cu"]
 HEADERS = ["rtmpc_common.cuh", "rtmpc_ipm.cuh", "rtmpc_as.cuh", "rtmpc_loop.cuh", "rtmpc_launch.h",
            os.path.join("..", "..", "include", "rtmpc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -114,7 +114,12 @@ class TubeRegulatorMPC(RegulatorMPC):
         self._Acl = A - B @ K
         self._Z = None
 
-    def determine_mRPI(self, W, eps_var=1.9e-5, Acl=None, rpi_method=0, K=None):
+    def determine_mRPI(self, W, eps_var=1.9e-5, Acl=None, rpi_method=0, K=None, skip_wasted_pass=False):
+        """``TubeRegulatorMPC.py:26-78``: approximate the mRPI set with a cap ``s_max`` on the iterations, multiply the cap by
+        10 and START OVER until the approximation succeeds, then ``pc.reduce``.  The reference starts at ``s_max = 200``
+        (``:48``); for the cartpole (k* = 308) that first pass is wasted work.  ``skip_wasted_pass=True`` starts at 2000
+        instead - the result is the same set (it does not depend on the cap once the cap is large enough), only the wasted
+        pass and its "RPI not determined in 200 steps" print go away.  Default: the reference's behaviour."""
         if K is None:
             K = self._K
         if Acl is None:
@@ -122,7 +127,7 @@ class TubeRegulatorMPC(RegulatorMPC):
         if np.max(np.abs(np.linalg.eigvals(Acl))) >= 1:
             print("The matrix Acl is not stable, such that the algorithm will never converge. \n Therefore, None is returned")
             return None
-        s_max = 200
+        s_max = 2000 if skip_wasted_pass else 200
         while True:
             if rpi_method == 1:
                 Fs_temp, status = up.calculate_RPI(Acl, W, self._X, self._U, K, eps_var=eps_var, s_max=s_max)
@@ -288,11 +293,12 @@ class TubeTrackingMPC(_TrackingMixin, TubeRegulatorMPC):
         self._Xf = _augmented_terminal_set(self._A, self._B, self._K, self._Acl, Hx, hx, Hu, hu, self._lambda,
                                            self._nx, self._nu)
 
-    def determine_mRPI(self, W, epsilon=1e-4, Acl=None, rpi_method=0):
+    def determine_mRPI(self, W, epsilon=1e-4, Acl=None, rpi_method=0, skip_wasted_pass=False):
         if Acl is None:
             Acl = self._Acl if self._Acl_plant is None else self._Acl_plant
         K = self._K if self._K_ancillary is None else self._K_ancillary
-        return TubeRegulatorMPC.determine_mRPI(self, W, epsilon, Acl=Acl, K=K, rpi_method=rpi_method)
+        return TubeRegulatorMPC.determine_mRPI(self, W, epsilon, Acl=Acl, K=K, rpi_method=rpi_method,
+                                               skip_wasted_pass=skip_wasted_pass)
 
     def tighten_constraints(self):
         K = self._K if self._K_ancillary is None else self._K_ancillary
@@ -307,8 +313,9 @@ class TubeTrackingMPC(_TrackingMixin, TubeRegulatorMPC):
     def generate_optimization_problem(self, fixed_initial_state=False):
         self._prob = BatchedQP(self._spec(fixed_initial_state), Kss=self._K)
 
-    def setup_optimization(self, W, fixed_initial_state=False, rpi_method=0):
-        self.determine_mRPI(W, rpi_method=rpi_method)
+    def setup_optimization(self, W, fixed_initial_state=False, rpi_method=0, skip_wasted_pass=False):
+        """``TubeTrackingMPC.py:158-168``; ``skip_wasted_pass``: see ``TubeRegulatorMPC.determine_mRPI``."""
+        self.determine_mRPI(W, rpi_method=rpi_method, skip_wasted_pass=skip_wasted_pass)
         self.tighten_constraints()
         self.determine_Xf()
         self.generate_optimization_problem(fixed_initial_state)
@@ -369,8 +376,9 @@ class ExtendedTubeTrackingMPC(TubeTrackingMPC):
                        tube_init=_Ab(self._ZmW), g2_free_terminal=not self._strict_terminal)
         self._prob_packet_received = BatchedQP(spec, Kss=self._K)
 
-    def setup_optimization(self, W, fixed_initial_state=False, rpi_method=0):
-        super().setup_optimization(W, fixed_initial_state=fixed_initial_state, rpi_method=rpi_method)
+    def setup_optimization(self, W, fixed_initial_state=False, rpi_method=0, skip_wasted_pass=False):
+        super().setup_optimization(W, fixed_initial_state=fixed_initial_state, rpi_method=rpi_method,
+                                   skip_wasted_pass=skip_wasted_pass)
         self.generate_optimization_problem_when_packet_received(W)
 
     def load_sets(self, Z, Xc, Uc, Xf, W=None, ZmW=None, fixed_initial_state=False):

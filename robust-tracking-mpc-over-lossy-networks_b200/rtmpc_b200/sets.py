@@ -165,7 +165,8 @@ def calculate_maximum_admissible_output_set(A, X, max_iter=100000, verbose=True,
     set, but without the reference's full redundancy removal in every iteration: only the
     new rows are tested against the current set (one LP each), only rows that cut are appended, and the
     LP-per-row ``reduce`` runs once at the end (and whenever the working representation has grown by more than
-    ``growth`` x since the last one) -- 6x less time for the 9-D cartpole terminal set (128 s -> 21 s)."""
+    ``growth`` x since the last one).  Every group of LPs is one batched ``rtmpc_lp_solve`` launch (``polytope.lp_batch``).
+    9-D cartpole terminal set: 128 s (reference's loop, HiGHS) -> 21 s (lazy loop, HiGHS) -> see DESIGN.md (GPU LPs)."""
     G, f = X.A, np.asarray(X.b, float).flatten()
     Ot = X if isinstance(X, Polytope) else Polytope(X.A, X.b)
     Ot = pc.reduce(Ot)
@@ -174,13 +175,9 @@ def calculate_maximum_admissible_output_set(A, X, max_iter=100000, verbose=True,
     for t in range(max_iter):
         Ap = Ap @ A
         new = Polytope(G @ Ap, f)
-        cuts = pc.support_lp(Ot, new.A) > new.b
-        changed = False
-        for j in np.nonzero(cuts)[0]:
-            piece = Polytope(np.vstack([Ot.A, -new.A[j:j + 1]]), np.hstack([Ot.b, -new.b[j]]), normalize=False)
-            if pc.is_fulldim(piece):
-                changed = True
-                break
+        cuts = pc.support_lp(Ot, new.A) > new.b               # one batch of LPs over the rows of O_t
+        # O_t == O_{t+1} unless a new row cuts off a piece with Chebyshev radius > 1e-7 (one batch of LPs, one per cutting row)
+        changed = bool(cuts.any()) and bool(np.any(pc.cut_radii(Ot, new.A[cuts], new.b[cuts]) > pc.ABS_TOL))
         if not changed:
             if verbose:
                 print(f"Admissible set calculation has converged at t = {t}")
