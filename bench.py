@@ -184,20 +184,40 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+_SETUP = {}
+
+
 def build_controller(extended=False):
-    from rtmpc_b200 import mpc
-    from rtmpc_b200.polytope import Polytope
-    s = load_sets()
-    P = lambda k: Polytope(s[k + "_A"], s[k + "_b"], normalize=False)      # noqa: E731
+    """The controller of Results/results_linear_system.py:26-125, built by the PRODUCT's own set-up call on the GPU
+    (``setup_optimization(W, fixed_initial_state=True, rpi_method=1)``: Darup RPI by support sweeps, reduce, tightening,
+    the 9-D terminal-set iteration on batched LPs, QP generation) - not loaded from a fixture.  The sets it produces are
+    compared with tests/golden/sets_cp.npz (same row counts, bounds after sorting) and the result goes into ``checks``."""
+    from rtmpc_b200 import mpc, numerics
+    from rtmpc_b200.polytope import box
+    A, B = numerics.cartpole_linear(0.02)
+    Q, R, N = np.diag([100.0, 10.0, 100.0, 10.0]), 0.1 * np.eye(1), 20
     cls = mpc.ExtendedTubeTrackingMPC if extended else mpc.TubeTrackingMPC
-    c = cls(s["A"], s["B"], s["Q"], s["R"], int(s["N"]))
-    c.set_input_constraints(P("U"))
-    c.set_state_constraints(P("X"))
-    if extended:
-        c.load_sets(P("Z"), P("Xc"), P("Uc"), P("Xf"), ZmW=P("ZmW"), fixed_initial_state=True)
-    else:
-        c.load_sets(P("Z"), P("Xc"), P("Uc"), P("Xf"), fixed_initial_state=True)
-    return c, P("Z")
+    c = cls(A, B, Q, R, N)
+    c.set_input_constraints(box([10.0]))
+    c.set_state_constraints(box([5.0, 5.0, 0.3, 2.0]))
+    t0 = time.perf_counter()
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):           # the set-up prints k_star / convergence lines like the reference
+        c.setup_optimization(box(HW), fixed_initial_state=True, rpi_method=1, skip_wasted_pass=True)
+    dt = time.perf_counter() - t0
+    s = load_sets()
+    same = True
+    worst = 0.0
+    for k in ("Z", "Xc", "Uc", "Xf"):
+        P = getattr(c, "_" + k)
+        if P.A.shape != s[k + "_A"].shape:
+            same = False
+            continue
+        worst = max(worst, float(np.abs(np.sort(P.b) - np.sort(s[k + "_b"])).max()))
+    _SETUP["extended" if extended else "tube"] = {"setup_seconds": dt, "rows_Z_Xf": [int(c._Z.A.shape[0]), int(c._Xf.A.shape[0])],
+                                                   "same_row_counts_as_fixture": same, "max_sorted_bound_diff_vs_fixture": worst}
+    return c, c._Z
 
 
 # BASELINE.json configs[1..3] (SURVEY 8d C2..C4): the same closed loop with another controller variant / plant
@@ -411,7 +431,8 @@ def run_gpu_arm(args):
                                        "baseline, not a like-for-like ratio; it does not grow with --gpus"},
             "checks": {"status_counts[optimal,max_iter,infeasible,inaccurate]": status_all.tolist(),
                        "max_tube_violation": tube_max, "mean_tracking_error": float(err_all.mean().item()),
-                       "stats_all_gather_ms": gather_ms, **gather},
+                       "stats_all_gather_ms": gather_ms, **gather,
+                       "controller_setup_on_gpu": _SETUP},
             "extra_workloads": extra,
         }
         print(json.dumps(out))

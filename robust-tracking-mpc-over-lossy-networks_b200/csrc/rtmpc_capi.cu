@@ -496,15 +496,16 @@ int rtmpc_loop_create(const rtmpc_loop_desc* d, int32_t B, rtmpc_loop** out) {
     rc |= lalloc(l, (size_t)nu * nx, &K, d->K);
     rc |= lalloc(l, (size_t)nu * nx, &Kp, d->K_plant ? d->K_plant : d->K);
     if (d->nz_rows > 0) {
-        // A centrally symmetric tube (every facet a'x <= h has its mirror -a'x <= h; the mRPI set of a symmetric
-        // disturbance box is) needs one dot product per pair: max(a'd - h, -a'd - h) = |a'd| - h.
+        // Facets in pairs with opposite normals (a'x <= h+, -a'x <= h-; the mRPI set of a symmetric disturbance box has
+        // them, with h+ and h- equal up to the rounding of two support evaluations) need one dot product per pair:
+        // max(a'd - h+, -a'd - h-).  The normals have to be exact negatives, the bounds may differ.
         const int nr = d->nz_rows;
         std::vector<int> mate(nr, -1);
         bool sym = (nr % 2) == 0;
         for (int i = 0; i < nr && sym; ++i) {
             if (mate[i] >= 0) continue;
             for (int j = i + 1; j < nr; ++j) {
-                if (mate[j] >= 0 || d->hz[j] != d->hz[i]) continue;
+                if (mate[j] >= 0) continue;
                 bool opp = true;
                 for (int k = 0; k < nx && opp; ++k) opp = d->Hz[(size_t)j * nx + k] == -d->Hz[(size_t)i * nx + k];
                 if (opp) { mate[i] = j; mate[j] = i; break; }
@@ -517,6 +518,7 @@ int rtmpc_loop_create(const rtmpc_loop_desc* d, int32_t B, rtmpc_loop** out) {
                 if (mate[i] > i) {
                     Hh.insert(Hh.end(), d->Hz + (size_t)i * nx, d->Hz + (size_t)(i + 1) * nx);
                     hh.push_back(d->hz[i]);
+                    hh.push_back(d->hz[mate[i]]);
                 }
             L.nz_rows = nr / 2;
             L.tube_sym = 1;

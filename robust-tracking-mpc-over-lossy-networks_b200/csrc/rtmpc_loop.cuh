@@ -22,7 +22,8 @@ constexpr int LOOP_MAX_NU = 4;
 
 struct LoopDev {
     int nx, nu, N, actuator, plant, nz_rows;
-    int tube_sym;      // 1: the tube is centrally symmetric and Hz/hz hold one facet of every +- pair: value |Hz d| - hz
+    int tube_sym;      // 1: the tube's facets come in pairs with opposite normals; Hz holds one normal per pair and hz the two
+                       //    bounds (h+, h-) of the pair: value max(Hz d - h+, -Hz d - h-), one dot product for both facets
     const double *A, *Bm, *K, *Kp, *Hz, *hz, *w_half;
     double cart[8];
     double *x, *x_nom, *x_hat, *buf, *u_last, *err_acc, *tube_max;
@@ -119,8 +120,7 @@ __device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, const State
     const bool sym = L.tube_sym != 0;
 #pragma unroll 4
     for (int i = first; i < L.nz_rows; i += stride) {
-        double acc = -__ldg(L.hz + i);
-        if (sym) acc = 0.0;
+        double acc = sym ? 0.0 : -__ldg(L.hz + i);
         if (NX > 0 && (NX & 1) == 0) {
             const double2* __restrict__ h2 = reinterpret_cast<const double2*>(L.Hz + i * NX);      // rows are 16-byte aligned
 #pragma unroll
@@ -133,7 +133,11 @@ __device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, const State
 #pragma unroll
             for (int k = 0; k < AX; ++k) if (k < nx) acc = fma(__ldg(L.Hz + i * nx + k), d[k], acc);
         }
-        if (sym) acc = fabs(acc) - __ldg(L.hz + i);       // both facets of the pair at once
+        if (sym) {                                          // both facets of the pair at once
+            const double2 hh = __ldg(reinterpret_cast<const double2*>(L.hz) + i);
+            const double a1 = acc - hh.x, a2 = -acc - hh.y;
+            acc = (a1 > a2) ? a1 : a2;
+        }
         if (acc > worst) worst = acc;          // (a compare and a select: FP64 fmax is a seven-instruction sequence)
     }
     return worst;

@@ -179,11 +179,10 @@ def condense(spec: MPCSpec) -> CondensedQP:
         HN, hN = np.asarray(spec.terminal[0], float), np.asarray(spec.terminal[1], float).flatten()
         if has_ss:
             if spec.g2_free_terminal:
-                lo_th, up_th = _project_terminal_on_theta(HN, hN, Mss, nx, nu)
-                Cth = np.r_[np.eye(nth), -np.eye(nth)]
+                Cth, hth = _project_terminal_on_theta(HN, hN, Mss, nx, nu)
                 Pth = np.zeros((nth, n))
                 Pth[:, o_th:] = np.eye(nth)
-                ineq(Cth, np.r_[up_th, -lo_th], Pth, kind="term")
+                ineq(Cth, hth, Pth, kind="term")
             else:
                 rows_tag.extend(("term", 0, j) for j in range(HN.shape[0]))
                 rows_g.append(HN[:, :nx] @ Px[N] + HN[:, nx:2 * nx] @ Pxb + HN[:, 2 * nx:] @ Pub)
@@ -295,16 +294,30 @@ def _merge_two_sided(Gi, h0, hx):
 
 
 def _project_terminal_on_theta(HN, hN, Mss, nx, nu):
-    """G2 mode: x_N and u_bar in the terminal rows are free, so only
-    {theta : exists (y,v): HN [y; Mss_x theta; v] <= hN} remains.  Exact for dim(theta) = 1."""
+    """G2 mode: x_N and u_bar in the terminal rows are free variables of the "packet received" problem
+    (``TubeTrackingMPC.py:293``), so what remains of the terminal set is its projection on the steady-state parameter,
+    ``{theta : exists (y, v): HN [y; Mss_x theta; v] <= hN}``.  Returns rows ``(C, h)`` with ``C theta <= h``.
+    dim(theta) = 1 (both systems of the reference): the interval, by two LPs.  dim(theta) > 1 (multi-input plants): the
+    polytope ``{(y, theta, v)}`` is vertex-enumerated, the vertices are projected and their convex hull taken - exact."""
     from scipy.optimize import linprog
     nth = Mss.shape[1]
-    if nth != 1:
-        raise NotImplementedError("G2-compatible terminal projection needs a 1-D steady-state family; "
-                                  "use strict_terminal=True")
     Aub = np.c_[HN[:, :nx], HN[:, nx:2 * nx] @ Mss[:nx], HN[:, 2 * nx:]]
-    c = np.zeros(Aub.shape[1])
-    c[nx] = 1.0
-    lo = linprog(c, A_ub=Aub, b_ub=hN, bounds=(None, None))
-    hi = linprog(-c, A_ub=Aub, b_ub=hN, bounds=(None, None))
-    return np.array([lo.fun]), np.array([-hi.fun])
+    if nth == 1:
+        c = np.zeros(Aub.shape[1])
+        c[nx] = 1.0
+        lo = linprog(c, A_ub=Aub, b_ub=hN, bounds=(None, None))
+        hi = linprog(-c, A_ub=Aub, b_ub=hN, bounds=(None, None))
+        return np.array([[1.0], [-1.0]]), np.array([-hi.fun, -lo.fun])
+    from scipy.spatial import ConvexHull, HalfspaceIntersection
+    nrm = np.linalg.norm(Aub, axis=1)
+    keep = nrm > 1e-12
+    A, b = Aub[keep] / nrm[keep, None], hN[keep] / nrm[keep]
+    cc = np.zeros(A.shape[1] + 1)                                   # Chebyshev centre as the interior point
+    cc[-1] = -1.0
+    res = linprog(cc, A_ub=np.c_[A, np.ones(len(b))], b_ub=b, bounds=[(None, None)] * A.shape[1] + [(0, None)])
+    if res.status != 0 or res.x[-1] <= 1e-9:
+        raise ValueError("terminal set has no interior: cannot project it on the steady-state parameter")
+    V = HalfspaceIntersection(np.c_[A, -b], res.x[:-1]).intersections
+    V = V[np.all(np.isfinite(V), axis=1)]
+    hull = ConvexHull(V[:, nx:nx + nth])
+    return hull.equations[:, :-1].copy(), -hull.equations[:, -1].copy()

@@ -93,3 +93,31 @@ def test_steady_state_basis():
     B = np.array([[0.0], [1.0]])
     M = steady_state_basis(A, B)
     assert M.shape == (3, 1) and np.abs(np.c_[A - np.eye(2), B] @ M).max() < 1e-12
+
+
+def test_g2_terminal_projection_for_a_two_dimensional_steady_state_family():
+    """G2 mode (TubeTrackingMPC.py:293) when the steady-state family has dimension 2 (a two-input plant): the projection of
+    the terminal set on theta, against LP support values of the un-projected set in random theta directions."""
+    from scipy.optimize import linprog
+    from rtmpc_b200.condense import _project_terminal_on_theta, steady_state_basis
+    rng = np.random.default_rng(5)
+    A = np.array([[1.0, 0.1, 0.0], [0.0, 1.0, 0.1], [0.0, 0.0, 0.9]])
+    B = np.array([[0.0, 0.0], [0.1, 0.0], [0.0, 0.2]])
+    nx, nu = B.shape
+    Mss = steady_state_basis(A, B)
+    nth = Mss.shape[1]
+    assert nth == 2
+    m = 60
+    HN = rng.normal(size=(m, 2 * nx + nu))
+    HN /= np.linalg.norm(HN, axis=1)[:, None]
+    hN = rng.uniform(0.5, 1.5, m)
+    C, h = _project_terminal_on_theta(HN, hN, Mss, nx, nu)
+    assert C.shape[1] == nth and C.shape[0] >= 3
+    Aub = np.c_[HN[:, :nx], HN[:, nx:2 * nx] @ Mss[:nx], HN[:, 2 * nx:]]
+    for _ in range(25):
+        a = rng.normal(size=nth)
+        c = np.zeros(Aub.shape[1])
+        c[nx:nx + nth] = -a
+        full = -linprog(c, A_ub=Aub, b_ub=hN, bounds=(None, None)).fun
+        proj = -linprog(-a, A_ub=C, b_ub=h, bounds=(None, None)).fun
+        assert abs(full - proj) <= 1e-8 * (1 + abs(full))

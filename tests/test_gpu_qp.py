@@ -309,3 +309,50 @@ def test_handles_are_bound_to_their_device():
         _lib.check(L.rtmpc_set_device(0), "rtmpc_set_device")
     _, _, st, _ = qp.solve_host(np.zeros((1, 2)), np.zeros((1, 2)))
     assert st[0] == 0
+
+
+def test_extended_g2_mode_with_a_two_dimensional_steady_state_family():
+    """ExtendedTubeTrackingMPC's "packet received" problem in the reference's G2 form (terminal rows act on free variables,
+    TubeTrackingMPC.py:293) for a two-input plant, where the steady-state family has dimension 2 and the terminal set has to
+    be projected on a 2-D theta (condense._project_terminal_on_theta): against the oracle's un-condensed problem with the
+    free variables kept."""
+    from oracle import ref_qp as rq
+    from oracle.ref_polytope import Polytope as OP
+    from rtmpc_b200.condense import MPCSpec
+    from rtmpc_b200.qp import BatchedQP
+    from rtmpc_b200 import numerics
+    rng = np.random.default_rng(7)
+    A = np.array([[1.0, 0.1, 0.0], [0.0, 1.0, 0.1], [0.0, -0.05, 0.95]])
+    B = np.array([[0.0, 0.0], [0.1, 0.0], [0.0, 0.1]])
+    Q, R, N = np.diag([1.0, 1.0, 0.5]), np.diag([0.1, 0.2]), 6
+    nx, nu = B.shape
+    K, _, _ = numerics.dlqr(A, B, Q, R)
+    Ql = Q + K.T @ R @ K
+    P = numerics.dlyap(A - B @ K, (Ql + Ql.T) / 2)
+    XA, Xb = np.r_[np.eye(3), -np.eye(3)], np.array([2.0, 1.0, 1.0, 2.0, 1.0, 1.0])
+    UA, Ub = np.r_[np.eye(2), -np.eye(2)], np.array([0.5, 0.4, 0.5, 0.4])
+    ZA, Zb = np.r_[np.eye(3), -np.eye(3)], np.full(6, 0.05)                    # initial tube: a small box
+    HN = rng.normal(size=(40, 2 * nx + nu))                                     # a bounded terminal set on (x_N, x_bar, u_bar)
+    HN /= np.linalg.norm(HN, axis=1)[:, None]
+    hN = rng.uniform(0.6, 1.2, 40)
+    spec = MPCSpec(A, B, Q, R, N, P_term=P, T_ss=10 * P, stage_x=(XA, Xb), stage_u=(UA, Ub), terminal=(HN, hN),
+                   tube_init=(ZA, Zb), g2_free_terminal=True)
+    qp = BatchedQP(spec, Kss=K)
+    assert qp.cq.nth == 2
+    oq = rq.build_extended_packet_received(A, B, Q, R, N, P, OP(XA, Xb, normalize=False), OP(UA, Ub, normalize=False),
+                                           OP(HN, hN, normalize=False), OP(ZA, Zb, normalize=False))
+    X = rng.uniform(-1, 1, (30, 3)) * np.array([1.0, 0.4, 0.4])
+    Rf = np.c_[rng.uniform(-1.0, 1.0, 30), np.zeros((30, 2))]
+    z, U, st, it = qp.solve_host(X, Rf)
+    n_ok = 0
+    for i in range(30):
+        sol, res = rq.solve_param(oq, X[i].copy(), Rf[i].copy())
+        if res.status == "infeasible":
+            assert st[i] == 2
+            continue
+        assert st[i] == 0
+        x_o, u_o, xb_o, ub_o = sol
+        assert np.abs(U[i, :N].T - u_o).max() <= TOL_TIGHT
+        assert np.abs(U[i, N] - (ub_o + K @ xb_o)).max() <= TOL_TIGHT
+        n_ok += 1
+    assert n_ok >= 10
