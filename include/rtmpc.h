@@ -90,7 +90,8 @@ int         rtmpc_device_count(void);
 int         rtmpc_set_device(int device);
 
 /*
- * Launch tuning, process-wide (nothing is read from the environment; results never depend on these, only speed):
+ * Launch tuning, process-wide (nothing is read from the environment; results never depend on these, only speed - except the last
+ * bits with RTMPC_TUNE_ROLLOUT_CARRY, see there):
  *   RTMPC_TUNE_ROLLOUT_QUANTUM  control steps a warp runs one closed loop for before it hands the loop's state on and
  *                               draws the next (instance, chunk) ticket (rtmpc_loop_rollout; default 25).  0: every warp
  *                               keeps its instance for the whole rollout.  Time slicing needs all thread blocks of the
@@ -99,11 +100,22 @@ int         rtmpc_set_device(int device);
  *   RTMPC_TUNE_ROLLOUT_WARPS    warps per thread block of the rollout kernel (0: automatic)
  *   RTMPC_TUNE_AS_WARPS         upper bound on the warps per thread block of the active-set kernel of rtmpc_qp_solve
  *                               (0: automatic)
+ *   RTMPC_TUNE_ROLLOUT_CARRY    1 (default): rtmpc_loop_rollout warm-starts every solve of a closed loop from the previous
+ *                               control step's certified working set AS IT IS and keeps that set's inverse on chip from
+ *                               one step to the next (no factorisation per solve; the inverse is rebuilt from scratch at
+ *                               control steps that are multiples of RTMPC_TUNE_ROLLOUT_QUANTUM, so the results do not depend
+ *                               on how the batch is cut, sliced or spread over GPUs).  0: the working set is moved one stage
+ *                               earlier (desc.shift) and inverted from scratch in every solve, exactly as rtmpc_qp_solve
+ *                               does.  The one knob that touches results, in the last bits only: every solution carries the
+ *                               same KKT certificate either way, but the certification refines the multipliers with the
+ *                               inverse as approximate inverse, so with 1 a rollout agrees with the step-by-step path
+ *                               (rtmpc_qp_solve + rtmpc_loop_step) to rounding, with 0 bit for bit.
  * A negative value restores the default.  rtmpc_get_tuning returns the value in force (-1: unknown knob).
  */
 #define RTMPC_TUNE_ROLLOUT_QUANTUM 0
 #define RTMPC_TUNE_ROLLOUT_WARPS   1
 #define RTMPC_TUNE_AS_WARPS        2
+#define RTMPC_TUNE_ROLLOUT_CARRY   3
 int     rtmpc_set_tuning(int32_t knob, int32_t value);
 int32_t rtmpc_get_tuning(int32_t knob);
 

@@ -38,6 +38,16 @@
 
 namespace rtmpc {
 
+#ifdef RTMPC_AS_DEBUG
+// development counters (scratch builds only): [0] solves past the unconstrained test, [1] carried, [2] moved, [3] changes,
+// [4] old set sizes, [5] from-scratch inversions, [6] their candidates, [7] GI adds, [8] GI drops, [9] warm multiplier drops,
+// [16 + k] histogram of the certified working-set size
+static __device__ unsigned long long g_as_dbg[64];      // one copy per translation unit; the rollout's is read out
+#define AS_DBG(i, v) do { if (lane == 0) atomicAdd(&g_as_dbg[i], (unsigned long long)(v)); } while (0)
+#else
+#define AS_DBG(i, v) do { } while (0)
+#endif
+
 constexpr int RTMPC_FALLBACK = RTMPC_FALLBACK_STATUS;
 // as_gi: the entering row is a combination of the working set, no multiplier blocks, and its violation is tiny
 constexpr int AS_STALL = 7;
@@ -322,6 +332,21 @@ __device__ __forceinline__ void as_mark(int lane, int row, int sgn, bool on, uns
 
 __device__ __forceinline__ int as_hi(unsigned amask) { return (35 - __clz(amask | 1u)) & ~3; }   // multiple of 4, covers amask
 
+// M and the slot lists of one warp back to "empty working set"
+__device__ __forceinline__ void as_clear(ASWarp& w, const QPDev& P, int lane) {
+    const int npad = P.npad, ms = as_ms(P);
+    if (lane < npad) {
+        if (lane < as_mrows(P)) {
+            double* row = w.M() + lane * ms;
+#pragma unroll 1
+            for (int b = 0; b < npad; b += 2) *reinterpret_cast<double2*>(row + b) = make_double2(0.0, 0.0);
+        }
+        w.act_row()[lane] = 0;
+        w.act_sgn()[lane] = 0;
+    }
+    __syncwarp();
+}
+
 // Goldfarb-Idnani iteration.  `apply_only`: the warm start left its multipliers in w.coef(); the first pass
 // only moves the row values (the row streaming code exists once).  Returns 0 when no row is violated by
 // more than tolp.
@@ -437,6 +462,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
             }
             if (apply_only) { apply_only = false; break; }
             if (full) {
+                AS_DBG(7, 1);
                 const unsigned freem = ~amask & slots;
                 if (na >= n || !freem) { w.ictl()[2] = 3; return RTMPC_FALLBACK; }
                 const int s = __ffs(freem) - 1;
@@ -452,6 +478,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 break;
             }
             // partial step: the blocking row leaves the working set
+            AS_DBG(8, 1);
             as_mark(lane, w.act_row()[j1], w.act_sgn()[j1], false, actu, actl);
             as_downdate(w.Mo(), w.vo(), ms, hi, as_mrows(P), lane, j1);
             amask &= ~(1u << j1);
@@ -595,17 +622,33 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
 // instance's warm-start record (npad + 1 ints) or NULL; z_out_inst (its first z_rows entries are written) /
 // U_out_inst: this instance's outputs or NULL.  Returns the status; on RTMPC_FALLBACK nothing has been written.
 // (no __restrict__ on the instance pointers: the rollout kernel writes them from the same warp)
+// carry (rollout kernel only; NULL elsewhere): two ints that outlive the call, [0] = tag of the problem whose solve left
+// its certified working set and that set's inverse in w (0: nothing usable), [1] = the set's slot mask; carry_tag (> 0)
+// names P.  With a carry the warm start is the previous control step's working set AS IT IS, not moved one stage
+// earlier: M depends on the rows of the working set only, not on x_init, so the carried inverse is exact for it and the
+// solve starts with one mat-vec (multipliers at the new x_init) instead of |A| pivots.  Measured on the closed loops of
+// the benchmarks (profiles/r2_carried_inverse.md) the unmoved set is also the better guess: 2.0 rank-one changes per
+// constrained solve against 4.1 after moving the set (plus the 3.8 changes the move itself takes on a carried inverse).
+// The warm-start record is then used unmoved as well (first step of a ticket).  Results agree with the step-by-step
+// path to rounding, not bit for bit: the certificate is the same, but the certification refines the multipliers with M
+// as an approximate inverse, so the last bits follow M's history.
 template <int R2, int ILP>
 __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int lane, const double* x_init,
                                                  const double* ref, int* warm_inst, double* z_out_inst, int z_rows,
-                                                 double* U_out_inst, ASCounters& cnt) {
+                                                 double* U_out_inst, ASCounters& cnt, int* carry = nullptr,
+                                                 int carry_tag = 0) {
     const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ms = as_ms(P);
     const double tolp = 1e-11 * P.sc_b;
     if (lane < nx) {
         w.xr()[lane] = x_init[lane];
         w.xr()[8 + lane] = ref ? ref[lane] : 0.0;
     }
+    // the previous solve of this instance was for this problem and left (M, slots) behind
+    bool carried = carry && carry[0] == carry_tag;
+    const unsigned carried_mask = carried ? (unsigned)carry[1] : 0u;
+    bool m_clean = carried && carried_mask == 0u;       // M is known to hold zeros only
     __syncwarp();
+    if (carry && lane == 0) carry[0] = 0;                // (set again when this solve ends with a certified working set)
     bool par_bad = false;
 #pragma unroll 1
     for (int i = lane; i < P.np; i += 32) {
@@ -670,30 +713,36 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             const bool feasible_u = !__any_sync(RTMPC_FULL_MASK, touched);
             __syncwarp();
             if (par_bad) { status = RTMPC_INFEASIBLE; break; }
-            if (feasible_u) break;                        // the unconstrained minimiser is feasible
-        }
-        // M starts empty
-        if (lane < npad) {
-            if (lane < as_mrows(P)) {
-                double* row = w.M() + lane * ms;
-#pragma unroll 1
-                for (int b = 0; b < npad; b += 2) *reinterpret_cast<double2*>(row + b) = make_double2(0.0, 0.0);
+            if (feasible_u) {                             // the unconstrained minimiser is feasible
+                if (carry && !m_clean) as_clear(w, P, lane);      // the empty working set is carried with an empty M
+                break;
             }
-            w.act_row()[lane] = 0;
-            w.act_sgn()[lane] = 0;
         }
-        __syncwarp();
+        // ---- 1a. carried working set and inverse: nothing to build ---------------------------------------------
+        bool moved = false;
+        AS_DBG(0, 1);
+        if (first && carried) {
+            AS_DBG(1, 1);
+            moved = true;
+            amask = carried_mask;
+            if ((amask >> lane) & 1u) { sl.ra = w.act_row()[lane]; sl.sa = (double)w.act_sgn()[lane]; }
+        }
+        const bool on_carried = moved;
+        carried = false;
+        m_clean = false;
+        // M starts empty
+        if (!moved) as_clear(w, P, lane);
         // ---- 1. candidates: the previous step's working set moved one stage (warm start), or the current one ----
-        {
+        if (!moved) {
             int prow = -1;
             double psg = 1.0;
             if (first) {
-                const int wn = (warm_inst && P.shift) ? warm_inst[0] : 0;
+                const int wn = (warm_inst && (P.shift || carry)) ? warm_inst[0] : 0;
                 if (lane < wn && lane < n) {
                     const int code = warm_inst[1 + lane];
                     const int row0 = code >> 1;
                     psg = (code & 1) ? -1.0 : 1.0;
-                    if (row0 >= 0 && row0 < mpad) prow = P.shift[row0];
+                    if (row0 >= 0 && row0 < mpad) prow = carry ? row0 : P.shift[row0];
                     // kept if the row has that bound
                     if (prow >= 0 && ((psg > 0) ? !(P.upI[prow] < 0.5 * RTMPC_INF) : !(P.loI[prow] > -0.5 * RTMPC_INF))) prow = -1;
                 }
@@ -712,9 +761,10 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             sl.ra = 0; sl.sa = 0.0; sl.lam = 0.0;
             __syncwarp();
         }
+        actu = 0; actl = 0;
         bool apply = false;
-        if (nc > 0) {
-            {
+        if (nc > 0 || (moved && amask)) {
+            if (!moved) {
                 // candidate c sits in slot c: S = signed sub-matrix of W, inverted in place
                 const int hi = (nc + 3) & ~3;
                 double diag0 = 1.0;
@@ -728,6 +778,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                     diag0 = Wa[sl.ra];
                 }
                 __syncwarp();
+                AS_DBG(5, 1); AS_DBG(6, nc);
                 const unsigned dead = as_invert(w.Mo(), ms, nc, hi, lane, diag0);
                 amask = (((nc >= 32) ? 0xffffffffu : ((1u << nc) - 1u))) & ~dead;
                 cnt.sq += nc * nc * nc / 2;
@@ -759,6 +810,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                     sl.lam = occ ? fmax(lamv, 0.0) : 0.0;
                     break;
                 }
+                AS_DBG(9, 1);
                 as_downdate(w.Mo(), w.vo(), ms, hi, as_mrows(P), lane, lm.idx);
                 amask &= ~(1u << lm.idx);
                 cnt.sq += na * na;
@@ -781,7 +833,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
         // answered by certification, which recomputes e exactly; a stall on exact values means the rows contradict
         // each other by `stall_cp`: up to 1e-8 (relative, the reference solver's own feasibility tolerance) the
         // solve carries on with that much slack and reports RTMPC_OPTIMAL_INACCURATE.
-        w.ictl()[0] = cnt.steps;
+        w.ictl()[0] = on_carried ? -(1 << 20) : cnt.steps;      // (a contradiction found on a carried inverse is never believed)
         w.ictl()[1] = -1;
 #pragma unroll 1
         for (int refresh = 0;; ++refresh) {
@@ -858,6 +910,12 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                 z_out_inst[i] = has_sol ? acc : nanv;
             }
         }
+    }
+    AS_DBG(16 + __popc(amask), 1);
+    if (carry && lane == 0) {
+        // (M, slots) of a certified working set stay in w for the next control step of this instance
+        carry[1] = (int)amask;
+        carry[0] = (status == RTMPC_OPTIMAL || status == RTMPC_OPTIMAL_INACCURATE) ? carry_tag : 0;
     }
     if (warm_inst) {
         // certified working set, compacted (the slots are sparse)

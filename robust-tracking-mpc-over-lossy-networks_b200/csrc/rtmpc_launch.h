@@ -38,6 +38,7 @@ struct Tuning {
     int rollout_quantum = 25;   // control steps per ticket of the time-sliced rollout; 0: whole chains per warp
     int rollout_warps = 0;      // warps per CTA of the rollout kernel; 0: automatic
     int as_warps = 0;           // cap on the warps per CTA of the active-set solve kernel; 0: automatic
+    int rollout_carry = 1;      // 1: the rollout carries each instance's working set and its inverse from one control step to the next
 };
 Tuning& tuning();
 
@@ -75,6 +76,9 @@ struct RolloutArgs {
     int* next;
     int* done;
     int quantum;
+    int carry;                    // 1: warm starts on the working set and inverse carried from the previous control step
+                                  //    (as_solve_instance); 0: moved one stage and inverted from scratch every step
+    int refresh;                  // the carried inverse is dropped at control steps t with t % refresh == 0 (0: never)
     unsigned long long* stats;    // [8] status counts[4], IPM iterations, active-set steps, rounds, flops (or NULL)
 };
 bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err);

@@ -49,7 +49,7 @@ struct LoopGlobalState {
     __device__ __forceinline__ int& last_loss() const { return L->last_loss[b]; }
     __device__ __forceinline__ int& gamma_last() const { return L->gamma_last[b]; }
 };
-// shared-memory block: x[8] x_nom[8] x_hat[8] u_last[4] err_acc tube_max | 6 ints (+2 pad) | buf[(N+1) nu]
+// shared-memory block: x[8] x_nom[8] x_hat[8] u_last[4] err_acc tube_max | 6 ints + 2 ints of the rollout's carried working set (tag, slot mask) | buf[(N+1) nu]
 // (fixed offsets on purpose: offsets that depend on nx cost registers the rollout kernel does not have)
 __host__ __device__ inline int loop_even(int v) { return (v + 1) & ~1; }
 constexpr int LOOP_SMEM_FIXED = 3 * LOOP_MAX_NX + LOOP_MAX_NU + 2 + 4;

@@ -14,6 +14,14 @@
 
 namespace rtmpc {
 
+#ifdef RTMPC_AS_DEBUG
+extern "C" int rtmpc_debug_counters(unsigned long long* out, int reset) {
+    if (cudaMemcpyFromSymbol(out, g_as_dbg, sizeof(g_as_dbg)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_as_dbg, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 // per-warp shared memory of the rollout, in doubles:
 //   closed-loop state | packet payload | x_nom_0 of this step's solve | warm-start record of each QP | solver scratch
 __host__ __device__ inline int rollout_fixed_doubles(const QPDev& P0, const QPDev& P1, bool two) {
@@ -27,14 +35,40 @@ __host__ __device__ inline int rollout_warp_doubles(const QPDev& P0, const QPDev
 
 // P0: the controller's problem; P1: the "packet received" problem of ExtendedTubeTrackingMPC, chosen per step and
 // instance on gamma_{t-1} (TubeTrackingMPC.py:307-349); P1 == P0 for the single-problem controllers.
+// Hand-over of an instance between warps of different SMs.  Everything the previous owner wrote is read by the next one with
+// ld.global.cg (served by L2, the point of coherence, and never allocated in L1), so no stale L1 line can exist and the
+// reader needs no acquire: ld.acquire.gpu / fence.*.gpu make ptxas emit CCTL.IVALL, which throws away the SM's whole L1 -
+// the shared tables of all 16 warps - at every ticket (twice per ticket with __threadfence on both sides: L1 hit rate
+// 85.8 % -> 81.9 % when time slicing came in).  The writer releases (MEMBAR.ALL.GPU + strong store, no invalidation): the
+// other lanes' stores are ordered before lane 0's release by the __syncwarp in front of it (cumulativity).
+#ifndef RTMPC_RO_FENCE
+#define RTMPC_RO_FENCE 0      // 1: the round-1 hand-over (two __threadfence per ticket), kept for A/B measurements
+#endif
+__device__ __forceinline__ int rollout_ld_relaxed(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rollout_st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ int rollout_take_next(int* next, int lane) {
     int v = 0;
     if (lane == 0) v = atomicAdd(next, 1);
     return __shfl_sync(RTMPC_FULL_MASK, v, 0);
 }
 
+#ifndef RTMPC_RO_MAXW5
+#define RTMPC_RO_MAXW5 16      // warps per CTA of the cartpole-sized instantiation (development knob)
+#endif
+#ifdef RTMPC_RO_MAXNREG
+#define RTMPC_RO_BOUNDS __maxnreg__(RTMPC_RO_MAXNREG)
+#else
+#define RTMPC_RO_BOUNDS __launch_bounds__(MAXW * 32, 1)
+#endif
 template <int R2, int MAXW>
-__global__ void __launch_bounds__(MAXW * 32, 1)
+__global__ void RTMPC_RO_BOUNDS
 rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
@@ -59,8 +93,13 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
     // (instance, chunk) from a global counter; all slots stay busy until the work runs out (1.73 chain lengths).  A ticket
     // waits for the previous ticket of its instance (`done`), which an earlier draw - a warp that is running - holds.
     // State written by one SM is read by another: these loads go to L2 (__ldcg), the hand-over is fence + flag.
+    // Tickets end at multiples of the quantum in ABSOLUTE time, and the carried working-set inverse of as_solve_instance is
+    // dropped at multiples of a.refresh (= the configured quantum, also when the chains are not sliced): where an inverse
+    // is built from scratch does then not depend on the launch shape, so sliced and whole chains, any cut of the batch and
+    // any number of GPUs give the same bits.
     const int Q = a.quantum;
-    const int nchunks = Q > 0 ? (a.T - a.t0 + Q - 1) / Q : 1;
+    const int c0 = Q > 0 ? a.t0 / Q : 0;
+    const int nchunks = Q > 0 ? (a.T + Q - 1) / Q - c0 : 1;
     const long long ntickets = (long long)a.B * nchunks;
     const int first_wave = gridDim.x * wpb;       // the first tickets are dealt statically: consecutive instances on different SMs
 #pragma unroll 1
@@ -68,12 +107,14 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
          ticket = (long long)first_wave + rollout_take_next(a.next, lane)) {
         const int inst = (int)(ticket % a.B), chunk = (int)(ticket / a.B);
         if (chunk > 0) {
-            if (lane == 0) while (*reinterpret_cast<volatile int*>(a.done + inst) < chunk) __nanosleep(128);
+            if (lane == 0) while (rollout_ld_relaxed(a.done + inst) < chunk) __nanosleep(128);
             __syncwarp();
+#if RTMPC_RO_FENCE
             __threadfence();
+#endif
         }
         int t = __ldcg(a.inst_t + inst);
-        const int t_stop = Q > 0 ? min(a.T, a.t0 + (chunk + 1) * Q) : a.T;
+        const int t_stop = Q > 0 ? min(a.T, (c0 + chunk + 1) * Q) : a.T;
         bool have = __ldcg(a.pending + inst) != 0;       // this step was solved by the interior-point kernel ...
         const bool parked = have && __ldcg(a.status + inst) <= RTMPC_FALLBACK;     // ... or is still waiting for it
         if (t < t_stop && !parked) {
@@ -102,11 +143,17 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
             S.q_t() = __ldcg(L.q_t + inst); S.s_t() = __ldcg(L.s_t + inst); S.Theta() = __ldcg(L.Theta + inst);
             S.alive() = __ldcg(L.alive + inst);
             S.last_loss() = __ldcg(L.last_loss + inst); S.gamma_last() = __ldcg(L.gamma_last + inst);
+            S.ints()[6] = 0;          // carried working set / inverse of as_solve_instance: none at the start of a ticket
+            S.ints()[7] = 0;
         }
         __syncwarp();
 #pragma unroll 1
         for (; t < t_stop; ++t) {
             if (!S.alive()) { t = a.T; break; }
+            if (a.refresh > 0 && t % a.refresh == 0) {
+                if (lane == 0) S.ints()[6] = 0;
+                __syncwarp();
+            }
             const int k = t - a.t0;
             const double* ref_t = a.ref ? a.ref + (size_t)k * a.ref_stride_t + (size_t)inst * a.ref_stride_b : nullptr;
             int status;
@@ -125,7 +172,8 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
                 ASWarp w = as_carve(scratch, P);
                 status = as_solve_instance<R2, (MAXW * R2 <= 100) ? 2 : 1>(P, w, lane, &S.x_hat(0), ref_t,
                                                                          recv ? warm1_s : warm0_s, ext ? x0_s : nullptr,
-                                                                         nx, U_s, cnt);
+                                                                         nx, U_s, cnt, a.carry ? S.ints() + 6 : nullptr,
+                                                                         recv ? 2 : 1);
                 n_steps += cnt.steps; n_rounds += cnt.rounds; n_flops += as_flops(P, cnt, false);
                 if (status == RTMPC_FALLBACK) {
                     if (lane == 0) {
@@ -184,16 +232,18 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
         }
         }   // (ticket had work)
         // hand the instance on: everything this warp wrote is visible before the flag moves
+#if RTMPC_RO_FENCE
         __threadfence();
+#endif
         __syncwarp();
-        if (Q > 0 && lane == 0) *reinterpret_cast<volatile int*>(a.done + inst) = chunk + 1;
+        if (Q > 0 && lane == 0) rollout_st_release(a.done + inst, chunk + 1);
     }
 }
 
 typedef void (*ro_fn)(QPDev, QPDev, LoopDev, RolloutArgs);
 struct RoChoice { int r2, maxw; ro_fn fn; };
 static const RoChoice kRo[] = {
-    {2, 24, rollout_kernel<2, 24>},  {5, 16, rollout_kernel<5, 16>},  {9, 16, rollout_kernel<9, 16>},
+    {2, 24, rollout_kernel<2, 24>},  {5, RTMPC_RO_MAXW5, rollout_kernel<5, RTMPC_RO_MAXW5>},  {9, 16, rollout_kernel<9, 16>},
     {12, 16, rollout_kernel<12, 16>}, {16, 16, rollout_kernel<16, 16>},
 };
 static const RoChoice* pick(int mpad) {
@@ -231,6 +281,8 @@ cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, in
     int warps = balanced_warps(a.B, num_sms, wpb);
     RolloutArgs b = a;
     const Tuning& tn = tuning();
+    b.carry = tn.rollout_carry;
+    b.refresh = tn.rollout_carry ? tn.rollout_quantum : 0;
     // more chains than warp slots: slice them (see the kernel) and use every slot
     const int q = tn.rollout_quantum;
     bool sliced = q > 0 && (long long)a.B > (long long)num_sms * wpb && a.T - a.t0 >= 2 * q;

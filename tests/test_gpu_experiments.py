@@ -27,7 +27,8 @@ def test_linear_system_experiment_statistics():
     loop = RemoteLoop(tube, 1, kind="tube", w_half=hw, Z=Z)
     loop.reset(np.zeros((1, 4)))
     loop.run(T, np.array([0.5, 0, 0, 0]), p_loss=np.array([0.5]), seed=11, id_offset=1 * n_mc + 2, fused=False)
-    assert abs(loop.tracking_error(T).item() - res.tracking_error_tube[1, 2]) == 0.0
+    # (to rounding: the experiment's rollout carries its working-set inverse from step to step, RTMPC_TUNE_ROLLOUT_CARRY)
+    assert abs(loop.tracking_error(T).item() - res.tracking_error_tube[1, 2]) <= 1e-10
     # R-MPC: NaN exactly where the controller became infeasible
     assert np.array_equal(np.isnan(res.tracking_error_track).sum(axis=1), res.is_track_infeasible)
     again = linear_system_experiment(tube, track, Z, hw, prob_packet_loss=probs, n_mc=n_mc, T=T, seed=11)

@@ -25,6 +25,10 @@ def run(label, mpc, kind, B, T, refs, w_half, Z, nx, plant="linear", p_max=0.9):
           f"ipm iterations {st[4]} steps/solve {st[5]/(B*T):.2f}; alive {int(loop.alive.sum().item())}/{B}; max tube {tube:.3e}", flush=True)
 
 
+if os.environ.get("CARRY"):
+    from rtmpc_b200 import _lib
+    _lib.set_tuning(_lib.TUNE_ROLLOUT_CARRY, int(os.environ["CARRY"]))
+    print("rollout carry mode", os.environ["CARRY"])
 which = os.environ.get("STRESS", "cp,cp_const,cp_ext,cp_track,di").split(",")
 s = H.load("sets_cp.npz")
 T = 2000
