@@ -135,6 +135,15 @@ __device__ __forceinline__ unsigned long long as_flops(const QPDev& P, const ASC
     return f;
 }
 
+// the same count for `solves` solves whose counters were summed into c (as_flops is linear in them)
+__device__ __forceinline__ unsigned long long as_flops_total(const QPDev& P, const ASCounters& c, unsigned solves) {
+    const unsigned long long n = P.n, m = P.m, nx = P.nx;
+    unsigned long long f = (unsigned long long)solves * (2ull * n * 2 * nx + 2ull * m * 4 * nx + 2ull * (unsigned long long)((P.N + 1) * P.nu) * (n + nx));
+    f += 2ull * m * (unsigned long long)c.rows + 2ull * (unsigned long long)c.sq;
+    f += (unsigned long long)c.rounds * (2ull * m * n + 12ull * n * n);
+    return f;
+}
+
 // Warp reductions.  Maxima / arg-maxima go through the integer reduction unit (REDUX) on an
 // order-preserving 64-bit key, two 32-bit halves: a handful of instructions instead of five shuffle stages.
 __device__ __forceinline__ unsigned long long as_key(double v) {
@@ -507,35 +516,36 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
     const double* __restrict__ Ga = P.G + (size_t)(occ ? sl.ra : 0) * npad;
     double lam = 0.0, resid = 0.0;
     double zj = (lane < n) ? w.zu()[lane] : 0.0;
-    if (lane < npad) w.z()[lane] = zj;
-    __syncwarp();
-    // pass 0 evaluates the residual at z_u, passes 1..3 refine
+    // pass 0 starts from the multipliers the Goldfarb-Idnani steps arrived at (usually already within the certificate's
+    // tolerance of the true rows: one pass instead of two), passes 1..3 refine with M as approximate inverse
 #pragma unroll 1
     for (int pass = 0; pass < 4; ++pass) {
-        if (pass > 0) {
+        double dl;
+        if (pass == 0) dl = occ ? sl.lam : 0.0;
+        else {
             if (lane < npad) w.v()[lane] = resid;
             __syncwarp();
-            const double dl = occ ? as_matvec(w.Mo(), ms, hi, lane, w.vo()) : 0.0;
-            lam += dl;
-            if (lane < npad) w.coef()[lane] = dl * sl.sa;
-            __syncwarp();
-            if (lane < n) {
-                double z2 = 0.0;
-#pragma unroll 1
-                for (unsigned mk = amask; mk;) {
-                    const int a = __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    const int a2 = mk ? __ffs(mk) - 1 : a;
-                    const double cb = mk ? w.coef()[a2] : 0.0;
-                    mk &= mk - 1;
-                    zj = fma(-w.coef()[a], P.Y[(size_t)w.act_row()[a] * npad + lane], zj);
-                    z2 = fma(-cb, P.Y[(size_t)w.act_row()[a2] * npad + lane], z2);
-                }
-                zj += z2;
-            }
-            if (lane < npad) w.z()[lane] = zj;
-            __syncwarp();
+            dl = occ ? as_matvec(w.Mo(), ms, hi, lane, w.vo()) : 0.0;
         }
+        lam += dl;
+        if (lane < npad) w.coef()[lane] = dl * sl.sa;
+        __syncwarp();
+        if (lane < n) {
+            double z2 = 0.0;
+#pragma unroll 1
+            for (unsigned mk = amask; mk;) {
+                const int a = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const int a2 = mk ? __ffs(mk) - 1 : a;
+                const double cb = mk ? w.coef()[a2] : 0.0;
+                mk &= mk - 1;
+                zj = fma(-w.coef()[a], P.Y[(size_t)w.act_row()[a] * npad + lane], zj);
+                z2 = fma(-cb, P.Y[(size_t)w.act_row()[a2] * npad + lane], z2);
+            }
+            zj += z2;
+        }
+        if (lane < npad) w.z()[lane] = zj;
+        __syncwarp();
         resid = 0.0;
         if (occ) {
             double a0 = 0.0, a1 = 0.0;
@@ -548,7 +558,7 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
             resid = sl.sa * (a0 + a1) - ba;
         }
         // converged (every active row on its bound to well below the certificate's tolerance): stop refining
-        if (pass >= 1 && !(as_wmax(fabs(resid)) > 1e-3 * w.ctl()[0])) break;
+        if (!(as_wmax(fabs(resid)) > 1e-3 * w.ctl()[0])) break;
     }
     cnt.rounds += 1;
     // exact row values at z:  e = G z - up through the transposed copies (coalesced 16-byte loads)
@@ -573,9 +583,9 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
     if (ILP >= 2) {
         // three columns per pass keep 3*R2 loads in flight
 #pragma unroll 1
-        for (int k = 0; k < npad; k += 3) {
-            const int k1 = (k + 1 < npad) ? k + 1 : k, k2 = (k + 2 < npad) ? k + 2 : k;
-            const double z0 = w.z()[k], z1 = (k + 1 < npad) ? w.z()[k1] : 0.0, z2 = (k + 2 < npad) ? w.z()[k2] : 0.0;
+        for (int k = 0; k < n; k += 3) {
+            const int k1 = (k + 1 < n) ? k + 1 : k, k2 = (k + 2 < n) ? k + 2 : k;
+            const double z0 = w.z()[k], z1 = (k + 1 < n) ? w.z()[k1] : 0.0, z2 = (k + 2 < n) ? w.z()[k2] : 0.0;
             const double* __restrict__ g0 = P.GT + (size_t)k * mpad + 2 * lane;
             const double* __restrict__ g1 = P.GT + (size_t)k1 * mpad + 2 * lane;
             const double* __restrict__ g2 = P.GT + (size_t)k2 * mpad + 2 * lane;

@@ -67,7 +67,10 @@ __device__ __forceinline__ int rollout_take_next(int* next, int lane) {
 #else
 #define RTMPC_RO_BOUNDS __launch_bounds__(MAXW * 32, 1)
 #endif
-template <int R2, int MAXW>
+// TWO = false: one problem (every controller but ExtendedTubeTrackingMPC).  The solver then reads the problem description
+// straight from the kernel's parameter bank (constant operands inside the instructions); with two problems every field
+// access is an indexed constant load into a register first - 1.2 % of the executed instructions plus their latency.
+template <int R2, int MAXW, bool TWO>
 __global__ void RTMPC_RO_BOUNDS
 rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -76,7 +79,7 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
     const int wpb = blockDim.x >> 5;
     const int nx = P0.nx, nu = P0.nu;
     const int usz = (P0.N + 1) * nu;
-    const bool two = a.two != 0;
+    constexpr bool two = TWO;
     double* wbase = smem + (size_t)warp * rollout_warp_doubles(P0, P1, two);
     LoopSmemState S;
     S.base = wbase;
@@ -118,8 +121,15 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
         bool have = __ldcg(a.pending + inst) != 0;       // this step was solved by the interior-point kernel ...
         const bool parked = have && __ldcg(a.status + inst) <= RTMPC_FALLBACK;     // ... or is still waiting for it
         if (t < t_stop && !parked) {
-        unsigned n_status[4] = {0, 0, 0, 0}, n_ipm = 0, n_steps = 0, n_rounds = 0;
-        unsigned long long n_flops = 0;
+        // per-ticket statistics: status counts packed 16 bits each (flushed before they can overflow), solver counters summed
+        // over the ticket's solves (the flop count is linear in them: evaluated once per ticket, as_flops)
+        unsigned long long n_status = 0;
+        unsigned n_ipm = 0, n_rounds = 0, n_solves0 = 0, n_solves1 = 0;
+        ASCounters tot0, tot1;
+        tot0.steps = tot0.rounds = tot0.rows = tot0.sq = 0;
+        tot1 = tot0;
+        int last = -1;            // packed iteration word | status of the last solve, stored when the ticket ends (-1: nothing to store)
+        int next_refresh = a.refresh > 0 ? ((t + a.refresh - 1) / a.refresh) * a.refresh : -1;
         double* traj_b = a.traj ? a.traj + (size_t)inst * a.traj_stride : nullptr;
         const double p = a.p_loss ? a.p_loss[inst] : 0.0;
         // ---- state, payload and warm-start records move on chip for the whole rollout -------------------
@@ -150,7 +160,12 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
 #pragma unroll 1
         for (; t < t_stop; ++t) {
             if (!S.alive()) { t = a.T; break; }
-            if (a.refresh > 0 && t % a.refresh == 0) {
+            if (((t + 1) & 0x7fff) == 0 && a.stats && lane == 0) {      // (whole chains of more than 65535 steps)
+                for (int i = 0; i < 4; ++i) if ((n_status >> (16 * i)) & 0xffffull) atomicAdd(a.stats + i, (n_status >> (16 * i)) & 0xffffull);
+                n_status = 0;
+            }
+            if (t == next_refresh) {
+                next_refresh += a.refresh;
                 if (lane == 0) S.ints()[6] = 0;
                 __syncwarp();
             }
@@ -168,13 +183,19 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
                 ASCounters cnt;
                 cnt.steps = 0; cnt.rounds = 0; cnt.rows = 0; cnt.sq = 0;
                 const bool recv = two && S.gamma_last() == 1;           // gamma of the previous step
-                const QPDev& P = recv ? P1 : P0;
+                const QPDev& P = (two && recv) ? P1 : P0;
                 ASWarp w = as_carve(scratch, P);
                 status = as_solve_instance<R2, (MAXW * R2 <= 100) ? 2 : 1>(P, w, lane, &S.x_hat(0), ref_t,
                                                                          recv ? warm1_s : warm0_s, ext ? x0_s : nullptr,
                                                                          nx, U_s, cnt, a.carry ? S.ints() + 6 : nullptr,
                                                                          recv ? 2 : 1);
-                n_steps += cnt.steps; n_rounds += cnt.rounds; n_flops += as_flops(P, cnt, false);
+                if (two && recv) {
+                    tot1.steps += cnt.steps; tot1.rounds += cnt.rounds; tot1.rows += cnt.rows; tot1.sq += cnt.sq;
+                    n_solves1 += 1;
+                } else {
+                    tot0.steps += cnt.steps; tot0.rounds += cnt.rounds; tot0.rows += cnt.rows; tot0.sq += cnt.sq;
+                    n_solves0 += 1;
+                }
                 if (status == RTMPC_FALLBACK) {
                     if (lane == 0) {
                         a.status[inst] = recv ? RTMPC_FALLBACK - 1 : RTMPC_FALLBACK;     // which problem the hand-over is for
@@ -183,11 +204,12 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
                         for (int j = 0; j < nx; ++j) a.ref_pending[(size_t)inst * nx + j] = ref_t ? ref_t[j] : 0.0;
                         atomicAdd(a.n_pending, 1);
                     }
+                    last = -1;
                     break;
                 }
-                if (lane == 0) { a.status[inst] = status; a.iters[inst] = as_pack_iters(cnt, w); }
+                last = as_pack_iters(cnt, w) | (status & 0xf);     // (the low 12 bits of the word count interior-point iterations: 0 here)
             }
-            if (status >= 0 && status < 4) n_status[status] += 1;
+            if (status >= 0 && status < 4) n_status += 1ull << (16 * status);
             __syncwarp();
             // ---- closed-loop step ------------------------------------------------------------
             int go = 0;
@@ -222,11 +244,15 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
             L.q_t[inst] = S.q_t(); L.s_t[inst] = S.s_t(); L.Theta[inst] = S.Theta(); L.alive[inst] = S.alive();
             L.last_loss[inst] = S.last_loss(); L.gamma_last[inst] = S.gamma_last();
             a.inst_t[inst] = t;
+            if (last != -1) { a.status[inst] = last & 0xf; a.iters[inst] = last & ~0xf; }
             if (a.stats) {
-                for (int i = 0; i < 4; ++i) if (n_status[i]) atomicAdd(a.stats + i, (unsigned long long)n_status[i]);
+                for (int i = 0; i < 4; ++i) if ((n_status >> (16 * i)) & 0xffffull) atomicAdd(a.stats + i, (n_status >> (16 * i)) & 0xffffull);
                 if (n_ipm) atomicAdd(a.stats + 4, (unsigned long long)n_ipm);
+                const unsigned n_steps = tot0.steps + tot1.steps, n_rounds_as = tot0.rounds + tot1.rounds;
                 if (n_steps) atomicAdd(a.stats + 5, (unsigned long long)n_steps);
-                if (n_rounds) atomicAdd(a.stats + 6, (unsigned long long)n_rounds);
+                if (n_rounds + n_rounds_as) atomicAdd(a.stats + 6, (unsigned long long)(n_rounds + n_rounds_as));
+                unsigned long long n_flops = as_flops_total(P0, tot0, n_solves0);
+                if (two) n_flops += as_flops_total(P1, tot1, n_solves1);
                 if (n_flops) atomicAdd(a.stats + 7, n_flops);
             }
         }
@@ -241,11 +267,9 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
 }
 
 typedef void (*ro_fn)(QPDev, QPDev, LoopDev, RolloutArgs);
-struct RoChoice { int r2, maxw; ro_fn fn; };
-static const RoChoice kRo[] = {
-    {2, 24, rollout_kernel<2, 24>},  {5, RTMPC_RO_MAXW5, rollout_kernel<5, RTMPC_RO_MAXW5>},  {9, 16, rollout_kernel<9, 16>},
-    {12, 16, rollout_kernel<12, 16>}, {16, 16, rollout_kernel<16, 16>},
-};
+struct RoChoice { int r2, maxw; ro_fn fn[2]; };      // fn[1]: two problems
+#define RO_ENTRY(R2, W) {R2, W, {rollout_kernel<R2, W, false>, rollout_kernel<R2, W, true>}}
+static const RoChoice kRo[] = {RO_ENTRY(2, 24), RO_ENTRY(5, RTMPC_RO_MAXW5), RO_ENTRY(9, 16), RO_ENTRY(12, 16), RO_ENTRY(16, 16)};
 static const RoChoice* pick(int mpad) {
     const int r_need = (mpad + 63) / 64;
     for (const auto& c : kRo)
@@ -263,8 +287,11 @@ const char* rollout_kernel_name(const QPDev& P) {
 bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err) {
     const RoChoice* kc = pick(P.mpad);
     if (!kc) { *err = cudaSuccess; return false; }
-    *err = cudaFuncSetAttribute((const void*)kc->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    return *err == cudaSuccess;
+    for (int k = 0; k < 2; ++k) {
+        *err = cudaFuncSetAttribute((const void*)kc->fn[k], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (*err != cudaSuccess) return false;
+    }
+    return true;
 }
 
 // Time slicing makes warps wait for tickets held by warps of OTHER CTAs, which is only safe when every CTA of the grid
@@ -295,7 +322,7 @@ cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, in
         int dev = 0, coop = 0, per_sm = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kc->fn, warps * 32, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kc->fn[a.two ? 1 : 0], warps * 32, smem);
         if (e != cudaSuccess) return e;
         const long long fit = (long long)per_sm * num_sms;
         if (coop && fit >= 1) {
@@ -304,7 +331,7 @@ cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, in
             QPDev p0 = P, p1 = P1;
             LoopDev ld = L;
             void* args[] = {&p0, &p1, &ld, &b};
-            e = cudaLaunchCooperativeKernel((const void*)kc->fn, dim3(blocks), dim3(warps * 32), args, smem, stream);
+            e = cudaLaunchCooperativeKernel((const void*)kc->fn[a.two ? 1 : 0], dim3(blocks), dim3(warps * 32), args, smem, stream);
             if (e == cudaSuccess) return cudaGetLastError();
             if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorNotSupported) return e;
             (void)cudaGetLastError();            // co-residency refused: fall through to whole chains
@@ -314,7 +341,7 @@ cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, in
         blocks = (a.B + warps - 1) / warps;
         if (blocks > num_sms) blocks = num_sms;
     }
-    kc->fn<<<blocks, warps * 32, per_warp * warps, stream>>>(P, P1, L, b);
+    kc->fn[a.two ? 1 : 0]<<<blocks, warps * 32, per_warp * warps, stream>>>(P, P1, L, b);
     return cudaGetLastError();
 }
 

@@ -254,7 +254,9 @@ def test_multi_input_system_qp_and_rollout():
         loop.reset(np.tile([0.5, 0.0, 0.0], (64, 1)))
         tr = loop.run(60, np.array([1.0, 0.0, 0.0]), p_loss=np.linspace(0.0, 0.6, 64), seed=5, record=True, fused=fused)
         res[fused] = (tr.cpu().numpy(), loop.status_count.cpu().numpy())
-    assert np.array_equal(res[True][0], res[False][0]) and np.array_equal(res[True][1], res[False][1])
+    # (to rounding: the rollout warm-starts on its carried working-set inverse, RTMPC_TUNE_ROLLOUT_CARRY; tests/test_gpu_loop.py
+    # checks the bit-for-bit equality of the two paths with the knob at 0)
+    assert np.abs(res[True][0] - res[False][0]).max() <= 1e-9 and np.array_equal(res[True][1], res[False][1])
     assert res[True][1][0] == 64 * 60
     assert np.abs(res[True][0][:, -1, 0] - 1.0).max() < 0.2       # every loop tracks the reference
 
