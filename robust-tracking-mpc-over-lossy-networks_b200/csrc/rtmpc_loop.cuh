@@ -509,6 +509,170 @@ __device__ __forceinline__ void loop_step_body_warp(const LoopDev& L, const Stat
     if (traj_b && lane < nx) traj_b[(size_t)(t + 1) * nx + lane] = S.x(lane);
 }
 
+// The warp step with the sizes known at compile time (the reference's two systems: nx = 4 / 2, nu = 1).  Lane group
+// g = lane / NX takes one of the three mat-vecs (0: nominal model, 1: plant, 2: estimator), lane i = lane % NX its row i;
+// the scalars (inputs, flags) are computed redundantly in every lane.  Straight-line code, a third of the generic
+// version's instructions; every output element goes through the same FMA sequence as loop_step_body_t (same bits).
+template <int NX, int NU, class State>
+__device__ __forceinline__ void loop_step_body_warp_t(const LoopDev& L, const State S, int lane, int t, const double* Ub,
+                                                      const double* x_nom0_b, const double* ref_b, int theta_in,
+                                                      int gamma_in, const double* w_in_b, double p,
+                                                      unsigned long long seed, unsigned long long id, double* traj_b,
+                                                      double tube_worst) {
+    static_assert(3 * NX <= 32 && ((NX + 1) >> 1) + 1 <= 32, "lane groups");
+    const int N = L.N;
+    const int g = lane / NX, i = lane - g * NX;          // (NX is a compile-time constant)
+    // ---- statistics on the pre-step state ---------------------------------------------------------------
+    if (lane == 0) {
+        if (ref_b) {
+            double e = 0.0;
+#pragma unroll
+            for (int k = 0; k < NX; ++k) { const double d = S.x(k) - ref_b[k]; e = fma(d, d, e); }
+            S.err_acc() += e;
+        }
+        if (L.nz_rows > 0) S.tube_max() = fmax(S.tube_max(), tube_worst);
+    }
+    // ---- network and disturbance realisation ------------------------------------------------------------
+    int theta, gamma;
+    double wi = 0.0;                                     // lane NX + i (plant group): disturbance on state i
+    if (theta_in >= 0) {
+        theta = theta_in;
+        gamma = gamma_in;
+        if (g == 1 && w_in_b) wi = w_in_b[i];
+    } else {
+        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        Philox4 r;
+        r.x = r.y = r.z = r.w = 0u;
+        if (lane <= ((NX + 1) >> 1)) r = loop_philox((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)t, (uint32_t)lane, k0, k1);
+        const int th0 = (t == 0) ? 1 : (u01_from_bits(r.x, r.y) < p ? 0 : 1);
+        const int ga0 = (t == 0) ? 1 : (u01_from_bits(r.z, r.w) < p ? 0 : 1);
+        theta = __shfl_sync(0xffffffffu, th0, 0);
+        gamma = __shfl_sync(0xffffffffu, ga0, 0);
+        double wa = 0.0, wb = 0.0;
+        if (lane >= 1 && lane <= ((NX + 1) >> 1)) {
+            const int k = 2 * (lane - 1);
+            wa = __ldg(L.w_half + k) * (2.0 * u01_from_bits(r.x, r.y) - 1.0);
+            if (k + 1 < NX) wb = __ldg(L.w_half + k + 1) * (2.0 * u01_from_bits(r.z, r.w) - 1.0);
+        }
+        const int src = 1 + (i >> 1);
+        const double ga = __shfl_sync(0xffffffffu, wa, src), gb = __shfl_sync(0xffffffffu, wb, src);
+        if (g == 1) wi = (i & 1) ? gb : ga;
+    }
+    // ---- local side ---------------------------------------------------------------------------------------
+    const int q_pkt = S.q_t();
+    int last_loss = S.last_loss();
+    int Theta = 0;
+    if (theta == 1) Theta = (last_loss <= q_pkt) ? 1 : 0;
+    else last_loss = t;
+    int s_t = S.s_t();
+    double* buf = S.buf();
+    const bool smart = L.actuator == RTMPC_ACT_SMART, cons = L.actuator == RTMPC_ACT_CONSISTENT,
+               ext = L.actuator == RTMPC_ACT_EXTENDED;
+    __syncwarp();
+    if (Theta) {
+        s_t = t;
+        for (int k = lane; k < (N + 1) * NU; k += 32) buf[k] = Ub[k];
+        if (!smart && x_nom0_b && lane < NX) S.x_nom(lane) = x_nom0_b[lane];
+    }
+    __syncwarp();
+    const int kk = t - s_t;
+    double x[NX], xn[NX];
+#pragma unroll
+    for (int k = 0; k < NX; ++k) { x[k] = S.x(k); xn[k] = S.x_nom(k); }
+    double u_nom[NU], u[NU], uh[NU];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+        if (kk < N) u_nom[j] = buf[kk * NU + j];
+        else {
+            double acc = buf[N * NU + j];
+#pragma unroll
+            for (int k = 0; k < NX; ++k) acc = fma(-__ldg(L.K + j * NX + k), smart ? x[k] : xn[k], acc);
+            u_nom[j] = acc;
+        }
+        u[j] = u_nom[j];
+        if (!smart) {
+            double acc = u_nom[j];
+#pragma unroll
+            for (int k = 0; k < NX; ++k) acc = fma(-__ldg(L.Kp + j * NX + k), x[k] - xn[k], acc);
+            u[j] = acc;
+        }
+        // remote side's input estimate (plant packet content = pre-update values)
+        if (gamma == 1) {
+            double un;
+            if (kk < N) un = buf[kk * NU + j];
+            else {
+                double acc = buf[N * NU + j];
+#pragma unroll
+                for (int k = 0; k < NX; ++k) acc = fma(-__ldg(L.K + j * NX + k), (ext || cons) ? xn[k] : x[k], acc);
+                un = acc;
+            }
+            if (ext) {
+                double acc = un;
+#pragma unroll
+                for (int k = 0; k < NX; ++k) acc = fma(-__ldg(L.Kp + j * NX + k), x[k] - xn[k], acc);
+                un = acc;
+            }
+            uh[j] = un;
+        } else uh[j] = Ub[j];                                 // first input of the latest sent sequence
+    }
+    // ---- group g: row i of nominal model (0), plant (1), estimator (2) --------------------------------------
+    double out = 0.0;
+    const bool use_x0 = ext && x_nom0_b && gamma != 1;
+    if (g < 3) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) {
+            double v;
+            if (g == 0) v = xn[k];
+            else if (g == 1) v = x[k];
+            else if (gamma == 1) v = cons ? xn[k] : x[k];
+            else v = use_x0 ? x_nom0_b[k] : S.x_hat(k);
+            acc = fma(__ldg(L.A + i * NX + k), v, acc);
+        }
+#pragma unroll
+        for (int j = 0; j < NU; ++j) acc = fma(__ldg(L.Bm + i * NU + j), (g == 0) ? u_nom[j] : (g == 1) ? u[j] : uh[j], acc);
+        out = (g == 1) ? acc + wi : acc;
+        if (g == 0 && smart) out = S.x_nom(i);                // (no nominal model in Pezzutto's scheme)
+    }
+    double xc[4] = {0.0, 0.0, 0.0, 0.0};
+    const bool cart = L.plant == RTMPC_PLANT_CARTPOLE;
+    if (NX == 4 && cart && lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xc[k] = x[k < NX ? k : 0];
+        cartpole_substeps(xc, u[0], L.cart);
+    }
+    __syncwarp();
+    // ---- write back -----------------------------------------------------------------------------------------
+    if (g == 0) S.x_nom(i) = out;
+    else if (g == 1) { if (!cart) S.x(i) = out; }
+    else if (g == 2) S.x_hat(i) = out;
+    if (lane == 0) {
+        if (NX == 4 && cart) for (int k = 0; k < 4; ++k) S.x(k) = xc[k];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) S.u_last(j) = u[j];
+        if (gamma == 1) S.q_t() = t;
+        S.s_t() = s_t;
+        S.Theta() = Theta;
+        S.last_loss() = last_loss;
+        S.gamma_last() = gamma;
+    }
+    __syncwarp();
+    if (traj_b && lane < NX) traj_b[(size_t)(t + 1) * NX + lane] = S.x(lane);
+}
+
+template <class State>
+__device__ __forceinline__ void loop_step_warp(const LoopDev& L, const State S, int lane, int t, const double* Ub,
+                                               const double* x_nom0_b, const double* ref_b, int theta_in, int gamma_in,
+                                               const double* w_in_b, double p, unsigned long long seed,
+                                               unsigned long long id, double* traj_b, double tube_worst) {
+    if (L.nx == 4 && L.nu == 1)
+        loop_step_body_warp_t<4, 1>(L, S, lane, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
+    else if (L.nx == 2 && L.nu == 1)
+        loop_step_body_warp_t<2, 1>(L, S, lane, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
+    else
+        loop_step_body_warp(L, S, lane, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
+}
+
 #ifdef RTMPC_LOOP_KERNELS   // the non-template kernels are compiled in one translation unit (rtmpc_capi.cu)
 __global__ void loop_step_kernel(LoopDev L, int B, int t, const double* __restrict__ U_t,
                                  const int* __restrict__ status, const double* __restrict__ x_nom0,

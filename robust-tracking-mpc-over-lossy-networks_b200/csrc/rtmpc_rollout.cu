@@ -219,7 +219,7 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
                 double worst = 0.0;
                 if (L.nz_rows > 0) worst = as_wmax(loop_tube_rows(L, S, lane, 32));
                 const bool expl = a.theta != nullptr;
-                loop_step_body_warp(L, S, lane, t, U_s, ext ? x0_s : nullptr, ref_t,
+                loop_step_warp(L, S, lane, t, U_s, ext ? x0_s : nullptr, ref_t,
                                     expl ? a.theta[(size_t)k * a.B + inst] : -1, expl ? a.gamma[(size_t)k * a.B + inst] : -1,
                                     (expl && a.w) ? a.w + ((size_t)k * a.B + inst) * nx : nullptr, p, a.seed,
                                     (unsigned long long)(a.id_offset + inst), traj_b, worst);
