@@ -118,7 +118,11 @@ __device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, const State
     for (int k = 0; k < AX; ++k) d[k] = (k < nx) ? S.x(k) - S.x_nom(k) : 0.0;
     double worst = -1e300;
     const bool sym = L.tube_sym != 0;
-#pragma unroll 4
+#ifndef RTMPC_TUBE_UNROLL
+#define RTMPC_TUBE_UNROLL 1     // rolled: the rollout kernel is bound by instruction fetch (4: 84.6, 2: 86.7, 1: 87.2 M solves/s)
+#endif
+    constexpr int kUnroll = RTMPC_TUBE_UNROLL;
+#pragma unroll kUnroll
     for (int i = first; i < L.nz_rows; i += stride) {
         double acc = sym ? 0.0 : -__ldg(L.hz + i);
         if (NX > 0 && (NX & 1) == 0) {
@@ -617,18 +621,17 @@ __device__ __forceinline__ void loop_step_body_warp_t(const LoopDev& L, const St
     }
     // ---- group g: row i of nominal model (0), plant (1), estimator (2) --------------------------------------
     double out = 0.0;
-    const bool use_x0 = ext && x_nom0_b && gamma != 1;
     if (g < 3) {
+        // the vector this group multiplies: one pointer select instead of a select per element
+        const double* src = &S.x_nom(0);
+        if (g == 1) src = &S.x(0);
+        else if (g == 2) {
+            if (gamma == 1) src = cons ? &S.x_nom(0) : &S.x(0);
+            else src = (ext && x_nom0_b) ? x_nom0_b : &S.x_hat(0);
+        }
         double acc = 0.0;
 #pragma unroll
-        for (int k = 0; k < NX; ++k) {
-            double v;
-            if (g == 0) v = xn[k];
-            else if (g == 1) v = x[k];
-            else if (gamma == 1) v = cons ? xn[k] : x[k];
-            else v = use_x0 ? x_nom0_b[k] : S.x_hat(k);
-            acc = fma(__ldg(L.A + i * NX + k), v, acc);
-        }
+        for (int k = 0; k < NX; ++k) acc = fma(__ldg(L.A + i * NX + k), src[k], acc);
 #pragma unroll
         for (int j = 0; j < NU; ++j) acc = fma(__ldg(L.Bm + i * NU + j), (g == 0) ? u_nom[j] : (g == 1) ? u[j] : uh[j], acc);
         out = (g == 1) ? acc + wi : acc;
