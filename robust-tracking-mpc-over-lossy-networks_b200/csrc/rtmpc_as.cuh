@@ -92,6 +92,20 @@ __device__ __forceinline__ ASWarp as_carve(double* base, const QPDev& P) {
     return w;
 }
 
+// The small dense helpers are inlined at their call sites.  (Round 1 made them real calls, which paid when the kernel was
+// 16 k instructions; with the kernel at half that size the call / return jumps cost more instruction fetches than the
+// copies: all three inlined 88.5 -> 92.6 M solves/s, reductions as calls 84.6 -> 80.1; RTMPC_AS_CALLS restores the calls.)
+#ifdef RTMPC_AS_CALLS
+#define AS_FN_MATVEC static __device__ __noinline__
+#define AS_FN_BORDER static __device__ __noinline__
+#define AS_FN_DOWNDATE static __device__ __noinline__
+#define AS_FN_INVERT static __device__ __noinline__
+#else
+#define AS_FN_MATVEC __device__ __forceinline__
+#define AS_FN_BORDER __device__ __forceinline__
+#define AS_FN_DOWNDATE __device__ __forceinline__
+#define AS_FN_INVERT __device__ __forceinline__
+#endif
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 // 16-byte read-only loads with an L1 policy.  The shared tables (1.3 MB for the cartpole) go through a ~118 KB L1 that
 // 16 warps at different points of their solves compete for; what is streamed once per use should not evict what every
@@ -196,7 +210,7 @@ struct ASSlot { int ra; double sa, lam; };
 // out_a = sum_b M[a][b] vec[b] over the slots below hi (free slots hold zeros)
 // (the helpers below are real calls; they address the per-warp block through offsets into the dynamic shared memory
 //  array so that their loads and stores are shared-memory instructions, not generic ones)
-static __device__ __noinline__ double as_matvec(int Mo, int ms, int hi, int lane, int vo) {
+AS_FN_MATVEC double as_matvec(int Mo, int ms, int hi, int lane, int vo) {
     extern __shared__ __align__(16) double as_smem[];
     double s0 = 0.0, s1 = 0.0;
     if (lane < hi) {
@@ -218,7 +232,7 @@ static __device__ __noinline__ double as_matvec(int Mo, int ms, int hi, int lane
 // M grows by slot s:  [[M + r r'/kappa, -r/kappa], [-r'/kappa, 1/kappa]]   (r in rv, zero on free slots;
 // hi = even number of slots covering every occupied one and s)
 // (nr = rows of M: hi is a multiple of 4 and may reach past them; those slots are never occupied)
-static __device__ __noinline__ void as_border(int Mo, int rvo, int ms, int hi, int nr, int lane, int s, double r_own, double kappa) {
+AS_FN_BORDER void as_border(int Mo, int rvo, int ms, int hi, int nr, int lane, int s, double r_own, double kappa) {
     extern __shared__ __align__(16) double as_smem[];
     double* M = as_smem + Mo;
     const double* rv = as_smem + rvo;
@@ -253,7 +267,7 @@ static __device__ __noinline__ void as_border(int Mo, int rvo, int ms, int hi, i
 }
 
 // slot j leaves:  M <- M - m_j m_j' / M_jj, row and column j cleared (tmp: npad doubles of scratch)
-static __device__ __noinline__ void as_downdate(int Mo, int tmpo, int ms, int hi, int nr, int lane, int j) {
+AS_FN_DOWNDATE void as_downdate(int Mo, int tmpo, int ms, int hi, int nr, int lane, int j) {
     extern __shared__ __align__(16) double as_smem[];
     double* M = as_smem + Mo;
     double* tmp = as_smem + tmpo;
@@ -283,7 +297,7 @@ static __device__ __noinline__ void as_downdate(int Mo, int tmpo, int ms, int hi
 // has lost its size relative to the original diagonal (diag0) marks a row that depends on the rows before it: it is
 // skipped, and its row and column are cleared at the end, which leaves the inverse over the remaining rows.
 // Returns the mask of skipped rows.
-static __device__ __noinline__ unsigned as_invert(int Mo, int ms, int nc, int hi, int lane, double diag0) {
+AS_FN_INVERT unsigned as_invert(int Mo, int ms, int nc, int hi, int lane, double diag0) {
     extern __shared__ __align__(16) double as_smem[];
     double* M = as_smem + Mo;
     unsigned dead = 0;

@@ -56,7 +56,11 @@ __host__ __device__ __forceinline__ void philox_mulhilo(uint32_t a, uint32_t b, 
 __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                           uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
+#ifndef RTMPC_PHILOX_UNROLL
+#define RTMPC_PHILOX_UNROLL 1      // rolled rounds: instruction footprint of the rollout kernel
+#endif
+    constexpr int kPhiloxUnroll = RTMPC_PHILOX_UNROLL;
+#pragma unroll kPhiloxUnroll
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         philox_mulhilo(M0, c0, hi0, lo0);

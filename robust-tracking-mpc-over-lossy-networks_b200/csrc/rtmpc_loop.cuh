@@ -170,7 +170,12 @@ __device__ __forceinline__ bool loop_step_begin(const LoopDev& L, const State S,
 // of this step's solve or NULL; theta_in < 0 selects the device RNG.
 // (no __restrict__: inside the rollout kernel these buffers are written by the same warp)
 // NX, NU > 0: sizes known at compile time (state in registers, loops unrolled); 0: taken from L.
-static __device__ __noinline__ Philox4 loop_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#ifdef RTMPC_AS_CALLS
+static __device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+Philox4 loop_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
     return philox4x32_10(c0, c1, c2, c3, k0, k1);
 }
 
