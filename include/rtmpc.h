@@ -153,7 +153,8 @@ int rtmpc_qp_solve(rtmpc_qp* qp, int32_t B, const double* d_x_init, const double
 int32_t rtmpc_qp_warm_stride(rtmpc_qp* qp);     /* int32 entries per instance of d_warm (npad + 1) */
 int32_t rtmpc_qp_rows(rtmpc_qp* qp);            /* rows the kernels work on (m padded to a multiple of 64) */
 const char* rtmpc_qp_rollout_kernel(rtmpc_qp* qp);  /* name of the kernel instantiation rtmpc_loop_rollout launches for this
-                                                   problem, e.g. "rollout_kernel<5,16>" (profiles, bench.py)          */
+                                                   problem, e.g. "rollout_kernel<5,16,*>" (profiles, bench.py); * = false /
+                                                   true: one problem / the extended controller's two              */
 
 /* Same call with HOST buffers: copies in, solves, copies out, synchronises.  This is the
  * reference-facing plugin call (numpy arrays in, numpy arrays out).  warm != 0 keeps the

@@ -655,7 +655,7 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
 // names P.  With a carry the warm start is the previous control step's working set AS IT IS, not moved one stage
 // earlier: M depends on the rows of the working set only, not on x_init, so the carried inverse is exact for it and the
 // solve starts with one mat-vec (multipliers at the new x_init) instead of |A| pivots.  Measured on the closed loops of
-// the benchmarks (profiles/r2_carried_inverse.md) the unmoved set is also the better guess: 2.0 rank-one changes per
+// the benchmarks (profiles/r2_rollout_ncu.md) the unmoved set is also the better guess: 2.0 rank-one changes per
 // constrained solve against 4.1 after moving the set (plus the 3.8 changes the move itself takes on a carried inverse).
 // The warm-start record is then used unmoved as well (first step of a ticket).  Results agree with the step-by-step
 // path to rounding, not bit for bit: the certificate is the same, but the certification refines the multipliers with M

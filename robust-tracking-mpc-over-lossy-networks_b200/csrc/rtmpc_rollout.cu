@@ -278,8 +278,9 @@ static const RoChoice* pick(int mpad) {
 }
 
 const char* rollout_kernel_name(const QPDev& P) {
-    static const char* names[] = {"rollout_kernel<2,24>", "rollout_kernel<5,16>", "rollout_kernel<9,16>", "rollout_kernel<12,16>",
-                                  "rollout_kernel<16,16>"};
+    // (the third template argument is true for ExtendedTubeTrackingMPC's pair of problems, false otherwise)
+    static const char* names[] = {"rollout_kernel<2,24,*>", "rollout_kernel<5,16,*>", "rollout_kernel<9,16,*>", "rollout_kernel<12,16,*>",
+                                  "rollout_kernel<16,16,*>"};
     const RoChoice* kc = pick(P.mpad);
     return kc ? names[kc - kRo] : "none";
 }

@@ -18,10 +18,10 @@ def line_of(fname, marker, nth=1):
 
 A = "rtmpc_as.cuh"
 marks = [("reductions / keys", A, "__device__ __forceinline__ unsigned long long as_key"),
-         ("mat-vec", A, "static __device__ __noinline__ double as_matvec"),
-         ("bordering", A, "static __device__ __noinline__ void as_border"),
-         ("down-date", A, "static __device__ __noinline__ void as_downdate"),
-         ("Gauss-Jordan inversion", A, "static __device__ __noinline__ unsigned as_invert"),
+         ("mat-vec", A, "double as_matvec(int Mo"),
+         ("bordering", A, "void as_border(int Mo"),
+         ("down-date", A, "void as_downdate(int Mo"),
+         ("Gauss-Jordan inversion", A, "unsigned as_invert(int Mo"),
          ("marks / misc", A, "__device__ __forceinline__ void as_mark"),
          ("GI: search + step logic", A, "__device__ __forceinline__ int as_gi("),
          ("GI: row streaming", A, "// row values move by  c W[p][:]"),
