@@ -11,17 +11,22 @@ Rules:
     package never does; it fails loudly when its CUDA library is missing.
   * Every function cites the reference file:line it follows.
 
-PARITY STATUS: **parity unpinned against Clarabel itself.**  The arithmetic of
-the reference lives in third-party packages (cvxpy>=1.4.1 -> clarabel, polytope
->=0.2.4, control>=0.9.3.post2, scipy linprog) of which only scipy is present in
-this image; the reference ships no tests, golden vectors or fixtures for the QP.
-What *does* pin this oracle:
-  * Darup-Teichrib ``k_star = 5 / 6 / 10`` for eps = 1e-1 / 1e-2 / 1e-3
-    ("Examples of Set Operations/Example of Approximation of mRPI_Darup.py":50-55);
-  * the run-time invariants of the example scripts (tube containment, x - x_hat in Z
-    when Theta_t = 1, exact estimate for the Pezzutto scheme, u in U);
-  * an independent solver cross-check of the QP oracle (scipy SLSQP / trust-constr
-    on the reference's un-condensed formulation) -- the QP is strictly convex in
-    (x, u, x_bar, u_bar) so its minimiser is unique and any solver converged well
-    below Clarabel's tol_gap=1e-7 reproduces Clarabel's answer to that tolerance.
+PARITY STATUS: **pinned to the reference's own code for everything but the numerical QP solver.**
+``oracle/refshim`` runs the reference's modules and scripts unmodified in the build container (stand-ins for the absent
+third-party packages ``polytope``, ``control``, ``cvxpy`` only); ``tests/golden/make_reference_fixtures.py`` writes
+``tests/golden/ref_*.npz`` from them; ``tests/test_reference_pin.py`` (CPU) holds the oracle to those fixtures and -
+where ``/root/reference`` exists - to the live modules; ``tests/test_gpu_reference.py`` holds the CUDA path to them.
+Rows of SURVEY 8(a):
+  * A1-A3, E1-E2 (actuators, estimators): reference classes themselves, integers bit-exact, floats to round-off;
+  * S1-S5 (support, Pontryagin difference, Rakovic, Darup, terminal set): the reference's ``utils_polytope`` functions
+    and the classes' ``setup_optimization`` on the stand-in set algebra; Darup ``k_star = 5 / 6 / 10`` as shipped;
+  * Q1, Q3-Q6 (problem statements, packets, class logic incl. the G2 quirk): the reference's
+    ``generate_optimization_problem`` / ``determine_packet`` / ``encapsulate`` executed unmodified, the stated problem
+    compared entry by entry with the oracle's;
+  * whole closed loops of configs 1-3 in the scripts' own call and random-number order.
+**Unpinned: Q2, Clarabel's floating-point answer** (cvxpy>=1.4.1 -> clarabel, absent: no wheel, no network).  The
+solver under the ``cvxpy`` stand-in is this oracle's interior-point method with a certified polish; the QPs are strictly
+convex in (x, u, x_bar, u_bar), so the minimiser Clarabel approximates to tol_gap = 1e-7 is the point the oracle and the
+CUDA kernels compute to round-off (every golden solution also carries an independent KKT / NNLS certificate and an SLSQP
+cross-check, ``tests/test_oracle_qp.py``).
 """
