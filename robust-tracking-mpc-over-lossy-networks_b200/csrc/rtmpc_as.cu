@@ -48,6 +48,7 @@ bool as_configure(const QPDev& P, int max_smem, int* wpb_out, size_t* smem_out, 
 
 cudaError_t as_launch(const QPDev& P, int wpb, size_t smem, int num_sms, const QPLaunch& a) {
     const AsChoice* kc = pick(P.mpad);
+    if (!kc || P.mpad != 64 * kc->r2) return cudaErrorInvalidValue;      // (the kernels take mpad = 64 * R2 as a constant)
     // spread the instances over all SMs first, then fill the warps of each CTA
     if (tuning().as_warps > 0 && tuning().as_warps < wpb) wpb = tuning().as_warps;   // RTMPC_TUNE_AS_WARPS
     int warps = balanced_warps(a.B, num_sms, wpb);

@@ -382,7 +382,8 @@ template <int R2, int ILP>
 __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask, ASSlot& sl, int lane,
                                      double (&e)[2 * R2], unsigned& actu, unsigned& actl, int max_steps,
                                      bool apply_only, ASCounters& cnt) {
-    const int npad = P.npad, n = P.n, mpad = P.mpad, ms = as_ms(P);
+    const int npad = P.npad, n = P.n, ms = as_ms(P);
+    constexpr int mpad = 64 * R2;          // (= P.mpad: rtmpc_qp_create pads the rows to the instantiation's 64 * R2)
     const unsigned slots = (1u << n) - 1u;          // n <= 30
     while (true) {
         int p = 0;
@@ -519,7 +520,8 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
 template <int R2, int ILP>
 __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned amask, ASSlot& sl, int lane,
                                           double (&e)[2 * R2], unsigned actu, unsigned actl, ASCounters& cnt) {
-    const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ms = as_ms(P);
+    const int n = P.n, npad = P.npad, nx = P.nx, ms = as_ms(P);
+    constexpr int mpad = 64 * R2;          // (= P.mpad)
     const bool occ = (amask >> lane) & 1u;
     const int hi = as_hi(amask);
     double ba = 0.0;
@@ -665,7 +667,8 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                                                  const double* ref, int* warm_inst, double* z_out_inst, int z_rows,
                                                  double* U_out_inst, ASCounters& cnt, int* carry = nullptr,
                                                  int carry_tag = 0) {
-    const int n = P.n, npad = P.npad, mpad = P.mpad, nx = P.nx, ms = as_ms(P);
+    const int n = P.n, npad = P.npad, nx = P.nx, ms = as_ms(P);
+    constexpr int mpad = 64 * R2;          // (= P.mpad)
     const double tolp = 1e-11 * P.sc_b;
     if (lane < nx) {
         w.xr()[lane] = x_init[lane];

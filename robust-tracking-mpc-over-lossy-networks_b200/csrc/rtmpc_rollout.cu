@@ -303,6 +303,7 @@ bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err) {
 cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, int wpb, int num_sms, int max_smem,
                            const RolloutArgs& a, cudaStream_t stream) {
     const RoChoice* kc = pick(P.mpad);
+    if (!kc || P.mpad != 64 * kc->r2 || (a.two && P1.mpad != P.mpad)) return cudaErrorInvalidValue;    // (rows padded by rtmpc_qp_create)
     if (wpb > kc->maxw) wpb = kc->maxw;
     const size_t per_warp = (size_t)rollout_warp_doubles(P, P1, a.two != 0) * sizeof(double);
     while (wpb > 1 && per_warp * wpb > (size_t)max_smem) --wpb;
