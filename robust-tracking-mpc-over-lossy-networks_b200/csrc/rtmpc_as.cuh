@@ -708,6 +708,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
     w.ctl()[0] = tolp;
     w.ictl()[2] = 0;
     w.ictl()[3] = 0;           // refactorisations so far
+    bool carry_started = false, cold = false;
     // A long sequence of bordering / downdating steps on a nearly dependent working set lets the explicit inverse
     // drift (seen as a wrong sign of kappa, a failed refinement, a contradiction that is none).  The cure is the warm
     // start's own procedure: start over from z_u with the CURRENT working set as the candidate list, inverted from
@@ -759,6 +760,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             if ((amask >> lane) & 1u) { sl.ra = w.act_row()[lane]; sl.sa = (double)w.act_sgn()[lane]; }
         }
         const bool on_carried = moved;
+        carry_started = carry_started || moved;
         carried = false;
         m_clean = false;
         // M starts empty
@@ -768,7 +770,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             int prow = -1;
             double psg = 1.0;
             if (first) {
-                const int wn = (warm_inst && (P.shift || carry)) ? warm_inst[0] : 0;
+                const int wn = (warm_inst && (P.shift || carry) && !cold) ? warm_inst[0] : 0;
                 if (lane < wn && lane < n) {
                     const int code = warm_inst[1 + lane];
                     const int row0 = code >> 1;
@@ -885,10 +887,20 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             if (c == 2 || refresh >= 12) { status = RTMPC_FALLBACK; w.ictl()[2] = (c == 2) ? 4 : 5; break; }
             w.ictl()[1] = cnt.steps;
         }
-        if (status == RTMPC_OPTIMAL || status == RTMPC_OPTIMAL_INACCURATE || cnt.steps >= max_steps) break;
+        if (status == RTMPC_OPTIMAL || status == RTMPC_OPTIMAL_INACCURATE) break;
         // a contradiction found a few steps after a fresh factorisation is believed; anything else starts over
         if (status == RTMPC_INFEASIBLE && cnt.steps - w.ictl()[0] <= 8) break;
-        if (w.ictl()[3] >= 4) { status = RTMPC_FALLBACK; break; }
+        if (cnt.steps >= max_steps || w.ictl()[3] >= 4) {
+            // out of steps or refactorisations.  A solve that started on a carried working set gets one more attempt, from
+            // the empty set with a fresh budget, before it is handed over: a carried start is then never worse than a cold one
+            if (!carry_started || cold) { if (status != RTMPC_INFEASIBLE || cnt.steps < max_steps) status = RTMPC_FALLBACK; break; }
+            cold = true;
+            cnt.steps = 0;
+            __syncwarp();
+            if (lane == 0) { w.ictl()[3] = 0; w.ctl()[0] = tolp; }
+            __syncwarp();
+            continue;
+        }
         if (lane == 0) w.ictl()[3] += 1;
         __syncwarp();
     }

@@ -710,6 +710,27 @@ int rtmpc_loop_rollout(rtmpc_loop* l, rtmpc_qp* q, rtmpc_qp* q1, int32_t T, cons
             CU(ipm_launch(qq->dev, qq->ipm_wpb, qq->ipm_smem, qq->num_sms, f));
             g_launches.fetch_add(1);
         }
+#ifdef RTMPC_AS_DEBUG
+        {   // development builds: which hand-overs did the interior-point kernel not solve either?
+            std::vector<int> st(B), pd(B), tt(B);
+            const int nx = l->dev.nx;
+            std::vector<double> xh((size_t)B * nx), rf((size_t)B * nx);
+            CU(cudaStreamSynchronize(s));
+            CU(cudaMemcpy(st.data(), l->r_status, B * sizeof(int), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(pd.data(), l->r_pending, B * sizeof(int), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(tt.data(), l->r_inst_t, B * sizeof(int), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(xh.data(), l->dev.x_hat, (size_t)B * nx * sizeof(double), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(rf.data(), l->r_ref, (size_t)B * nx * sizeof(double), cudaMemcpyDeviceToHost));
+            for (long long b = 0; b < B; ++b)
+                if (pd[b] && st[b] != RTMPC_OPTIMAL) {
+                    std::fprintf(stderr, "HANDOVER inst %lld t %d status %d xhat", b, tt[b], st[b]);
+                    for (int k = 0; k < nx; ++k) std::fprintf(stderr, " %.17g", xh[(size_t)b * nx + k]);
+                    std::fprintf(stderr, " ref");
+                    for (int k = 0; k < nx; ++k) std::fprintf(stderr, " %.17g", rf[(size_t)b * nx + k]);
+                    std::fprintf(stderr, "\n");
+                }
+        }
+#endif
     }
     l->t += T;
     return 0;
