@@ -295,6 +295,8 @@ def run_gpu_arm(args):
         _lib.set_tuning(_lib.TUNE_ROLLOUT_QUANTUM, args.rollout_quantum)
     if args.rollout_carry >= 0:
         _lib.set_tuning(_lib.TUNE_ROLLOUT_CARRY, args.rollout_carry)
+    if args.rollout_fixed_dims >= 0:
+        _lib.set_tuning(_lib.TUNE_ROLLOUT_FIXED_DIMS, args.rollout_fixed_dims)
     wl = WORKLOADS[args.workload]
     SEED = wl["seed"]
     mpc, Z = build_controller(extended=wl["extended"])
@@ -752,6 +754,8 @@ def main():
                     help="development: rtmpc_set_tuning(RTMPC_TUNE_ROLLOUT_QUANTUM) (-1 = the library's default)")
     ap.add_argument("--rollout-carry", type=int, default=-1, dest="rollout_carry",
                     help="development: rtmpc_set_tuning(RTMPC_TUNE_ROLLOUT_CARRY) (-1 = the library's default, 1)")
+    ap.add_argument("--rollout-fixed-dims", type=int, default=-1, dest="rollout_fixed_dims",
+                    help="development: rtmpc_set_tuning(RTMPC_TUNE_ROLLOUT_FIXED_DIMS) (-1 = the library's default, 1)")
     ap.add_argument("--instances", type=int, default=B_PER_GPU, help="closed-loop instances per GPU (BASELINE configs[1]: 4096; configs[2] = --workload c3 --instances 8192 on 8 GPUs, "
                          "configs[3] = --workload c4 --instances 32768 on 8 GPUs)")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"],

@@ -110,12 +110,17 @@ int         rtmpc_set_device(int device);
  *                               same KKT certificate either way, but the certification refines the multipliers with the
  *                               inverse as approximate inverse, so with 1 a rollout agrees with the step-by-step path
  *                               (rtmpc_qp_solve + rtmpc_loop_step) to rounding, with 0 bit for bit.
+ *   RTMPC_TUNE_ROLLOUT_FIXED_DIMS 1 (default): a single-problem rollout whose controller has the dimensions of the
+ *                               reference's cartpole study (nx = 4, nu = 1, N = 20, fixed initial state: 21 unknowns) runs the
+ *                               kernel instantiation that has those dimensions as compile-time constants.  0: the general
+ *                               instantiation.  Same arithmetic in the same order: identical bits.
  * A negative value restores the default.  rtmpc_get_tuning returns the value in force (-1: unknown knob).
  */
 #define RTMPC_TUNE_ROLLOUT_QUANTUM 0
 #define RTMPC_TUNE_ROLLOUT_WARPS   1
 #define RTMPC_TUNE_AS_WARPS        2
 #define RTMPC_TUNE_ROLLOUT_CARRY   3
+#define RTMPC_TUNE_ROLLOUT_FIXED_DIMS 4
 int     rtmpc_set_tuning(int32_t knob, int32_t value);
 int32_t rtmpc_get_tuning(int32_t knob);
 

@@ -55,6 +55,29 @@ constexpr int AS_STALL = 7;
 // per-warp shared memory, in doubles: M (one row per working-set slot), zu, z, v, coef, 16 parameters, slot lists
 // (2*npad ints).  Kept as small as possible: what the warps do not take is L1 for the shared tables, and
 // the L1 / shared split moves in steps (.., 100, 132, .. KB): 16 warps of the cartpole problem fit the 100 KB step.
+// Problem dimensions as the solver sees them: read from the problem description (ASDimsDyn, any problem) or compile-time
+// constants (ASDimsFix: the rollout kernel's instantiation for the reference's cartpole controller - offsets into the
+// per-warp shared memory become immediates, the short loops over nx / npad get constant trip counts; same arithmetic in
+// the same order, so the same bits).
+struct ASDimsDyn {
+    static constexpr bool kFixed = false;
+    static constexpr int kNx = 0, kNu = 0;
+    static __device__ __forceinline__ int n(const QPDev& P) { return P.n; }
+    static __device__ __forceinline__ int npad(const QPDev& P) { return P.npad; }
+    static __device__ __forceinline__ int nx(const QPDev& P) { return P.nx; }
+    static __device__ __forceinline__ int nu(const QPDev& P) { return P.nu; }
+    static __device__ __forceinline__ int N(const QPDev& P) { return P.N; }
+};
+template <int N_VARS, int NPAD, int NX, int NU, int HORIZON>
+struct ASDimsFix {
+    static constexpr bool kFixed = true;
+    static constexpr int kNx = NX, kNu = NU;
+    static __device__ __forceinline__ constexpr int n(const QPDev&) { return N_VARS; }
+    static __device__ __forceinline__ constexpr int npad(const QPDev&) { return NPAD; }
+    static __device__ __forceinline__ constexpr int nx(const QPDev&) { return NX; }
+    static __device__ __forceinline__ constexpr int nu(const QPDev&) { return NU; }
+    static __device__ __forceinline__ constexpr int N(const QPDev&) { return HORIZON; }
+};
 __host__ __device__ inline int as_ms(const QPDev& P) { return P.npad + 2; }
 __host__ __device__ inline int as_mrows(const QPDev& P) { return P.n; }      // one row per slot (<= n rows in the working set; the row stride is even)
 __host__ __device__ inline int as_warp_doubles(const QPDev& P) {
@@ -85,10 +108,11 @@ struct ASWarp {
     __device__ __forceinline__ int* ictl() const { return reinterpret_cast<int*>(base + mm + 5 * npad + 18); }
 };
 
+template <class D = ASDimsDyn>
 __device__ __forceinline__ ASWarp as_carve(double* base, const QPDev& P) {
     extern __shared__ __align__(16) double as_smem[];
     ASWarp w;
-    w.base = base; w.off = (int)(base - as_smem); w.npad = P.npad; w.mm = as_mrows(P) * as_ms(P);
+    w.base = base; w.off = (int)(base - as_smem); w.npad = D::npad(P); w.mm = D::n(P) * (D::npad(P) + 2);
     return w;
 }
 
@@ -360,10 +384,11 @@ __device__ __forceinline__ void as_mark(int lane, int row, int sgn, bool on, uns
 __device__ __forceinline__ int as_hi(unsigned amask) { return (35 - __clz(amask | 1u)) & ~3; }   // multiple of 4, covers amask
 
 // M and the slot lists of one warp back to "empty working set"
+template <class D>
 __device__ __forceinline__ void as_clear(ASWarp& w, const QPDev& P, int lane) {
-    const int npad = P.npad, ms = as_ms(P);
+    const int npad = D::npad(P), ms = D::npad(P) + 2;
     if (lane < npad) {
-        if (lane < as_mrows(P)) {
+        if (lane < D::n(P)) {
             double* row = w.M() + lane * ms;
 #pragma unroll 1
             for (int b = 0; b < npad; b += 2) *reinterpret_cast<double2*>(row + b) = make_double2(0.0, 0.0);
@@ -378,11 +403,11 @@ __device__ __forceinline__ void as_clear(ASWarp& w, const QPDev& P, int lane) {
 // only moves the row values (the row streaming code exists once).  Returns 0 when no row is violated by
 // more than tolp.
 // ILP = 2: two rows of W / three columns of G' per pass (more loads in flight, more registers)
-template <int R2, int ILP>
+template <int R2, int ILP, class D>
 __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask, ASSlot& sl, int lane,
                                      double (&e)[2 * R2], unsigned& actu, unsigned& actl, int max_steps,
                                      bool apply_only, ASCounters& cnt) {
-    const int npad = P.npad, n = P.n, ms = as_ms(P);
+    const int npad = D::npad(P), n = D::n(P), ms = D::npad(P) + 2;
     constexpr int mpad = 64 * R2;          // (= P.mpad: rtmpc_qp_create pads the rows to the instantiation's 64 * R2)
     const unsigned slots = (1u << n) - 1u;          // n <= 30
     while (true) {
@@ -497,7 +522,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 __syncwarp();                 // rv shares coef's storage: every lane is done streaming
                 if (lane < npad) w.rv()[lane] = rr;
                 __syncwarp();
-                as_border(w.Mo(), w.rvo(), ms, as_hi(amask | (1u << s)), as_mrows(P), lane, s, rr, kappa);
+                as_border(w.Mo(), w.rvo(), ms, as_hi(amask | (1u << s)), n, lane, s, rr, kappa);
                 if (lane == s) { sl.ra = p; sl.sa = sp; sl.lam = lam_p; w.act_row()[s] = p; w.act_sgn()[s] = (int)sp; }
                 as_mark(lane, p, (int)sp, true, actu, actl);
                 amask |= 1u << s;
@@ -508,7 +533,7 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
             // partial step: the blocking row leaves the working set
             AS_DBG(8, 1);
             as_mark(lane, w.act_row()[j1], w.act_sgn()[j1], false, actu, actl);
-            as_downdate(w.Mo(), w.vo(), ms, hi, as_mrows(P), lane, j1);
+            as_downdate(w.Mo(), w.vo(), ms, hi, n, lane, j1);
             amask &= ~(1u << j1);
             cnt.sq += na * na;
         }
@@ -517,10 +542,10 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
 
 // Certification on the working set.  Returns 0 when the KKT conditions hold, 1 when a row is still
 // violated (t holds exact values: go back to as_gi), 2 on a negative multiplier / no convergence.
-template <int R2, int ILP>
+template <int R2, int ILP, class D>
 __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned amask, ASSlot& sl, int lane,
                                           double (&e)[2 * R2], unsigned actu, unsigned actl, ASCounters& cnt) {
-    const int n = P.n, npad = P.npad, nx = P.nx, ms = as_ms(P);
+    const int n = D::n(P), npad = D::npad(P), nx = D::nx(P), ms = D::npad(P) + 2;
     constexpr int mpad = 64 * R2;          // (= P.mpad)
     const bool occ = (amask >> lane) & 1u;
     const int hi = as_hi(amask);
@@ -662,12 +687,12 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
 // The warm-start record is then used unmoved as well (first step of a ticket).  Results agree with the step-by-step
 // path to rounding, not bit for bit: the certificate is the same, but the certification refines the multipliers with M
 // as an approximate inverse, so the last bits follow M's history.
-template <int R2, int ILP>
+template <int R2, int ILP, class D = ASDimsDyn>
 __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int lane, const double* x_init,
                                                  const double* ref, int* warm_inst, double* z_out_inst, int z_rows,
                                                  double* U_out_inst, ASCounters& cnt, int* carry = nullptr,
                                                  int carry_tag = 0) {
-    const int n = P.n, npad = P.npad, nx = P.nx, ms = as_ms(P);
+    const int n = D::n(P), npad = D::npad(P), nx = D::nx(P), ms = D::npad(P) + 2;
     constexpr int mpad = 64 * R2;          // (= P.mpad)
     const double tolp = 1e-11 * P.sc_b;
     if (lane < nx) {
@@ -746,7 +771,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             __syncwarp();
             if (par_bad) { status = RTMPC_INFEASIBLE; break; }
             if (feasible_u) {                             // the unconstrained minimiser is feasible
-                if (carry && !m_clean) as_clear(w, P, lane);      // the empty working set is carried with an empty M
+                if (carry && !m_clean) as_clear<D>(w, P, lane);      // the empty working set is carried with an empty M
                 break;
             }
         }
@@ -764,7 +789,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
         carried = false;
         m_clean = false;
         // M starts empty
-        if (!moved) as_clear(w, P, lane);
+        if (!moved) as_clear<D>(w, P, lane);
         // ---- 1. candidates: the previous step's working set moved one stage (warm start), or the current one ----
         if (!moved) {
             int prow = -1;
@@ -844,7 +869,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                     break;
                 }
                 AS_DBG(9, 1);
-                as_downdate(w.Mo(), w.vo(), ms, hi, as_mrows(P), lane, lm.idx);
+                as_downdate(w.Mo(), w.vo(), ms, hi, n, lane, lm.idx);
                 amask &= ~(1u << lm.idx);
                 cnt.sq += na * na;
             }
@@ -870,7 +895,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
         w.ictl()[1] = -1;
 #pragma unroll 1
         for (int refresh = 0;; ++refresh) {
-            status = as_gi<R2, ILP>(P, w, amask, sl, lane, e, actu, actl, max_steps, apply, cnt);
+            status = as_gi<R2, ILP, D>(P, w, amask, sl, lane, e, actu, actl, max_steps, apply, cnt);
             apply = false;
             if (status == AS_STALL) {
                 status = RTMPC_FALLBACK;
@@ -882,7 +907,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                     continue;
                 }
             } else if (status != 0) break;
-            const int c = as_certify<R2, ILP>(P, w, amask, sl, lane, e, actu, actl, cnt);
+            const int c = as_certify<R2, ILP, D>(P, w, amask, sl, lane, e, actu, actl, cnt);
             if (c == 0) { status = (w.ctl()[0] > tolp) ? RTMPC_OPTIMAL_INACCURATE : RTMPC_OPTIMAL; break; }
             if (c == 2 || refresh >= 12) { status = RTMPC_FALLBACK; w.ictl()[2] = (c == 2) ? 4 : 5; break; }
             w.ictl()[1] = cnt.steps;
@@ -909,7 +934,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
     if (status != RTMPC_FALLBACK) {
         const bool has_sol = (status == RTMPC_OPTIMAL || status == RTMPC_OPTIMAL_INACCURATE);
         const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-        const int nu = P.nu, N = P.N;
+        const int nu = D::nu(P), N = D::N(P);
         const int nrow = (N + 1) * nu;
         if (U_out_inst) {
             // packet payload straight from the scaled decision: U = UPhi z + UPsi x_init, last column u_bar + K x_bar

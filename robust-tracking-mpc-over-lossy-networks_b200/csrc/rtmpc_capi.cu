@@ -105,6 +105,7 @@ int rtmpc_set_tuning(int32_t knob, int32_t value) {
         case RTMPC_TUNE_ROLLOUT_WARPS: t.rollout_warps = value < 0 ? 0 : value; return 0;
         case RTMPC_TUNE_AS_WARPS: t.as_warps = value < 0 ? 0 : value; return 0;
         case RTMPC_TUNE_ROLLOUT_CARRY: t.rollout_carry = value < 0 ? 1 : (value ? 1 : 0); return 0;
+        case RTMPC_TUNE_ROLLOUT_FIXED_DIMS: t.rollout_fixed_dims = value < 0 ? 1 : (value ? 1 : 0); return 0;
         default: return fail("rtmpc_set_tuning: unknown knob");
     }
 }
@@ -115,6 +116,7 @@ int32_t rtmpc_get_tuning(int32_t knob) {
         case RTMPC_TUNE_ROLLOUT_WARPS: return t.rollout_warps;
         case RTMPC_TUNE_AS_WARPS: return t.as_warps;
         case RTMPC_TUNE_ROLLOUT_CARRY: return t.rollout_carry;
+        case RTMPC_TUNE_ROLLOUT_FIXED_DIMS: return t.rollout_fixed_dims;
         default: return -1;
     }
 }

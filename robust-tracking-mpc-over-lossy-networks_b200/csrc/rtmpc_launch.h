@@ -39,6 +39,7 @@ struct Tuning {
     int rollout_warps = 0;      // warps per CTA of the rollout kernel; 0: automatic
     int as_warps = 0;           // cap on the warps per CTA of the active-set solve kernel; 0: automatic
     int rollout_carry = 1;      // 1: the rollout carries each instance's working set and its inverse from one control step to the next
+    int rollout_fixed_dims = 1; // 1: problems with the cartpole controller's dimensions run the instantiation that has them as constants
 };
 Tuning& tuning();
 

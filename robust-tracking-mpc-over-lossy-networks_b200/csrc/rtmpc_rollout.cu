@@ -33,6 +33,37 @@ __host__ __device__ inline int rollout_warp_doubles(const QPDev& P0, const QPDev
     return rollout_fixed_doubles(P0, P1, two) + (s0 > s1 ? s0 : s1);
 }
 
+// the same sizes inside the kernel, from the instantiation's dimensions (ASDimsFix: compile-time constants)
+template <class D, bool TWO>
+__device__ __forceinline__ int rollout_fixed_doubles_d(const QPDev& P0, const QPDev& P1) {
+    return loop_smem_doubles(D::N(P0), D::nu(P0)) + loop_even((D::N(P0) + 1) * D::nu(P0)) + loop_even(D::nx(P0)) +
+           ((((D::npad(P0) + 2) >> 1) + 1) & ~1) + (TWO ? ((((P1.npad + 2) >> 1) + 1) & ~1) : 0);
+}
+template <class D, bool TWO>
+__device__ __forceinline__ int rollout_warp_doubles_d(const QPDev& P0, const QPDev& P1) {
+    const int s0 = D::n(P0) * (D::npad(P0) + 2) + 5 * D::npad(P0) + 20;       // (= as_warp_doubles)
+    if (!TWO) return rollout_fixed_doubles_d<D, TWO>(P0, P1) + s0;            // (P1 == P0)
+    const int s1 = as_warp_doubles(P1);
+    return rollout_fixed_doubles_d<D, TWO>(P0, P1) + (s0 > s1 ? s0 : s1);
+}
+
+// closed-loop step and tube statistic: straight to the compile-time-sized versions when the instantiation fixes the sizes
+template <class D, class State>
+__device__ __forceinline__ double rollout_tube_rows(const LoopDev& L, const State S, int first, int stride) {
+    if constexpr (D::kFixed) return loop_tube_rows_t<D::kNx>(L, S, first, stride);
+    else return loop_tube_rows(L, S, first, stride);
+}
+template <class D, class State>
+__device__ __forceinline__ void rollout_step_warp(const LoopDev& L, const State S, int lane, int t, const double* Ub,
+                                                  const double* x_nom0_b, const double* ref_b, int theta_in, int gamma_in,
+                                                  const double* w_in_b, double p, unsigned long long seed,
+                                                  unsigned long long id, double* traj_b, double tube_worst) {
+    if constexpr (D::kFixed)
+        loop_step_body_warp_t<D::kNx, D::kNu>(L, S, lane, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
+    else
+        loop_step_warp(L, S, lane, t, Ub, x_nom0_b, ref_b, theta_in, gamma_in, w_in_b, p, seed, id, traj_b, tube_worst);
+}
+
 // P0: the controller's problem; P1: the "packet received" problem of ExtendedTubeTrackingMPC, chosen per step and
 // instance on gamma_{t-1} (TubeTrackingMPC.py:307-349); P1 == P0 for the single-problem controllers.
 // Hand-over of an instance between warps of different SMs.  Everything the previous owner wrote is read by the next one with
@@ -70,24 +101,27 @@ __device__ __forceinline__ int rollout_take_next(int* next, int lane) {
 // TWO = false: one problem (every controller but ExtendedTubeTrackingMPC).  The solver then reads the problem description
 // straight from the kernel's parameter bank (constant operands inside the instructions); with two problems every field
 // access is an indexed constant load into a register first - 1.2 % of the executed instructions plus their latency.
-template <int R2, int MAXW, bool TWO>
+// D: ASDimsDyn (any problem) or ASDimsFix (the problem's dimensions as compile-time constants; one problem only).
+template <int R2, int MAXW, bool TWO, class D>
 __global__ void RTMPC_RO_BOUNDS
 rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
+    static_assert(!(D::kFixed && TWO), "fixed dimensions: single-problem controllers only");
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    const int nx = P0.nx, nu = P0.nu;
-    const int usz = (P0.N + 1) * nu;
+    const int nx = D::nx(P0), nu = D::nu(P0);
+    const int usz = (D::N(P0) + 1) * nu;
+    const int npad0 = D::npad(P0);
     constexpr bool two = TWO;
-    double* wbase = smem + (size_t)warp * rollout_warp_doubles(P0, P1, two);
+    double* wbase = smem + warp * rollout_warp_doubles_d<D, TWO>(P0, P1);
     LoopSmemState S;
     S.base = wbase;
-    double* U_s = S.base + loop_smem_doubles(P0.N, nu);                  // this step's packet payload
+    double* U_s = S.base + loop_smem_doubles(D::N(P0), nu);              // this step's packet payload
     double* x0_s = U_s + loop_even(usz);                                  // x_nom[:,0] of this step's solve
     int* warm0_s = reinterpret_cast<int*>(x0_s + loop_even(nx));          // warm-start records
-    int* warm1_s = warm0_s + 2 * ((((P0.npad + 2) >> 1) + 1) & ~1);
-    double* scratch = wbase + rollout_fixed_doubles(P0, P1, two);
+    int* warm1_s = warm0_s + 2 * ((((npad0 + 2) >> 1) + 1) & ~1);
+    double* scratch = wbase + rollout_fixed_doubles_d<D, TWO>(P0, P1);
     const bool ext = L.actuator == RTMPC_ACT_EXTENDED;
 
     // Time slicing.  An instance is a chain of T dependent steps, so B chains on S warp slots take ceil(B / S) chain
@@ -146,7 +180,7 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
             S.buf()[i] = __ldcg(L.buf + (size_t)inst * usz + i);
             U_s[i] = __ldcg(a.U + (size_t)inst * usz + i);
         }
-        for (int i = lane; i < P0.npad + 1; i += 32) warm0_s[i] = __ldcg(a.warm + (size_t)inst * (P0.npad + 1) + i);
+        for (int i = lane; i < npad0 + 1; i += 32) warm0_s[i] = __ldcg(a.warm + (size_t)inst * (npad0 + 1) + i);
         if (two) for (int i = lane; i < P1.npad + 1; i += 32) warm1_s[i] = __ldcg(a.warm1 + (size_t)inst * (P1.npad + 1) + i);
         if (lane == 0) {
             S.err_acc() = __ldcg(L.err_acc + inst); S.tube_max() = __ldcg(L.tube_max + inst);
@@ -184,8 +218,8 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
                 cnt.steps = 0; cnt.rounds = 0; cnt.rows = 0; cnt.sq = 0;
                 const bool recv = two && S.gamma_last() == 1;           // gamma of the previous step
                 const QPDev& P = (two && recv) ? P1 : P0;
-                ASWarp w = as_carve(scratch, P);
-                status = as_solve_instance<R2, (MAXW * R2 <= 100) ? 2 : 1>(P, w, lane, &S.x_hat(0), ref_t,
+                ASWarp w = as_carve<D>(scratch, P);
+                status = as_solve_instance<R2, (MAXW * R2 <= 100) ? 2 : 1, D>(P, w, lane, &S.x_hat(0), ref_t,
                                                                          recv ? warm1_s : warm0_s, ext ? x0_s : nullptr,
                                                                          nx, U_s, cnt, a.carry ? S.ints() + 6 : nullptr,
                                                                          recv ? 2 : 1);
@@ -217,9 +251,9 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
             go = __shfl_sync(RTMPC_FULL_MASK, go, 0);
             if (go) {
                 double worst = 0.0;
-                if (L.nz_rows > 0) worst = as_wmax(loop_tube_rows(L, S, lane, 32));
+                if (L.nz_rows > 0) worst = as_wmax(rollout_tube_rows<D>(L, S, lane, 32));
                 const bool expl = a.theta != nullptr;
-                loop_step_warp(L, S, lane, t, U_s, ext ? x0_s : nullptr, ref_t,
+                rollout_step_warp<D>(L, S, lane, t, U_s, ext ? x0_s : nullptr, ref_t,
                                     expl ? a.theta[(size_t)k * a.B + inst] : -1, expl ? a.gamma[(size_t)k * a.B + inst] : -1,
                                     (expl && a.w) ? a.w + ((size_t)k * a.B + inst) * nx : nullptr, p, a.seed,
                                     (unsigned long long)(a.id_offset + inst), traj_b, worst);
@@ -237,7 +271,7 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
             L.buf[(size_t)inst * usz + i] = S.buf()[i];
             a.U[(size_t)inst * usz + i] = U_s[i];
         }
-        for (int i = lane; i < P0.npad + 1; i += 32) a.warm[(size_t)inst * (P0.npad + 1) + i] = warm0_s[i];
+        for (int i = lane; i < npad0 + 1; i += 32) a.warm[(size_t)inst * (npad0 + 1) + i] = warm0_s[i];
         if (two) for (int i = lane; i < P1.npad + 1; i += 32) a.warm1[(size_t)inst * (P1.npad + 1) + i] = warm1_s[i];
         if (lane == 0) {
             L.err_acc[inst] = S.err_acc(); L.tube_max[inst] = S.tube_max();
@@ -267,9 +301,21 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
 }
 
 typedef void (*ro_fn)(QPDev, QPDev, LoopDev, RolloutArgs);
-struct RoChoice { int r2, maxw; ro_fn fn[2]; };      // fn[1]: two problems
-#define RO_ENTRY(R2, W) {R2, W, {rollout_kernel<R2, W, false>, rollout_kernel<R2, W, true>}}
-static const RoChoice kRo[] = {RO_ENTRY(2, 24), RO_ENTRY(5, RTMPC_RO_MAXW5), RO_ENTRY(9, 16), RO_ENTRY(12, 16), RO_ENTRY(16, 16)};
+struct RoChoice { int r2, maxw; ro_fn fn[3]; };      // fn[1]: two problems; fn[2]: one problem with the cartpole controller's dimensions (or NULL)
+// the reference's cartpole controllers (results_linear_system.py / results_nonlinear_system.py): nx = 4, nu = 1, N = 20,
+// condensed problem with 21 unknowns (fixed initial state), rows padded to 320
+typedef ASDimsFix<21, 24, 4, 1, 20> RoCartpoleDims;
+#define RO_ENTRY(R2, W, FIX) {R2, W, {rollout_kernel<R2, W, false, ASDimsDyn>, rollout_kernel<R2, W, true, ASDimsDyn>, FIX}}
+static const RoChoice kRo[] = {RO_ENTRY(2, 24, nullptr), RO_ENTRY(5, RTMPC_RO_MAXW5, (rollout_kernel<5, RTMPC_RO_MAXW5, false, RoCartpoleDims>)),
+                               RO_ENTRY(9, 16, nullptr), RO_ENTRY(12, 16, nullptr), RO_ENTRY(16, 16, nullptr)};
+// the instantiation a launch uses: index into RoChoice::fn
+static int pick_fn(const RoChoice* kc, const QPDev& P, const LoopDev* L, bool two) {
+    if (two) return 1;
+    if (kc->fn[2] && tuning().rollout_fixed_dims && P.n == 21 && P.npad == 24 && P.nx == 4 && P.nu == 1 && P.N == 20 &&
+        (!L || (L->nx == 4 && L->nu == 1 && L->N == 20)))
+        return 2;
+    return 0;
+}
 static const RoChoice* pick(int mpad) {
     const int r_need = (mpad + 63) / 64;
     for (const auto& c : kRo)
@@ -282,13 +328,15 @@ const char* rollout_kernel_name(const QPDev& P) {
     static const char* names[] = {"rollout_kernel<2,24,*>", "rollout_kernel<5,16,*>", "rollout_kernel<9,16,*>", "rollout_kernel<12,16,*>",
                                   "rollout_kernel<16,16,*>"};
     const RoChoice* kc = pick(P.mpad);
+    if (kc && pick_fn(kc, P, nullptr, false) == 2) return "rollout_kernel<5,16,*,cartpole dims>";
     return kc ? names[kc - kRo] : "none";
 }
 
 bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err) {
     const RoChoice* kc = pick(P.mpad);
     if (!kc) { *err = cudaSuccess; return false; }
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 3; ++k) {
+        if (!kc->fn[k]) continue;
         *err = cudaFuncSetAttribute((const void*)kc->fn[k], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (*err != cudaSuccess) return false;
     }
@@ -320,11 +368,12 @@ cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, in
     int blocks = (a.B + warps - 1) / warps;
     if (blocks > num_sms) blocks = num_sms;
     const size_t smem = per_warp * warps;
+    const ro_fn fn = kc->fn[pick_fn(kc, P, &L, a.two != 0)];
     if (sliced) {
         int dev = 0, coop = 0, per_sm = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kc->fn[a.two ? 1 : 0], warps * 32, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, warps * 32, smem);
         if (e != cudaSuccess) return e;
         const long long fit = (long long)per_sm * num_sms;
         if (coop && fit >= 1) {
@@ -333,7 +382,7 @@ cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, in
             QPDev p0 = P, p1 = P1;
             LoopDev ld = L;
             void* args[] = {&p0, &p1, &ld, &b};
-            e = cudaLaunchCooperativeKernel((const void*)kc->fn[a.two ? 1 : 0], dim3(blocks), dim3(warps * 32), args, smem, stream);
+            e = cudaLaunchCooperativeKernel((const void*)fn, dim3(blocks), dim3(warps * 32), args, smem, stream);
             if (e == cudaSuccess) return cudaGetLastError();
             if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorNotSupported) return e;
             (void)cudaGetLastError();            // co-residency refused: fall through to whole chains
@@ -343,7 +392,7 @@ cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, in
         blocks = (a.B + warps - 1) / warps;
         if (blocks > num_sms) blocks = num_sms;
     }
-    kc->fn[a.two ? 1 : 0]<<<blocks, warps * 32, per_warp * warps, stream>>>(P, P1, L, b);
+    fn<<<blocks, warps * 32, per_warp * warps, stream>>>(P, P1, L, b);
     return cudaGetLastError();
 }
 

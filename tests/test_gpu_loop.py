@@ -364,3 +364,31 @@ def test_time_sliced_rollout_is_bit_identical_to_whole_chains(kind, step_cap):
         assert st_big[:4].sum() == B * T or kind == "extended"
     finally:
         mpc._prob.set_step_cap(0)
+
+
+@pytest.mark.parametrize("plant", ["linear", "cartpole"])
+def test_fixed_dimension_instantiation_is_bit_identical_to_the_general_one(plant):
+    """RTMPC_TUNE_ROLLOUT_FIXED_DIMS: the rollout kernel instantiated with the cartpole controller's dimensions as
+    compile-time constants does the same arithmetic in the same order as the general instantiation."""
+    import bench
+    from rtmpc_b200 import _lib
+    from rtmpc_b200.rollout import RemoteLoop
+    mpc, Z = bench.build_controller(extended=False)
+    assert _lib.get_tuning(_lib.TUNE_ROLLOUT_FIXED_DIMS) == 1
+    B, T = 3000, 75
+    p = np.array([0.1 * (i % 10) for i in range(B)])
+    out = []
+    try:
+        for fixed in (1, 0):
+            _lib.set_tuning(_lib.TUNE_ROLLOUT_FIXED_DIMS, fixed)
+            loop = RemoteLoop(mpc, B, kind="tube", plant=plant, w_half=None if plant == "cartpole" else bench.HW, Z=Z)
+            loop.reset()
+            tr = loop.run(T, bench.REF, p_loss=p, seed=5, record=True).cpu().numpy()
+            out.append((tr, loop.x_hat.cpu().numpy(), loop.s_t.cpu().numpy(), loop.stats.cpu().numpy(),
+                        loop.tube_max.cpu().numpy(), mpc._prob.rollout_kernel))
+    finally:
+        _lib.set_tuning(_lib.TUNE_ROLLOUT_FIXED_DIMS, -1)
+    assert "cartpole dims" in out[0][5] and "cartpole dims" not in out[1][5]
+    for a, b in zip(out[0][:5], out[1][:5]):
+        assert np.array_equal(a, b)
+    assert out[0][3][:4].sum() == B * T
