@@ -5,6 +5,8 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 #define RTMPC_LOOP_KERNELS
@@ -516,22 +518,59 @@ int rtmpc_loop_create(const rtmpc_loop_desc* d, int32_t B, rtmpc_loop** out) {
             }
             if (mate[i] < 0) sym = false;
         }
+        // rows (one per facet, or one per pair of opposite facets: normal, h+, h-)
+        std::vector<double> Hh, hh;
+        const int per = sym ? 2 : 1;                    // bounds per row
         if (sym) {
-            std::vector<double> Hh, hh;
             for (int i = 0; i < nr; ++i)
                 if (mate[i] > i) {
                     Hh.insert(Hh.end(), d->Hz + (size_t)i * nx, d->Hz + (size_t)(i + 1) * nx);
                     hh.push_back(d->hz[i]);
                     hh.push_back(d->hz[mate[i]]);
                 }
-            L.nz_rows = nr / 2;
             L.tube_sym = 1;
-            rc |= lalloc(l, Hh.size(), &Hz, Hh.data());
-            rc |= lalloc(l, hh.size(), &hz, hh.data());
         } else {
-            rc |= lalloc(l, (size_t)nr * nx, &Hz, d->Hz);
-            rc |= lalloc(l, (size_t)nr, &hz, d->hz);
+            Hh.assign(d->Hz, d->Hz + (size_t)nr * nx);
+            hh.assign(d->hz, d->hz + nr);
         }
+        // Sorted by the distance of the facet from the origin, nearest first, and padded to whole blocks of 32 rows
+        // (one row per lane of the rollout kernel's warp).  A row's value a'd - h is at most |a| (|d| - h / |a|): once
+        // some row already seen is above that bound for every row still to come, the scan stops (tube_cut[b] = smallest
+        // distance and smallest |a| over the rows from block b on).  The maximum is the same, bit for bit: skipped rows
+        // cannot reach it.  For the cartpole tube (427 pairs) 3 of 14 blocks are read on average.
+        const int rows = (int)hh.size() / per;
+        std::vector<int> order(rows);
+        std::vector<double> key(rows), nrm(rows);
+        for (int r = 0; r < rows; ++r) {
+            double s2 = 0.0;
+            for (int k = 0; k < nx; ++k) s2 += Hh[(size_t)r * nx + k] * Hh[(size_t)r * nx + k];
+            nrm[r] = std::sqrt(s2);
+            const double hmin = sym ? std::min(hh[2 * r], hh[2 * r + 1]) : hh[r];
+            key[r] = nrm[r] > 0.0 ? hmin / nrm[r] : 1e300;
+            order[r] = r;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+        const int nb = (rows + 31) / 32, padded = nb * 32;
+        std::vector<double> Hs((size_t)padded * nx, 0.0), hs((size_t)padded * per, 1e300), cut((size_t)2 * (nb + 1));
+        for (int r = 0; r < rows; ++r) {
+            std::copy(Hh.begin() + (size_t)order[r] * nx, Hh.begin() + (size_t)(order[r] + 1) * nx, Hs.begin() + (size_t)r * nx);
+            for (int k = 0; k < per; ++k) hs[(size_t)r * per + k] = hh[(size_t)order[r] * per + k];
+        }
+        cut[2 * nb] = -1e300; cut[2 * nb + 1] = 1.0;          // (never read as a reason to stop)
+        double kmin = 1e300, nmin = 1e300;
+        for (int b = nb - 1; b >= 0; --b) {
+            for (int r = 32 * b; r < std::min(rows, 32 * (b + 1)); ++r) {
+                kmin = std::min(kmin, key[order[r]]);
+                nmin = std::min(nmin, nrm[order[r]]);
+            }
+            cut[2 * b] = kmin; cut[2 * b + 1] = nmin;
+        }
+        L.nz_rows = padded;
+        rc |= lalloc(l, Hs.size(), &Hz, Hs.data());
+        rc |= lalloc(l, hs.size(), &hz, hs.data());
+        double* cutd = nullptr;
+        rc |= lalloc(l, cut.size(), &cutd, cut.data());
+        L.tube_cut = cutd;
     }
     rc |= lalloc(l, (size_t)nx, &wh, d->w_half ? d->w_half : zeros.data());
     L.A = A; L.Bm = Bm; L.K = K; L.Kp = Kp; L.Hz = Hz; L.hz = hz; L.w_half = wh;

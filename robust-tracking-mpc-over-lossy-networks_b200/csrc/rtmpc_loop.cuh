@@ -25,6 +25,7 @@ struct LoopDev {
     int tube_sym;      // 1: the tube's facets come in pairs with opposite normals; Hz holds one normal per pair and hz the two
                        //    bounds (h+, h-) of the pair: value max(Hz d - h+, -Hz d - h-), one dot product for both facets
     const double *A, *Bm, *K, *Kp, *Hz, *hz, *w_half;
+    const double* tube_cut;   // [2 * (nz_rows / 32 + 1)] per block of 32 tube rows: smallest facet distance and smallest |normal| from that block on
     double cart[8];
     double *x, *x_nom, *x_hat, *buf, *u_last, *err_acc, *tube_max;
     int *q_t, *s_t, *Theta, *alive, *last_loss, *gamma_last;
@@ -145,6 +146,58 @@ __device__ __forceinline__ double loop_tube_rows_t(const LoopDev& L, const State
         if (acc > worst) worst = acc;          // (a compare and a select: FP64 fmax is a seven-instruction sequence)
     }
     return worst;
+}
+// The same statistic for one instance per warp (row 32 j + lane in trip j; the rows are sorted by the facet's distance
+// from the origin and padded to whole blocks, rtmpc_loop_create).  Every lane returns the maximum over its own rows; the
+// scan stops as soon as one lane holds a value no remaining row can reach (value of a row <= |a| (|d| - h / |a|)), so
+// the maximum over the lanes is the maximum over all rows, bit for bit.
+template <int NX, class State>
+__device__ __forceinline__ double loop_tube_rows_warp_t(const LoopDev& L, const State S, int lane) {
+    const int nx = NX ? NX : L.nx;
+    constexpr int AX = NX ? NX : LOOP_MAX_NX;
+    double d[AX];
+    double s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < AX; ++k) { d[k] = (k < nx) ? S.x(k) - S.x_nom(k) : 0.0; s2 = fma(d[k], d[k], s2); }
+    // |d| rounded up (single-precision root with a margin far above its error)
+    const double nd = (double)sqrtf((float)s2) * (1.0 + 1e-6) + 1e-30;
+    double worst = -1e300;
+    const bool sym = L.tube_sym != 0;
+    const double2* __restrict__ cut = reinterpret_cast<const double2*>(L.tube_cut);
+#pragma unroll 1
+    for (int i = lane, j = 1; i < L.nz_rows; i += 32, ++j) {
+        double acc = sym ? 0.0 : -__ldg(L.hz + i);
+        if (NX > 0 && (NX & 1) == 0) {
+            const double2* __restrict__ h2 = reinterpret_cast<const double2*>(L.Hz + i * NX);
+#pragma unroll
+            for (int k = 0; k < AX / 2; ++k) {
+                const double2 hh = __ldg(h2 + k);
+                acc = fma(hh.x, d[2 * k], acc);
+                acc = fma(hh.y, d[2 * k + 1], acc);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < AX; ++k) if (k < nx) acc = fma(__ldg(L.Hz + i * nx + k), d[k], acc);
+        }
+        if (sym) {
+            const double2 hh = __ldg(reinterpret_cast<const double2*>(L.hz) + i);
+            const double a1 = acc - hh.x, a2 = -acc - hh.y;
+            acc = (a1 > a2) ? a1 : a2;
+        }
+        if (acc > worst) worst = acc;
+        // rows from block j on: at most c.y * (|d| - c.x) when that is negative (c.x their smallest distance, c.y their
+        // smallest |a|); the margins are orders of magnitude above the rounding of a row value
+        const double2 c = __ldg(cut + j);
+        const double g = nd - c.x;
+        if (__any_sync(0xffffffffu, g < 0.0 && worst > fma(c.y * g, 1.0 - 1e-9, 1e-12))) break;
+    }
+    return worst;
+}
+template <class State>
+__device__ __forceinline__ double loop_tube_rows_warp(const LoopDev& L, const State S, int lane) {
+    if (L.nx == 4) return loop_tube_rows_warp_t<4>(L, S, lane);
+    if (L.nx == 2) return loop_tube_rows_warp_t<2>(L, S, lane);
+    return loop_tube_rows_warp_t<0>(L, S, lane);
 }
 template <class State>
 __device__ __forceinline__ double loop_tube_rows(const LoopDev& L, const State S, int first, int stride) {

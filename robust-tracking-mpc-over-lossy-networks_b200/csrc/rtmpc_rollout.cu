@@ -49,9 +49,9 @@ __device__ __forceinline__ int rollout_warp_doubles_d(const QPDev& P0, const QPD
 
 // closed-loop step and tube statistic: straight to the compile-time-sized versions when the instantiation fixes the sizes
 template <class D, class State>
-__device__ __forceinline__ double rollout_tube_rows(const LoopDev& L, const State S, int first, int stride) {
-    if constexpr (D::kFixed) return loop_tube_rows_t<D::kNx>(L, S, first, stride);
-    else return loop_tube_rows(L, S, first, stride);
+__device__ __forceinline__ double rollout_tube_rows(const LoopDev& L, const State S, int lane) {
+    if constexpr (D::kFixed) return loop_tube_rows_warp_t<D::kNx>(L, S, lane);
+    else return loop_tube_rows_warp(L, S, lane);
 }
 template <class D, class State>
 __device__ __forceinline__ void rollout_step_warp(const LoopDev& L, const State S, int lane, int t, const double* Ub,
@@ -251,7 +251,7 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
             go = __shfl_sync(RTMPC_FULL_MASK, go, 0);
             if (go) {
                 double worst = 0.0;
-                if (L.nz_rows > 0) worst = as_wmax(rollout_tube_rows<D>(L, S, lane, 32));
+                if (L.nz_rows > 0) worst = as_wmax(rollout_tube_rows<D>(L, S, lane));
                 const bool expl = a.theta != nullptr;
                 rollout_step_warp<D>(L, S, lane, t, U_s, ext ? x0_s : nullptr, ref_t,
                                     expl ? a.theta[(size_t)k * a.B + inst] : -1, expl ? a.gamma[(size_t)k * a.B + inst] : -1,

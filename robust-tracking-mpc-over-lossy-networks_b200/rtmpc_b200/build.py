@@ -32,7 +32,9 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        # RTMPC_NVCC_EXTRA: extra flags for development builds (e.g. "-DRTMPC_RO_MAXW5=20"); never set by the product
+        extra = os.environ.get("RTMPC_NVCC_EXTRA", "").split()
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)

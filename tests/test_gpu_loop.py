@@ -217,7 +217,9 @@ def test_fused_rollout_matches_golden_and_stepwise_bit_for_bit(carry):
                           record=True, fused=fused).cpu().numpy()
             out[fused] = (tr, loop.x_hat.cpu().numpy(), loop.x_nom.cpu().numpy(), loop.s_t.cpu().numpy(),
                           loop.q_t.cpu().numpy(), loop.Theta.cpu().numpy(), loop.err_acc.cpu().numpy(),
-                          loop.status_count.cpu().numpy())
+                          loop.status_count.cpu().numpy(),
+                          # tube statistic: the rollout's scan stops early (sorted facets), the step kernel reads every facet
+                          loop.tube_max.cpu().numpy())
         assert np.abs(out[True][0] - g[key + "_x"]).max() <= TOL
         assert np.abs(out[True][1] - g[key + "_x_hat"][:, -1]).max() <= TOL
         for a, b in zip(out[True], out[False]):
