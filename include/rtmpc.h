@@ -267,7 +267,9 @@ int rtmpc_loop_step(rtmpc_loop* loop, const double* d_U_t, const int32_t* d_stat
  *            d_ref[k*ref_stride_t + b*ref_stride_b + 0..nx)  (strides in doubles; 0 = shared)
  *   d_theta, d_gamma [T*B], d_w [T*B*nx]: explicit realisations, or NULL for the device RNG of
  *            rtmpc_loop_step (same counters, so a rollout equals T single steps bit for bit)
- *   d_traj_x [B*traj_stride] or NULL: x_t at d_traj_x[b*traj_stride + t*nx + :], t = 0..T
+ *   d_traj_x [B*traj_stride] or NULL: x_t at d_traj_x[b*traj_stride + t*nx + :], t = 0..T.  Device memory, or pinned
+ *            (mapped) host memory: the kernel then writes the trajectory through the bus while it runs and no copy
+ *            follows (RemoteLoop.run(..., out=pinned tensor); bench.py's e2e leg: 107 against 100 M solves/s staged)
  *   d_stats  [8] uint64 or NULL, accumulated: solves by status [4], interior-point iterations,
  *            active-set steps, certification rounds, algorithmic flops of the active-set method
  * Instances the active-set method hands over are solved by the interior-point kernel between

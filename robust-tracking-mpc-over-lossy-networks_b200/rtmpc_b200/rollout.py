@@ -168,7 +168,7 @@ class RemoteLoop:
         self.iters_total += torch.stack(((it & 0xFFF).sum(), ((it >> 12) & 0xFFF).sum(), ((it >> 24) & 0xF).sum()))
 
     def run(self, T, ref, p_loss=None, theta=None, gamma=None, w=None, seed=0, id_offset=0, record=False, stats=True,
-            fused=None):
+            fused=None, out=None):
         """T steps.  ``ref`` [nx], [T,nx] or [T,B,nx]; explicit arrays theta/gamma [T,B], w [T,B,nx] (host or
         device) or p_loss [B].  Returns the trajectory tensor [B,T+1,nx] when ``record``.
 
@@ -181,7 +181,7 @@ class RemoteLoop:
         if fused is None:
             fused = True
         if fused:
-            return self._run_fused(T, ref, p_loss, theta, gamma, w, seed, id_offset, record)
+            return self._run_fused(T, ref, p_loss, theta, gamma, w, seed, id_offset, record, out)
         ref = np.asarray(ref, float)
         if ref.ndim == 1:
             ref = np.broadcast_to(ref, (T, self.nx))
@@ -211,7 +211,7 @@ class RemoteLoop:
             p_loss = torch.as_tensor(np.asarray(p_loss, dtype=float))
         return p_loss.to(self.dev, torch.float64).reshape(-1).expand(self.B).contiguous()
 
-    def _run_fused(self, T, ref, p_loss, theta, gamma, w, seed, id_offset, record):
+    def _run_fused(self, T, ref, p_loss, theta, gamma, w, seed, id_offset, record, out=None):
         f64 = torch.float64
         recv = None
         if self.kind == "extended":
@@ -231,7 +231,16 @@ class RemoteLoop:
             st, sb = nx, 0
         else:
             st, sb = B * nx, nx
-        traj = torch.zeros(B, T + 1, nx, device=self.dev, dtype=f64) if record else None
+        if record and out is not None:
+            # caller's buffer [B, T+1, nx]: device memory, or PINNED host memory - the kernel then writes the trajectory
+            # through the bus while it runs (no device buffer, no copy afterwards); rows after an instance stops are left as they are
+            if out.dtype != f64 or tuple(out.shape) != (B, T + 1, nx) or not out.is_contiguous():
+                raise _lib.RtmpcError("out: contiguous float64 tensor [B, T+1, nx] expected")
+            if not (out.is_cuda or out.is_pinned()):
+                raise _lib.RtmpcError("out: device tensor or pinned host tensor expected")
+            traj = out
+        else:
+            traj = torch.zeros(B, T + 1, nx, device=self.dev, dtype=f64) if record else None
         if theta is not None:
             theta = torch.as_tensor(np.ascontiguousarray(theta), device=self.dev).to(torch.int32).contiguous()
             gamma = torch.as_tensor(np.ascontiguousarray(gamma), device=self.dev).to(torch.int32).contiguous()

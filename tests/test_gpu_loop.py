@@ -394,3 +394,25 @@ def test_fixed_dimension_instantiation_is_bit_identical_to_the_general_one(plant
     for a, b in zip(out[0][:5], out[1][:5]):
         assert np.array_equal(a, b)
     assert out[0][3][:4].sum() == B * T
+
+
+def test_rollout_records_into_a_pinned_host_buffer():
+    """run(..., record=True, out=pinned host tensor): the kernel writes the trajectory into host memory itself; same
+    bits as recording on the device and copying back."""
+    import bench
+    from rtmpc_b200 import _lib
+    from rtmpc_b200.rollout import RemoteLoop
+    mpc, Z = bench.build_controller(extended=False)
+    B, T = 2500, 60
+    p = np.array([0.1 * (i % 10) for i in range(B)])
+    loop = RemoteLoop(mpc, B, kind="tube", w_half=bench.HW, Z=Z)
+    loop.reset()
+    dev_tr = loop.run(T, bench.REF, p_loss=p, seed=3, record=True).cpu()
+    host = torch.full((B, T + 1, 4), float("nan"), dtype=torch.float64).pin_memory()
+    loop.reset()
+    ret = loop.run(T, bench.REF, p_loss=p, seed=3, record=True, out=host)
+    torch.cuda.synchronize()
+    assert ret is host and torch.equal(host, dev_tr)
+    with pytest.raises(_lib.RtmpcError):
+        loop.reset()
+        loop.run(T, bench.REF, p_loss=p, seed=3, record=True, out=torch.zeros(B, T + 1, 4, dtype=torch.float64))   # pageable
