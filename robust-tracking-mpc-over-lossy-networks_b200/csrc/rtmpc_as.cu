@@ -55,7 +55,9 @@ cudaError_t as_launch(const QPDev& P, int wpb, size_t smem, int num_sms, const Q
     int blocks = (a.B + warps - 1) / warps;
     if (blocks > num_sms) blocks = num_sms;
     const size_t per_warp = (size_t)as_warp_doubles(P) * sizeof(double);
-    kc->fn<<<blocks, warps * 32, per_warp * warps, a.stream>>>(P, a.B, a.x_init, a.ref, a.sel, a.sel_value, a.z, a.U,
+    QPDev Pl = P;
+    if (!tuning().cert_factored) Pl.kap = nullptr;      // RTMPC_TUNE_CERT_FACTORED
+    kc->fn<<<blocks, warps * 32, per_warp * warps, a.stream>>>(Pl, a.B, a.x_init, a.ref, a.sel, a.sel_value, a.z, a.U,
                                                              a.status, a.iters, a.warm, a.work);
     return cudaGetLastError();
 }

@@ -157,8 +157,9 @@ __device__ __forceinline__ double2 ld2_hint(const double* p) {
 #endif
 __device__ __forceinline__ double2 ld2_stream(const double* p) { return ld2_hint<RTMPC_HINT_GT>(p); }
 
-// steps: rows added + dropped; rounds: certifications; rows: rows of W streamed; sq: sum of na^2 over the
-// small dense operations (mat-vec, bordering, downdate).  Algorithmic flops are derived from these.
+// steps: rows added + dropped; rounds: certifications; rows: passes over all m rows (rows of W streamed, columns of the
+// certification's tables); sq: sum of na^2 over the small dense operations (mat-vec, bordering, downdate) and 6 n^2 per
+// certification (refinement).  Algorithmic flops are derived from these: 2 m per row pass, 2 per unit of sq.
 // why (kept in ASWarp::ictl()[2]): last reason the Goldfarb-Idnani / certification pair gave up on a factorisation (diagnostics; 0 = never)
 //   1 step cap, 2 dependent row without a blocking multiplier and a tiny violation, 3 no free slot,
 //   4 certification failed (negative multiplier / refinement), 5 certification rounds, 6 contradiction late in a leg
@@ -167,8 +168,7 @@ struct ASCounters { int steps, rounds, rows, sq; };
 __device__ __forceinline__ unsigned long long as_flops(const QPDev& P, const ASCounters& c, bool with_z) {
     const unsigned long long n = P.n, m = P.m, nx = P.nx;
     unsigned long long f = 2ull * n * 2 * nx + 2ull * m * 4 * nx;                 // z_u, row values and bounds
-    f += 2ull * m * (unsigned long long)c.rows + 2ull * (unsigned long long)c.sq; // steps
-    f += (unsigned long long)c.rounds * (2ull * m * n + 12ull * n * n);            // certification: G z + refinement
+    f += 2ull * m * (unsigned long long)c.rows + 2ull * (unsigned long long)c.sq; // steps and certifications (as_certify adds its passes to rows / sq)
     f += 2ull * (with_z ? (unsigned long long)P.nz : (unsigned long long)((P.N + 1) * P.nu)) * (n + nx);
     return f;
 }
@@ -178,7 +178,6 @@ __device__ __forceinline__ unsigned long long as_flops_total(const QPDev& P, con
     const unsigned long long n = P.n, m = P.m, nx = P.nx;
     unsigned long long f = (unsigned long long)solves * (2ull * n * 2 * nx + 2ull * m * 4 * nx + 2ull * (unsigned long long)((P.N + 1) * P.nu) * (n + nx));
     f += 2ull * m * (unsigned long long)c.rows + 2ull * (unsigned long long)c.sq;
-    f += (unsigned long long)c.rounds * (2ull * m * n + 12ull * n * n);
     return f;
 }
 
@@ -605,7 +604,75 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
         // converged (every active row on its bound to well below the certificate's tolerance): stop refining
         if (!__any_sync(RTMPC_FULL_MASK, fabs(resid) > 1e-3 * w.ctl()[0])) break;      // (a vote: only the threshold matters)
     }
+    AS_DBG(11, 1);
     cnt.rounds += 1;
+    cnt.sq += 6 * n * n;                              // refinement
+    cnt.rows += 2 * nx + __popc(amask);               // factored row values
+    const double tolp = w.ctl()[0];
+    const double lmaxabs = as_wmax(occ ? fabs(lam) : 0.0);
+    // Row values at z.  First through the factored tables, e = Ex x + Tr r - up0 - W[:,A] (s lam): 2 nx columns and |A| rows
+    // that the solve has just read, against n + nx columns of G' and Ux streamed from L2.  The two differ by at most
+    // kap_i S (rounding of either evaluation and of the tables, P.kap); where every row outside the working set clears the
+    // tolerance by that bound the rows of G z are certified without being formed.  Otherwise - a row within the bound of
+    // the tolerance, or really violated - they are recomputed from G' z below and the decision is taken on those.
+    bool exact = true, violated = false;
+    if (P.kap) {                                      // (NULL: RTMPC_TUNE_CERT_FACTORED 0)
+        double S = 1.0 + (double)__popc(amask) * lmaxabs;
+#pragma unroll 1
+        for (int k = 0; k < nx; ++k) S += fabs(w.xr()[k]) + fabs(w.xr()[8 + k]);
+        S *= 1.0 + 1e-9;
+#pragma unroll
+        for (int r2 = 0; r2 < R2; ++r2) {
+            const double2 uu = ld2(P.upI + r2 * 64 + 2 * lane);
+            e[2 * r2] = -uu.x;
+            e[2 * r2 + 1] = -uu.y;
+        }
+#pragma unroll 1
+        for (int k = 0; k < nx; ++k) {
+            const double xk = w.xr()[k], rk = w.xr()[8 + k];
+            const size_t o = (size_t)k * mpad + 2 * lane;
+#pragma unroll
+            for (int r2 = 0; r2 < R2; ++r2) {
+                const double2 a = ld2_hint<RTMPC_HINT_SETUP>(P.ExT + o + r2 * 64), b = ld2_hint<RTMPC_HINT_SETUP>(P.TrT + o + r2 * 64);
+                e[2 * r2] = fma(b.x, rk, fma(a.x, xk, e[2 * r2]));
+                e[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, e[2 * r2 + 1]));
+            }
+        }
+        __syncwarp();
+        if (lane < npad) w.coef()[lane] = occ ? -sl.sa * lam : 0.0;
+        __syncwarp();
+#pragma unroll 1
+        for (unsigned mk = amask; mk;) {
+            const int a = __ffs(mk) - 1;
+            mk &= mk - 1;
+            const int a2 = mk ? __ffs(mk) - 1 : a;
+            const double ca = w.coef()[a], cb = mk ? w.coef()[a2] : 0.0;
+            mk &= mk - 1;
+            const double* __restrict__ Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
+            const double* __restrict__ Wb = P.W + (unsigned)(w.act_row()[a2] * mpad + 2 * lane);
+#pragma unroll
+            for (int r2 = 0; r2 < R2; ++r2) {
+                const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64), h = ld2_hint<RTMPC_HINT_W>(Wb + r2 * 64);
+                e[2 * r2] = fma(cb, h.x, fma(ca, g.x, e[2 * r2]));
+                e[2 * r2 + 1] = fma(cb, h.y, fma(ca, g.y, e[2 * r2 + 1]));
+            }
+        }
+        // (negated comparisons: a NaN counts as not cleared)
+        bool close = false;
+#pragma unroll
+        for (int r2 = 0; r2 < R2; ++r2) {
+            const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane), kp = ld2(P.kap + r2 * 64 + 2 * lane);
+            const double m0 = fma(kp.x, S, -tolp), m1 = fma(kp.y, S, -tolp);      // e + kap S <= tolp  <=>  e + m <= 0
+            close = close || (!((actu >> (2 * r2)) & 1u) && !(e[2 * r2] + m0 <= 0.0)) ||
+                    (!((actl >> (2 * r2)) & 1u) && !(-e[2 * r2] - wd.x + m0 <= 0.0)) ||
+                    (!((actu >> (2 * r2 + 1)) & 1u) && !(e[2 * r2 + 1] + m1 <= 0.0)) ||
+                    (!((actl >> (2 * r2 + 1)) & 1u) && !(-e[2 * r2 + 1] - wd.y + m1 <= 0.0));
+        }
+        exact = __any_sync(RTMPC_FULL_MASK, close);
+    }
+    if (exact) {
+    AS_DBG(10, 1);
+    cnt.rows += n + nx;
     // exact row values at z:  e = G z - up through the transposed copies (coalesced 16-byte loads)
 #pragma unroll
     for (int r2 = 0; r2 < R2; ++r2) {
@@ -654,8 +721,7 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
             }
         }
     }
-    // any row outside the working set violated by more than the tolerance?
-    const double tolp = w.ctl()[0];
+    // any row outside the working set violated by more than the tolerance?  (not after the factored values cleared it)
     bool viol = false;
 #pragma unroll
     for (int r2 = 0; r2 < R2; ++r2) {
@@ -664,8 +730,8 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
                (!((actu >> (2 * r2 + 1)) & 1u) && e[2 * r2 + 1] > tolp) ||
                (!((actl >> (2 * r2 + 1)) & 1u) && e[2 * r2 + 1] + wd.y < -tolp);
     }
-    const bool violated = __any_sync(RTMPC_FULL_MASK, viol);
-    const double lmaxabs = as_wmax(occ ? fabs(lam) : 0.0);
+    violated = __any_sync(RTMPC_FULL_MASK, viol);
+    }   // (exact rows)
     const bool bad = (fabs(resid) > tolp) ||                      // refinement did not converge
                      (occ && lam < -1e-9 * (1.0 + lmaxabs));     // a negative multiplier
     if (occ) sl.lam = fmax(lam, 0.0);

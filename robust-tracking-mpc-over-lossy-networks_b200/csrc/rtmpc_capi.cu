@@ -108,6 +108,7 @@ int rtmpc_set_tuning(int32_t knob, int32_t value) {
         case RTMPC_TUNE_AS_WARPS: t.as_warps = value < 0 ? 0 : value; return 0;
         case RTMPC_TUNE_ROLLOUT_CARRY: t.rollout_carry = value < 0 ? 1 : (value ? 1 : 0); return 0;
         case RTMPC_TUNE_ROLLOUT_FIXED_DIMS: t.rollout_fixed_dims = value < 0 ? 1 : (value ? 1 : 0); return 0;
+        case RTMPC_TUNE_CERT_FACTORED: t.cert_factored = value < 0 ? 1 : (value ? 1 : 0); return 0;
         default: return fail("rtmpc_set_tuning: unknown knob");
     }
 }
@@ -119,6 +120,7 @@ int32_t rtmpc_get_tuning(int32_t knob) {
         case RTMPC_TUNE_AS_WARPS: return t.as_warps;
         case RTMPC_TUNE_ROLLOUT_CARRY: return t.rollout_carry;
         case RTMPC_TUNE_ROLLOUT_FIXED_DIMS: return t.rollout_fixed_dims;
+        case RTMPC_TUNE_CERT_FACTORED: return t.cert_factored;
         default: return -1;
     }
 }
@@ -195,15 +197,22 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
             Zx[(size_t)j * nx + k] = ax;
             Zr[(size_t)j * nx + k] = ar;
         }
+    // Row values at z_u:  G z_u - up = (G Zx - Ux) x + (G Zr) r - up0 with the Zx, Zr the kernels compute z_u from
+    // (accumulated in long double, rounded once: the tables agree with G z to the last bit or two, which is what the
+    // certification's bound below relies on; -Y Fx would differ from G Zx by the rounding of Y = G Hinv, ~1e-7 here).
+    std::vector<double> kap(mpad, 0.0);
+    double zy_max = 0.0;
+    for (size_t i = 0; i < Zx.size(); ++i) zy_max = std::max(zy_max, std::max(std::fabs(Zx[i]), std::fabs(Zr[i])));
+    for (size_t i = 0; i < mn; ++i) zy_max = std::max(zy_max, std::fabs(Y[i]));
     for (int r = 0; r < mpad; ++r) {
         for (int k = 0; k < nx; ++k) {
-            double ax = 0.0, ar = 0.0;
+            long double ax = 0.0L, ar = 0.0L;
             for (int i = 0; i < npad; ++i) {
-                ax -= Y[(size_t)r * npad + i] * d->Fx[(size_t)i * nx + k];
-                ar -= Y[(size_t)r * npad + i] * d->Fr[(size_t)i * nx + k];
+                ax += (long double)G[(size_t)r * npad + i] * (long double)Zx[(size_t)i * nx + k];
+                ar += (long double)G[(size_t)r * npad + i] * (long double)Zr[(size_t)i * nx + k];
             }
-            ExT[(size_t)k * mpad + r] = ax - Ux[(size_t)r * nx + k];
-            TrT[(size_t)k * mpad + r] = ar;
+            ExT[(size_t)k * mpad + r] = (double)(ax - (long double)Ux[(size_t)r * nx + k]);
+            TrT[(size_t)k * mpad + r] = (double)ar;
             UxT[(size_t)k * mpad + r] = Ux[(size_t)r * nx + k];
             LxT[(size_t)k * mpad + r] = Lx[(size_t)r * nx + k];
         }
@@ -215,6 +224,34 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
         if (has_up[r] && has_lo[r])
             for (int k = 0; k < nx; ++k)
                 if (Lx[(size_t)r * nx + k] != Ux[(size_t)r * nx + k]) as_ok = false;   // ... and needs a constant width
+    }
+    // kap[i] (S = 1 + |x|_1 + |ref|_1 + sum |multipliers|):  | (G z - up)_i - (Ex x + Tr r - up0 - W[:,A] (s lam))_i | <= kap[i] S
+    // for the z and the factored row value the kernels compute - rounding of the two evaluations (at most 32 operations
+    // each on terms bounded by the row's largest table entry) plus what the stored tables differ by from G Zx - Ux,
+    // G Zr, G Y' (measured here in long double); doubled for margin.  as_certify accepts the factored values only where
+    // they clear the tolerance by this bound and recomputes the rows from G' z otherwise.
+    for (int r = 0; r < mpad; ++r) {
+        long double g1 = 0.0L, dmax = 0.0L;
+        double big = has_up[r] ? std::fabs(up0[r]) : 0.0;
+        for (int k = 0; k < npad; ++k) g1 += std::fabs((long double)G[(size_t)r * npad + k]);
+        for (int k = 0; k < nx; ++k) {
+            long double ax = 0.0L, ar = 0.0L;
+            for (int i = 0; i < npad; ++i) {
+                ax += (long double)G[(size_t)r * npad + i] * (long double)Zx[(size_t)i * nx + k];
+                ar += (long double)G[(size_t)r * npad + i] * (long double)Zr[(size_t)i * nx + k];
+            }
+            dmax = std::max(dmax, std::fabs(ax - (long double)Ux[(size_t)r * nx + k] - (long double)ExT[(size_t)k * mpad + r]));
+            dmax = std::max(dmax, std::fabs(ar - (long double)TrT[(size_t)k * mpad + r]));
+            big = std::max(big, std::max(std::fabs(ExT[(size_t)k * mpad + r]), std::fabs(TrT[(size_t)k * mpad + r])));
+        }
+        for (int a = 0; a < mpad; ++a) {
+            long double acc = 0.0L;          // effect on row r of a unit step along Y_a, as W[a][r] is read by the kernels
+            for (int k = 0; k < npad; ++k) acc += (long double)G[(size_t)r * npad + k] * (long double)Y[(size_t)a * npad + k];
+            dmax = std::max(dmax, std::fabs(acc - (long double)W[(size_t)a * mpad + r]));
+            big = std::max(big, std::fabs(W[(size_t)a * mpad + r]));
+        }
+        const long double u = 1.1102230246251566e-16L;      // 2^-53
+        kap[r] = (double)(2.0L * (64.0L * u * ((long double)big + g1 * (long double)zy_max) + dmax)) * (1.0 + 1e-9);
     }
     if (!as_ok) {
         delete q;
@@ -286,6 +323,7 @@ int rtmpc_qp_create(const rtmpc_qp_desc* d, rtmpc_qp** out) {
     rc |= upload(q, upI.data(), upI.size(), &P.upI);
     rc |= upload(q, loI.data(), loI.size(), &P.loI);
     rc |= upload(q, wid.data(), wid.size(), &P.wid);
+    rc |= upload(q, kap.data(), kap.size(), &P.kap);
     rc |= upload(q, UPhiT.data(), UPhiT.size(), &P.UPhiT);
     rc |= upload(q, UPsiT.data(), UPsiT.size(), &P.UPsiT);
     if (rc) { rtmpc_qp_destroy(q); return -1; }

@@ -42,6 +42,8 @@ struct QPDev {
     const double *UxT, *LxT; // [nx*mpad]    Ux, Lx transposed
     const double *upI, *loI; // [mpad]       up0 / lo0 with +-1e30 where the row has no such bound
     const double* wid;       // [mpad]       up - lo (independent of x_init), 3e30 where the row has no lower bound
+    const double* kap;       // [mpad]       bound per unit of (1 + |x|_1 + |ref|_1 + sum |multipliers|) on the difference between a
+                             //              row value from G' z and through the factored tables (rtmpc_qp_create)
     const int* Uidx;               // [(N+1)nu] or NULL: payload row i = Ucoef[i] * z[Uidx[i]] (every row of UPhi has one entry,
     const double* Ucoef;           //                    UPsi = 0: inputs are decision variables; else the dense maps below)
     const double *UPhiT, *UPsiT;   // [npad*(N+1)nu], [nx*(N+1)nu]  packet payload from the scaled decision:

@@ -40,6 +40,8 @@ struct Tuning {
     int as_warps = 0;           // cap on the warps per CTA of the active-set solve kernel; 0: automatic
     int rollout_carry = 1;      // 1: the rollout carries each instance's working set and its inverse from one control step to the next
     int rollout_fixed_dims = 1; // 1: problems with the cartpole controller's dimensions run the instantiation that has them as constants
+    int cert_factored = 1;      // 1: the certification accepts row values through the factored tables where they clear the tolerance by the
+                                //    rounding bound (QPDev::kap); 0: every certification forms the rows from G' z
 };
 Tuning& tuning();
 

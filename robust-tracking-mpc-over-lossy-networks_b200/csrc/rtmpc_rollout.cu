@@ -348,8 +348,10 @@ bool rollout_configure(const QPDev& P, int max_smem, cudaError_t* err) {
 // letting it hang when the grid cannot be co-resident: SM-limited MPS / green contexts) with the grid clamped to what
 // the occupancy calculator says fits; when the device or context cannot give that guarantee the rollout runs with
 // whole chains per warp (quantum 0: no cross-CTA waits, same results bit for bit).
-cudaError_t rollout_launch(const QPDev& P, const QPDev& P1, const LoopDev& L, int wpb, int num_sms, int max_smem,
+cudaError_t rollout_launch(const QPDev& P_in, const QPDev& P1_in, const LoopDev& L, int wpb, int num_sms, int max_smem,
                            const RolloutArgs& a, cudaStream_t stream) {
+    QPDev P = P_in, P1 = P1_in;
+    if (!tuning().cert_factored) { P.kap = nullptr; P1.kap = nullptr; }      // RTMPC_TUNE_CERT_FACTORED
     const RoChoice* kc = pick(P.mpad);
     if (!kc || P.mpad != 64 * kc->r2 || (a.two && P1.mpad != P.mpad)) return cudaErrorInvalidValue;    // (rows padded by rtmpc_qp_create)
     if (wpb > kc->maxw) wpb = kc->maxw;

@@ -28,7 +28,7 @@ EXPORTS = [
 OPTIMAL, MAX_ITER, INFEASIBLE, OPTIMAL_INACCURATE = 0, 1, 2, 3
 METHOD_ACTIVE_SET, METHOD_INTERIOR_POINT = 0, 1
 ABI_VERSION = 3
-TUNE_ROLLOUT_QUANTUM, TUNE_ROLLOUT_WARPS, TUNE_AS_WARPS, TUNE_ROLLOUT_CARRY, TUNE_ROLLOUT_FIXED_DIMS = 0, 1, 2, 3, 4
+TUNE_ROLLOUT_QUANTUM, TUNE_ROLLOUT_WARPS, TUNE_AS_WARPS, TUNE_ROLLOUT_CARRY, TUNE_ROLLOUT_FIXED_DIMS, TUNE_CERT_FACTORED = 0, 1, 2, 3, 4, 5
 ACT_SMART, ACT_CONSISTENT, ACT_EXTENDED = 0, 1, 2
 PLANT_LINEAR, PLANT_CARTPOLE = 0, 1
 
@@ -129,7 +129,7 @@ def check(rc, what=""):
 
 def set_tuning(knob, value):
     """Process-wide launch tuning (``rtmpc_set_tuning``): ``knob`` one of TUNE_ROLLOUT_QUANTUM / TUNE_ROLLOUT_WARPS /
-    TUNE_AS_WARPS / TUNE_ROLLOUT_CARRY / TUNE_ROLLOUT_FIXED_DIMS; a negative value restores the default.  Results never depend on it, except in
+    TUNE_AS_WARPS / TUNE_ROLLOUT_CARRY / TUNE_ROLLOUT_FIXED_DIMS / TUNE_CERT_FACTORED; a negative value restores the default.  Results never depend on it, except in
     the last bits for TUNE_ROLLOUT_CARRY (include/rtmpc.h)."""
     check(lib().rtmpc_set_tuning(int(knob), int(value)), "rtmpc_set_tuning")
 

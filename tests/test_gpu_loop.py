@@ -416,3 +416,28 @@ def test_rollout_records_into_a_pinned_host_buffer():
     with pytest.raises(_lib.RtmpcError):
         loop.reset()
         loop.run(T, bench.REF, p_loss=p, seed=3, record=True, out=torch.zeros(B, T + 1, 4, dtype=torch.float64))   # pageable
+
+
+def test_factored_certification_gives_the_same_closed_loops():
+    """RTMPC_TUNE_CERT_FACTORED: accepting the certification on row values through the factored tables (where they clear
+    the tolerance by the rounding bound) against forming the rows from G' z in every certification: same trajectories,
+    same status counts, fewer flops."""
+    import bench
+    from rtmpc_b200 import _lib
+    from rtmpc_b200.rollout import RemoteLoop
+    mpc, Z = bench.build_controller(extended=False)
+    B, T = 3000, 100
+    p = np.array([0.1 * (i % 10) for i in range(B)])
+    out = []
+    try:
+        for factored in (1, 0):
+            _lib.set_tuning(_lib.TUNE_CERT_FACTORED, factored)
+            loop = RemoteLoop(mpc, B, kind="tube", w_half=bench.HW, Z=Z)
+            loop.reset()
+            tr = loop.run(T, bench.REF, p_loss=p, seed=9, record=True).cpu().numpy()
+            out.append((tr, loop.x_hat.cpu().numpy(), loop.stats.cpu().numpy()))
+    finally:
+        _lib.set_tuning(_lib.TUNE_CERT_FACTORED, -1)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2][:7], out[1][2][:7])          # statuses, interior-point iterations, steps, certifications
+    assert out[0][2][7] < out[1][2][7]                            # algorithmic flops

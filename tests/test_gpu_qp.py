@@ -284,6 +284,15 @@ def test_cartpole_hard_cases_after_reference_jumps():
     ipm, steps, _ = qp.decode_iters(it)
     assert ipm.max() == 0, int((ipm > 0).sum())
     assert steps.max() <= 16 * 24 + 128
+    # every certification forced through the rows of G' z (RTMPC_TUNE_CERT_FACTORED 0): the factored row values only ever
+    # replace that pass where they clear the tolerance by the rounding bound, so statuses and solutions are the same bits
+    from rtmpc_b200 import _lib
+    try:
+        _lib.set_tuning(_lib.TUNE_CERT_FACTORED, 0)
+        z0, U0, st0, _ = qp.solve_host(g["x"], g["ref"])
+    finally:
+        _lib.set_tuning(_lib.TUNE_CERT_FACTORED, -1)
+    assert np.array_equal(st0, st) and np.array_equal(z0[ok], z[ok]) and np.array_equal(U0[ok], U[ok])
     # the interior-point kernel (the fallback) on its own: same statuses, certified by its endgame (more active rows
     # than unknowns at a degenerate vertex are thinned by the dependency-dropping factorisation)
     qp.set_method("interior_point")
