@@ -452,11 +452,10 @@ def run_gpu_arm(args):
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
                          "limiter": "no single roof, and neither arithmetic nor DRAM: in the committed ncu --set full capture of this launch "
-                                    "(profiles/r2_rollout_ncu.md section 5) the GPC-level instruction cache serves requests at 79 % of its peak "
-                                    "rate (gcc__cache_requests_type_instruction; SM instruction cache hit rate 80 %), the L1 data pipe runs at "
-                                    "63 % of its wavefront rate (142 KB of shared-table reads per solve + step, L1 hit 75 %, L2 hit 98.8 %), "
-                                    "issue slots are 38 % busy behind L2 latency with four warps per scheduler (128 registers), the FP64 pipe "
-                                    "is 16 % busy",
+                                    "(profiles/r2_rollout_ncu.md section 5) the GPC-level instruction cache serves requests at 83 % of its peak "
+                                    "rate (gcc__cache_requests_type_instruction; SM instruction cache hit rate 76 %), the L1 data pipe runs at "
+                                    "62 % of its wavefront rate (129 KB of shared-table reads per solve + step, L1 hit 96 %), issue slots are "
+                                    "39 % busy with four warps per scheduler (128 registers), the FP64 pipe is 16 % busy",
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure; "
                                         f"its hbm_gbs={peaks.get('hbm_gbs')}, bf16_tflops={peaks.get('bf16_tflops')})",
                          "algorithmic_flops_active_set": as_flops, "flops_per_ipm_iteration": f_it,
