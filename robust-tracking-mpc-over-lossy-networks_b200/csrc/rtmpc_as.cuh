@@ -641,20 +641,35 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
         __syncwarp();
         if (lane < npad) w.coef()[lane] = occ ? -sl.sa * lam : 0.0;
         __syncwarp();
+        if (ILP >= 2) {
 #pragma unroll 1
-        for (unsigned mk = amask; mk;) {
-            const int a = __ffs(mk) - 1;
-            mk &= mk - 1;
-            const int a2 = mk ? __ffs(mk) - 1 : a;
-            const double ca = w.coef()[a], cb = mk ? w.coef()[a2] : 0.0;
-            mk &= mk - 1;
-            const double* __restrict__ Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
-            const double* __restrict__ Wb = P.W + (unsigned)(w.act_row()[a2] * mpad + 2 * lane);
+            for (unsigned mk = amask; mk;) {
+                const int a = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const int a2 = mk ? __ffs(mk) - 1 : a;
+                const double ca = w.coef()[a], cb = mk ? w.coef()[a2] : 0.0;
+                mk &= mk - 1;
+                const double* __restrict__ Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
+                const double* __restrict__ Wb = P.W + (unsigned)(w.act_row()[a2] * mpad + 2 * lane);
 #pragma unroll
-            for (int r2 = 0; r2 < R2; ++r2) {
-                const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64), h = ld2_hint<RTMPC_HINT_W>(Wb + r2 * 64);
-                e[2 * r2] = fma(cb, h.x, fma(ca, g.x, e[2 * r2]));
-                e[2 * r2 + 1] = fma(cb, h.y, fma(ca, g.y, e[2 * r2 + 1]));
+                for (int r2 = 0; r2 < R2; ++r2) {
+                    const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64), h = ld2_hint<RTMPC_HINT_W>(Wb + r2 * 64);
+                    e[2 * r2] = fma(cb, h.x, fma(ca, g.x, e[2 * r2]));
+                    e[2 * r2 + 1] = fma(cb, h.y, fma(ca, g.y, e[2 * r2 + 1]));
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (unsigned mk = amask; mk; mk &= mk - 1) {
+                const int a = __ffs(mk) - 1;
+                const double ca = w.coef()[a];
+                const double* __restrict__ Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
+#pragma unroll
+                for (int r2 = 0; r2 < R2; ++r2) {
+                    const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64);
+                    e[2 * r2] = fma(ca, g.x, e[2 * r2]);
+                    e[2 * r2 + 1] = fma(ca, g.y, e[2 * r2 + 1]);
+                }
             }
         }
         // (negated comparisons: a NaN counts as not cleared)

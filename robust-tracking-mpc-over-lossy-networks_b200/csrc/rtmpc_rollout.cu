@@ -219,7 +219,12 @@ rollout_kernel(QPDev P0, QPDev P1, LoopDev L, RolloutArgs a) {
                 const bool recv = two && S.gamma_last() == 1;           // gamma of the previous step
                 const QPDev& P = (two && recv) ? P1 : P0;
                 ASWarp w = as_carve<D>(scratch, P);
-                status = as_solve_instance<R2, (MAXW * R2 <= 100) ? 2 : 1, D>(P, w, lane, &S.x_hat(0), ref_t,
+// rows of W / columns of G' per streaming pass.  One: the smaller loop bodies are worth more to the rollout kernel (instruction
+// fetch) than the extra loads in flight of two (116.4 -> 120.4 M solves/s on the benchmark; same FMA order, same bits)
+#ifndef RTMPC_RO_ILP
+#define RTMPC_RO_ILP 1
+#endif
+                status = as_solve_instance<R2, RTMPC_RO_ILP, D>(P, w, lane, &S.x_hat(0), ref_t,
                                                                          recv ? warm1_s : warm0_s, ext ? x0_s : nullptr,
                                                                          nx, U_s, cnt, a.carry ? S.ints() + 6 : nullptr,
                                                                          recv ? 2 : 1);
