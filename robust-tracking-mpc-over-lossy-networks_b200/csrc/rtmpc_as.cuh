@@ -81,7 +81,7 @@ struct ASDimsFix {
 __host__ __device__ inline int as_ms(const QPDev& P) { return P.npad + 2; }
 __host__ __device__ inline int as_mrows(const QPDev& P) { return P.n; }      // one row per slot (<= n rows in the working set; the row stride is even)
 __host__ __device__ inline int as_warp_doubles(const QPDev& P) {
-    return as_mrows(P) * as_ms(P) + 4 * P.npad + 16 + P.npad + 4;
+    return as_mrows(P) * as_ms(P) + 4 * P.npad + 16 + P.npad + 6;
 }
 
 // (offsets are added to one base pointer where they are used: nine live pointers would not stay in registers)
@@ -102,10 +102,12 @@ struct ASWarp {
     __device__ __forceinline__ int* act_row() const { return reinterpret_cast<int*>(base + mm + 4 * npad + 16); }
     __device__ __forceinline__ int* act_sgn() const { return act_row() + npad; }
     // rarely touched control state lives here rather than in registers: ctl()[0] the row tolerance in force,
-    // ctl()[1] violation of the row a stall happened on; ictl()[0] steps at the last factorisation, [1] steps at
+    // ctl()[1] violation of the row a stall happened on, ctl()[2] sum of the magnitudes of every coefficient applied to the row
+    // values since they were last evaluated from scratch (1e300: they no longer follow the multipliers; as_certify);
+    // ictl()[4] value of ASCounters::rows at that evaluation; ictl()[0] steps at the last factorisation, [1] steps at
     // the last exact row values, [2] why the solve last refactorised or gave up (ASCounters), [3] refactorisations
     __device__ __forceinline__ double* ctl() const { return base + mm + 5 * npad + 16; }
-    __device__ __forceinline__ int* ictl() const { return reinterpret_cast<int*>(base + mm + 5 * npad + 18); }
+    __device__ __forceinline__ int* ictl() const { return reinterpret_cast<int*>(base + mm + 5 * npad + 19); }
 };
 
 template <class D = ASDimsDyn>
@@ -471,6 +473,9 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 }
                 if (occ) sl.lam = (!full && lane == j1) ? 0.0 : fma(-step, rr, sl.lam);
                 lam_p += step;
+                // the row values move by  step (|1| W_p + sum_a |r_a| W_a)  at most; a step along a dependent row moves the
+                // multipliers but not the row values, which then no longer follow the multipliers exactly
+                if (lane == 0) w.ctl()[2] = dependent ? 1e300 : fma(step, 1.0 + (double)na * rmax, w.ctl()[2]);
                 cnt.sq += na * na;
                 if (lane < npad) w.coef()[lane] = occ ? step * sl.sa * rr : 0.0;
                 __syncwarp();
@@ -562,9 +567,11 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
     double zj = (lane < n) ? w.zu()[lane] : 0.0;
     // pass 0 starts from the multipliers the Goldfarb-Idnani steps arrived at (usually already within the certificate's
     // tolerance of the true rows: one pass instead of two), passes 1..3 refine with M as approximate inverse
+    bool refined = false;                            // multipliers moved away from the ones the row values were built with
 #pragma unroll 1
     for (int pass = 0; pass < 4; ++pass) {
         double dl;
+        refined = pass > 0;
         if (pass == 0) dl = occ ? sl.lam : 0.0;
         else {
             if (lane < npad) w.v()[lane] = resid;
@@ -607,87 +614,96 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
     AS_DBG(11, 1);
     cnt.rounds += 1;
     cnt.sq += 6 * n * n;                              // refinement
-    cnt.rows += 2 * nx + __popc(amask);               // factored row values
     const double tolp = w.ctl()[0];
     const double lmaxabs = as_wmax(occ ? fabs(lam) : 0.0);
-    // Row values at z.  First through the factored tables, e = Ex x + Tr r - up0 - W[:,A] (s lam): 2 nx columns and |A| rows
-    // that the solve has just read, against n + nx columns of G' and Ux streamed from L2.  The two differ by at most
-    // kap_i S (rounding of either evaluation and of the tables, P.kap); where every row outside the working set clears the
-    // tolerance by that bound the rows of G z are certified without being formed.  Otherwise - a row within the bound of
-    // the tolerance, or really violated - they are recomputed from G' z below and the decision is taken on those.
+    const int na = __popc(amask);
+    // Row values at z, in three tiers.  Every evaluation of a row differs from (G z - up)_i by rounding only, and the
+    // rounding is bounded:  kap_i S f,  kap from rtmpc_qp_create (rounding of one evaluation and of the tables, in long
+    // double), S = 1 + |x|_1 + |ref|_1 + the magnitudes of the coefficients that went into the value, f = 1 + (passes over
+    // the rows since the value was started from scratch) / 32.  A row outside the working set that clears the tolerance by
+    // its bound is certified without G z being formed.
+    //   tier 0: the values the Goldfarb-Idnani steps arrived at, e = e_u - sum of every step's W rows (nothing is read).
+    //           Only when the refinement left the multipliers where they were (one pass) and no step moved multipliers
+    //           without moving rows (ctl()[2] < 1e300).
+    //   tier 1: through the factored tables from scratch, e = Ex x + Tr r - up0 - W[:,A] (s lam): 2 nx columns and |A|
+    //           rows the solve has just read.
+    //   tier 2 (below): from G' z, n + nx columns streamed from L2 - when a row is within its bound of the tolerance, or
+    //           really violated; the decision is then taken on those values.
     bool exact = true, violated = false;
     if (P.kap) {                                      // (NULL: RTMPC_TUNE_CERT_FACTORED 0)
-        double S = 1.0 + (double)__popc(amask) * lmaxabs;
+        double S0 = 1.0;
 #pragma unroll 1
-        for (int k = 0; k < nx; ++k) S += fabs(w.xr()[k]) + fabs(w.xr()[8 + k]);
-        S *= 1.0 + 1e-9;
+        for (int k = 0; k < nx; ++k) S0 += fabs(w.xr()[k]) + fabs(w.xr()[8 + k]);
+        const double hist = w.ctl()[2];
+        const int since = cnt.rows - w.ictl()[4];
+#pragma unroll 1
+        for (int tier = (refined || !(hist < 1e299)) ? 1 : 0; tier < 2; ++tier) {
+            double S;
+            if (tier == 0) {
+                AS_DBG(12, 1);
+                S = (S0 + hist) * (1.0 + (double)since * 0.03125) * (1.0 + 1e-9);
+            } else {
+                AS_DBG(13, 1);
+                cnt.rows += 2 * nx + na;
+                S = (S0 + (double)na * lmaxabs) * (1.0 + 1e-9);
 #pragma unroll
-        for (int r2 = 0; r2 < R2; ++r2) {
-            const double2 uu = ld2(P.upI + r2 * 64 + 2 * lane);
-            e[2 * r2] = -uu.x;
-            e[2 * r2 + 1] = -uu.y;
-        }
+                for (int r2 = 0; r2 < R2; ++r2) {
+                    const double2 uu = ld2(P.upI + r2 * 64 + 2 * lane);
+                    e[2 * r2] = -uu.x;
+                    e[2 * r2 + 1] = -uu.y;
+                }
 #pragma unroll 1
-        for (int k = 0; k < nx; ++k) {
-            const double xk = w.xr()[k], rk = w.xr()[8 + k];
-            const size_t o = (size_t)k * mpad + 2 * lane;
+                for (int k = 0; k < nx; ++k) {
+                    const double xk = w.xr()[k], rk = w.xr()[8 + k];
+                    const size_t o = (size_t)k * mpad + 2 * lane;
+#pragma unroll
+                    for (int r2 = 0; r2 < R2; ++r2) {
+                        const double2 a = ld2_hint<RTMPC_HINT_SETUP>(P.ExT + o + r2 * 64), b = ld2_hint<RTMPC_HINT_SETUP>(P.TrT + o + r2 * 64);
+                        e[2 * r2] = fma(b.x, rk, fma(a.x, xk, e[2 * r2]));
+                        e[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, e[2 * r2 + 1]));
+                    }
+                }
+                __syncwarp();
+                if (lane < npad) w.coef()[lane] = occ ? -sl.sa * lam : 0.0;
+                __syncwarp();
+#pragma unroll 1
+                for (unsigned mk = amask; mk; mk &= mk - 1) {
+                    const int a = __ffs(mk) - 1;
+                    const double ca = w.coef()[a];
+                    const double* __restrict__ Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
+#pragma unroll
+                    for (int r2 = 0; r2 < R2; ++r2) {
+                        const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64);
+                        e[2 * r2] = fma(ca, g.x, e[2 * r2]);
+                        e[2 * r2 + 1] = fma(ca, g.y, e[2 * r2 + 1]);
+                    }
+                }
+            }
+            // (negated comparisons: a NaN counts as not cleared)
+            bool close = false;
 #pragma unroll
             for (int r2 = 0; r2 < R2; ++r2) {
-                const double2 a = ld2_hint<RTMPC_HINT_SETUP>(P.ExT + o + r2 * 64), b = ld2_hint<RTMPC_HINT_SETUP>(P.TrT + o + r2 * 64);
-                e[2 * r2] = fma(b.x, rk, fma(a.x, xk, e[2 * r2]));
-                e[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, e[2 * r2 + 1]));
+                const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane), kp = ld2(P.kap + r2 * 64 + 2 * lane);
+                const double m0 = fma(kp.x, S, -tolp), m1 = fma(kp.y, S, -tolp);      // e + kap S <= tolp  <=>  e + m <= 0
+                close = close || (!((actu >> (2 * r2)) & 1u) && !(e[2 * r2] + m0 <= 0.0)) ||
+                        (!((actl >> (2 * r2)) & 1u) && !(-e[2 * r2] - wd.x + m0 <= 0.0)) ||
+                        (!((actu >> (2 * r2 + 1)) & 1u) && !(e[2 * r2 + 1] + m1 <= 0.0)) ||
+                        (!((actl >> (2 * r2 + 1)) & 1u) && !(-e[2 * r2 + 1] - wd.y + m1 <= 0.0));
             }
+            exact = __any_sync(RTMPC_FULL_MASK, close);
+            if (!exact) break;
         }
-        __syncwarp();
-        if (lane < npad) w.coef()[lane] = occ ? -sl.sa * lam : 0.0;
-        __syncwarp();
-        if (ILP >= 2) {
-#pragma unroll 1
-            for (unsigned mk = amask; mk;) {
-                const int a = __ffs(mk) - 1;
-                mk &= mk - 1;
-                const int a2 = mk ? __ffs(mk) - 1 : a;
-                const double ca = w.coef()[a], cb = mk ? w.coef()[a2] : 0.0;
-                mk &= mk - 1;
-                const double* __restrict__ Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
-                const double* __restrict__ Wb = P.W + (unsigned)(w.act_row()[a2] * mpad + 2 * lane);
-#pragma unroll
-                for (int r2 = 0; r2 < R2; ++r2) {
-                    const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64), h = ld2_hint<RTMPC_HINT_W>(Wb + r2 * 64);
-                    e[2 * r2] = fma(cb, h.x, fma(ca, g.x, e[2 * r2]));
-                    e[2 * r2 + 1] = fma(cb, h.y, fma(ca, g.y, e[2 * r2 + 1]));
-                }
-            }
-        } else {
-#pragma unroll 1
-            for (unsigned mk = amask; mk; mk &= mk - 1) {
-                const int a = __ffs(mk) - 1;
-                const double ca = w.coef()[a];
-                const double* __restrict__ Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
-#pragma unroll
-                for (int r2 = 0; r2 < R2; ++r2) {
-                    const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64);
-                    e[2 * r2] = fma(ca, g.x, e[2 * r2]);
-                    e[2 * r2 + 1] = fma(ca, g.y, e[2 * r2 + 1]);
-                }
-            }
-        }
-        // (negated comparisons: a NaN counts as not cleared)
-        bool close = false;
-#pragma unroll
-        for (int r2 = 0; r2 < R2; ++r2) {
-            const double2 wd = ld2(P.wid + r2 * 64 + 2 * lane), kp = ld2(P.kap + r2 * 64 + 2 * lane);
-            const double m0 = fma(kp.x, S, -tolp), m1 = fma(kp.y, S, -tolp);      // e + kap S <= tolp  <=>  e + m <= 0
-            close = close || (!((actu >> (2 * r2)) & 1u) && !(e[2 * r2] + m0 <= 0.0)) ||
-                    (!((actl >> (2 * r2)) & 1u) && !(-e[2 * r2] - wd.x + m0 <= 0.0)) ||
-                    (!((actu >> (2 * r2 + 1)) & 1u) && !(e[2 * r2 + 1] + m1 <= 0.0)) ||
-                    (!((actl >> (2 * r2 + 1)) & 1u) && !(-e[2 * r2 + 1] - wd.y + m1 <= 0.0));
-        }
-        exact = __any_sync(RTMPC_FULL_MASK, close);
     }
     if (exact) {
     AS_DBG(10, 1);
     cnt.rows += n + nx;
+    // the rows are about to hold fresh values again, built with `lam`; multipliers clamped below (tiny negative ones) leave them
+    __syncwarp();
+    if (lane == 0) {
+        w.ctl()[2] = (double)na * lmaxabs;
+        w.ictl()[4] = cnt.rows;
+    }
+    if (__any_sync(RTMPC_FULL_MASK, occ && lam < 0.0) && lane == 0) w.ctl()[2] = 1e300;
     // exact row values at z:  e = G z - up through the transposed copies (coalesced 16-byte loads)
 #pragma unroll
     for (int r2 = 0; r2 < R2; ++r2) {
@@ -839,6 +855,8 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
                 e[2 * r2 + 1] = fma(b.y, rk, fma(a.y, xk, e[2 * r2 + 1]));
             }
         }
+        // (the row values start from scratch here: history of applied coefficients for as_certify)
+        if (lane == 0) { w.ctl()[2] = 0.0; w.ictl()[4] = cnt.rows; }
         int nc = 0;
         if (first) {
             // is any row on or beyond a bound?  (only the sign matters here: compares and a vote, no FP64 max chain)
@@ -957,6 +975,8 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             if (amask) {
                 const bool occ = (amask >> lane) & 1u;
                 if (lane < npad) w.coef()[lane] = occ ? -sl.sa * sl.lam : 0.0;
+                const double lw = as_wmax(occ ? sl.lam : 0.0);
+                if (lane == 0) w.ctl()[2] = (double)__popc(amask) * lw;
                 __syncwarp();
 #pragma unroll 1
                 for (unsigned mk = amask; mk; mk &= mk - 1) {

@@ -41,7 +41,7 @@ __device__ __forceinline__ int rollout_fixed_doubles_d(const QPDev& P0, const QP
 }
 template <class D, bool TWO>
 __device__ __forceinline__ int rollout_warp_doubles_d(const QPDev& P0, const QPDev& P1) {
-    const int s0 = D::n(P0) * (D::npad(P0) + 2) + 5 * D::npad(P0) + 20;       // (= as_warp_doubles)
+    const int s0 = D::n(P0) * (D::npad(P0) + 2) + 5 * D::npad(P0) + 22;       // (= as_warp_doubles)
     if (!TWO) return rollout_fixed_doubles_d<D, TWO>(P0, P1) + s0;            // (P1 == P0)
     const int s1 = as_warp_doubles(P1);
     return rollout_fixed_doubles_d<D, TWO>(P0, P1) + (s0 > s1 ? s0 : s1);

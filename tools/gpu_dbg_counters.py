@@ -33,7 +33,7 @@ L.rtmpc_debug_counters(buf, 0)
 c = list(buf)
 names = {0: "solves past the unconstrained test", 1: "carried", 2: "moved", 3: "changes", 5: "from-scratch inversions",
          6: "their candidates", 7: "GI adds", 8: "GI drops", 9: "warm multiplier drops", 10: "certifications that formed the rows from G' z",
-         11: "certifications"}
+         11: "certifications", 12: "tier 0 tried (accumulated row values)", 13: "tier 1 tried (factored tables)"}
 for k, v in names.items():
     print(f"[{k:2d}] {v:55s} {c[k]}")
 print("working-set size histogram:", c[16:48])
