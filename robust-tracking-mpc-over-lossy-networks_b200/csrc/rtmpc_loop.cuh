@@ -99,8 +99,9 @@ static __device__ __noinline__ void cartpole_substeps(double* x, double F, const
             ge += -I * om * (kd + kd * fabs(om)) + fpx * l * cs - fpz * l * sn;
         }
         const double D = (M + m) * (I + m * l * l) - (m * l * cs) * (m * l * cs);
-        const double acc = ((I + m * l * l) * fe - m * l * cs * ge) / D;
-        const double alp = ((M + m) * ge - m * l * cs * fe) / D;
+        const double iD = 1.0 / D;                      // (one division per sub-step; the oracle's two differ in the last bit)
+        const double acc = ((I + m * l * l) * fe - m * l * cs * ge) * iD;
+        const double alp = ((M + m) * ge - m * l * cs * fe) * iD;
         vel += dt * acc;
         om += dt * alp;
         pos += dt * vel;
