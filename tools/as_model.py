@@ -4,7 +4,9 @@ Goldfarb-Idnani dual active-set iteration on the scaled two-sided problem of
 ``rtmpc_b200.ipm_data.prepare``, on the operators shared by the whole batch
 (``Hinv``, ``Y = G Hinv``, ``W = G Hinv G'``), warm-started from the previous control step's
 active set moved one stage earlier, certified at the end by one round of the endgame
-(``ipm_model.polish_model``).  Mirrors ``csrc/rtmpc_as.cuh``.
+(``ipm_model.polish_model``).  Mirrors the control flow of ``csrc/rtmpc_as.cuh`` (steps, ratio tests, safeguards); the kernel's
+carried working set (rollout) and its tiered certification (row values accepted with a rounding bound before ``G' z`` is
+formed) are not modelled - the model always certifies on recomputed rows, which is the kernel's last tier.
 """
 import numpy as np
 
