@@ -98,6 +98,10 @@ struct ASWarp {
     __device__ __forceinline__ double* v() const { return base + mm + 2 * npad; }
     __device__ __forceinline__ double* coef() const { return base + mm + 3 * npad; }
     __device__ __forceinline__ double* rv() const { return base + mm + 3 * npad; }      // shares coef's storage
+    // list of the rows a streaming pass adds to the row values, 16 bytes each: coefficient, offset of the row in W (in doubles).
+    // Lives in v's and coef's storage (2 npad doubles = npad entries), which nothing else uses between the step's mat-vec and
+    // its bordering / down-date.
+    __device__ __forceinline__ double* lst() const { return base + mm + 2 * npad; }
     __device__ __forceinline__ double* xr() const { return base + mm + 4 * npad; }
     __device__ __forceinline__ int* act_row() const { return reinterpret_cast<int*>(base + mm + 4 * npad + 16); }
     __device__ __forceinline__ int* act_sgn() const { return act_row() + npad; }
@@ -400,6 +404,12 @@ __device__ __forceinline__ void as_clear(ASWarp& w, const QPDev& P, int lane) {
     __syncwarp();
 }
 
+__device__ __forceinline__ void as_list_put(const ASWarp& w, int k, double coef, int off) {
+    double* q = w.lst() + 2 * k;
+    q[0] = coef;
+    reinterpret_cast<int*>(q + 1)[0] = off;
+}
+
 // Goldfarb-Idnani iteration.  `apply_only`: the warm start left its multipliers in w.coef(); the first pass
 // only moves the row values (the row streaming code exists once).  Returns 0 when no row is violated by
 // more than tolp.
@@ -477,30 +487,38 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                 // multipliers but not the row values, which then no longer follow the multipliers exactly
                 if (lane == 0) w.ctl()[2] = dependent ? 1e300 : fma(step, 1.0 + (double)na * rmax, w.ctl()[2]);
                 cnt.sq += na * na;
-                if (lane < npad) w.coef()[lane] = occ ? step * sl.sa * rr : 0.0;
-                __syncwarp();
                 c = -step * sp;
+                // rows of this pass: the entering row, then the working set's in slot order (na < n here whenever the pass
+                // runs: at most n <= npad entries)
+                // (every lane is past the mat-vec that read v: the reductions behind it are warp-wide)
+                if (occ) as_list_put(w, 1 + __popc(amask & ((1u << lane) - 1u)), step * sl.sa * rr, sl.ra * mpad);
+                if (lane == 0) as_list_put(w, 0, c, p * mpad);
+                __syncwarp();
             }
             if (!dependent) {
-                // row values move by  c W[p][:] + sum_a coef_a W[row_a][:]; the entering row is paired with the first
-                // active row (ILP = 2: two rows per pass, twice the loads in flight)
-                double ca = c;
-                const double* __restrict__ Wa = Wp + 2 * lane;
-                unsigned mk = amask;
+                // row values move by  c W[p][:] + sum_a coef_a W[row_a][:]  (the list; the warm start's pass has no entering row)
+                const int nl = apply_only ? na : na + 1;
+                const double* __restrict__ lq = w.lst();
+                if (ILP >= 2) {
 #pragma unroll 1
-                while (true) {
-                    if (ILP >= 2) {
-                        const int a2 = mk ? __ffs(mk) - 1 : 0;
-                        const double cb = mk ? w.coef()[a2] : 0.0;
-                        const double* __restrict__ Wb = mk ? P.W + (unsigned)(w.act_row()[a2] * mpad + 2 * lane) : Wa;
-                        mk &= mk - 1;
+                    for (int k = 0; k < nl; k += 2) {
+                        const double ca = lq[2 * k];
+                        const double* __restrict__ Wa = P.W + (unsigned)(reinterpret_cast<const int*>(lq + 2 * k + 1)[0] + 2 * lane);
+                        const bool two = k + 1 < nl;
+                        const double cb = two ? lq[2 * k + 2] : 0.0;
+                        const double* __restrict__ Wb = two ? P.W + (unsigned)(reinterpret_cast<const int*>(lq + 2 * k + 3)[0] + 2 * lane) : Wa;
 #pragma unroll
                         for (int r2 = 0; r2 < R2; ++r2) {
                             const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64), h = ld2_hint<RTMPC_HINT_W>(Wb + r2 * 64);
                             e[2 * r2] = fma(cb, h.x, fma(ca, g.x, e[2 * r2]));
                             e[2 * r2 + 1] = fma(cb, h.y, fma(ca, g.y, e[2 * r2 + 1]));
                         }
-                    } else {
+                    }
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < nl; ++k) {
+                        const double ca = lq[2 * k];
+                        const double* __restrict__ Wa = P.W + (unsigned)(reinterpret_cast<const int*>(lq + 2 * k + 1)[0] + 2 * lane);
 #pragma unroll
                         for (int r2 = 0; r2 < R2; ++r2) {
                             const double2 g = ld2_hint<RTMPC_HINT_W>(Wa + r2 * 64);
@@ -508,14 +526,9 @@ __device__ __forceinline__ int as_gi(const QPDev& P, ASWarp& w, unsigned& amask,
                             e[2 * r2 + 1] = fma(ca, g.y, e[2 * r2 + 1]);
                         }
                     }
-                    if (!mk) break;
-                    const int a = __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    ca = w.coef()[a];
-                    Wa = P.W + (unsigned)(w.act_row()[a] * mpad + 2 * lane);
                 }
                 cp = fma(-step, kappa, cp);
-                cnt.rows += na + 1;
+                cnt.rows += nl;
             }
             if (apply_only) { apply_only = false; break; }
             if (full) {
@@ -974,7 +987,7 @@ __device__ __forceinline__ int as_solve_instance(const QPDev& P, ASWarp& w, int 
             }
             if (amask) {
                 const bool occ = (amask >> lane) & 1u;
-                if (lane < npad) w.coef()[lane] = occ ? -sl.sa * sl.lam : 0.0;
+                if (occ) as_list_put(w, __popc(amask & ((1u << lane) - 1u)), -sl.sa * sl.lam, sl.ra * mpad);      // as_gi's first pass
                 const double lw = as_wmax(occ ? sl.lam : 0.0);
                 if (lane == 0) w.ctl()[2] = (double)__popc(amask) * lw;
                 __syncwarp();
