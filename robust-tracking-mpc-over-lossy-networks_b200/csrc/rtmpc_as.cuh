@@ -592,19 +592,23 @@ __device__ __forceinline__ int as_certify(const QPDev& P, ASWarp& w, unsigned am
             dl = occ ? as_matvec(w.Mo(), ms, hi, lane, w.vo()) : 0.0;
         }
         lam += dl;
-        if (lane < npad) w.coef()[lane] = dl * sl.sa;
+        // z -= Y_A' (s dl): the rows of Y as a packed list (coefficient, offset), two per trip
+        __syncwarp();                                 // (the list lives in v's storage: every lane is past the mat-vec)
+        if (occ) as_list_put(w, __popc(amask & ((1u << lane) - 1u)), dl * sl.sa, sl.ra * npad);
         __syncwarp();
         if (lane < n) {
             double z2 = 0.0;
+            const int nl = __popc(amask);
+            const double* __restrict__ lq = w.lst();
+            const double* __restrict__ Yl = P.Y + lane;
 #pragma unroll 1
-            for (unsigned mk = amask; mk;) {
-                const int a = __ffs(mk) - 1;
-                mk &= mk - 1;
-                const int a2 = mk ? __ffs(mk) - 1 : a;
-                const double cb = mk ? w.coef()[a2] : 0.0;
-                mk &= mk - 1;
-                zj = fma(-w.coef()[a], P.Y[(size_t)w.act_row()[a] * npad + lane], zj);
-                z2 = fma(-cb, P.Y[(size_t)w.act_row()[a2] * npad + lane], z2);
+            for (int k = 0; k < nl; k += 2) {
+                const bool two = k + 1 < nl;
+                const double ca = lq[2 * k], cb = two ? lq[2 * k + 2] : 0.0;
+                const int oa = reinterpret_cast<const int*>(lq + 2 * k + 1)[0];
+                const int ob = two ? reinterpret_cast<const int*>(lq + 2 * k + 3)[0] : oa;
+                zj = fma(-ca, Yl[oa], zj);
+                z2 = fma(-cb, Yl[ob], z2);
             }
             zj += z2;
         }
