@@ -441,3 +441,32 @@ def test_factored_certification_gives_the_same_closed_loops():
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     assert np.array_equal(out[0][2][:7], out[1][2][:7])          # statuses, interior-point iterations, steps, certifications
     assert out[0][2][7] < out[1][2][7]                            # algorithmic flops
+
+
+@pytest.mark.parametrize("kind", ["tube", "extended"])
+def test_certification_tiers_under_reference_jumps(kind):
+    """The same equivalence where the rounding bounds matter: reference jumps that leave the feasible set nearly empty
+    (multipliers of 1e6, steps along dependent rows, solves that end OPTIMAL_INACCURATE or infeasible) - closed loops with the
+    tiered certification and with every certification forced through G' z agree bit for bit, status for status."""
+    import bench
+    from rtmpc_b200 import _lib
+    from rtmpc_b200.rollout import RemoteLoop
+    mpc, Z = bench.build_controller(extended=(kind == "extended"))
+    B, T = 1024, 800
+    jumps = [0.5, -0.8, 1.2, 0.0, 2.0, -1.5, 0.3, 1.0]
+    r = np.zeros((T, 4))
+    r[:, 0] = np.repeat(jumps, T // 8)
+    p = np.array([0.1 * (i % 10) for i in range(B)])
+    out = []
+    try:
+        for factored in (1, 0):
+            _lib.set_tuning(_lib.TUNE_CERT_FACTORED, factored)
+            loop = RemoteLoop(mpc, B, kind=kind, w_half=bench.HW, Z=Z)
+            loop.reset()
+            tr = loop.run(T, r, p_loss=p, seed=99, record=True).cpu().numpy()
+            out.append((tr, loop.x_hat.cpu().numpy(), loop.alive.cpu().numpy(), loop.stats.cpu().numpy()))
+    finally:
+        _lib.set_tuning(_lib.TUNE_CERT_FACTORED, -1)
+    assert np.array_equal(out[0][0], out[1][0], equal_nan=True) and np.array_equal(out[0][1], out[1][1], equal_nan=True)
+    assert np.array_equal(out[0][2], out[1][2])
+    assert np.array_equal(out[0][3][:7], out[1][3][:7])
