@@ -785,7 +785,7 @@ support_sweep_kernel(const double* __restrict__ V, int nv, int dim, const double
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long base = warp0 * (8 * RT); base < M; base += nwarps * (8 * RT)) {
-        double a[RT][KC], best0[RT], best1[RT];
+        double a[RT][KC];
 #pragma unroll
         for (int t = 0; t < RT; ++t) {
             const long long j = base + 8 * t + row;
@@ -794,10 +794,49 @@ support_sweep_kernel(const double* __restrict__ V, int nv, int dim, const double
                 const int k = kc * 4 + col;
                 a[t][kc] = (j < M && k < dim) ? dirs[j * dim + k] : 0.0;
             }
-            best0[t] = -RTMPC_INF;
-            best1[t] = -RTMPC_INF;
         }
+        // Running maxima as SIGNED 64-BIT INTEGERS on the bit patterns: for doubles >= 0 the integer order is the order of
+        // the values, and every negative double is a negative integer, i.e. below every non-negative one - so the integer
+        // maximum is the maximum whenever it is >= 0, which it is for a set that contains the origin (every set the tube
+        // pipeline sweeps).  The compares then run on the integer pipe instead of sharing the FP64 pipe with the DMMAs
+        // (DSETP: the kernel was limited by that pipe at 66 % DMMA utilisation).  A direction whose maximum comes out
+        // negative is redone with FP64 compares below.
+        long long k0[RT], k1[RT];
+#pragma unroll
+        for (int t = 0; t < RT; ++t) { k0[t] = (long long)0x8000000000000000ull; k1[t] = k0[t]; }
 #pragma unroll 2
+        for (int vt = 0; vt < nv8; vt += 8) {
+            double b[KC];
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) b[kc] = sv[(kc * nv8 + vt) * 4 + lane];
+#pragma unroll
+            for (int t = 0; t < RT; ++t) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) dmma884(c0, c1, a[t][kc], b[kc], c0, c1);
+                const long long i0 = __double_as_longlong(c0), i1 = __double_as_longlong(c1);
+                k0[t] = (i0 > k0[t]) ? i0 : k0[t];
+                k1[t] = (i1 > k1[t]) ? i1 : k1[t];
+            }
+        }
+        bool redo = false;
+#pragma unroll
+        for (int t = 0; t < RT; ++t) {
+            long long m = (k0[t] > k1[t]) ? k0[t] : k1[t];
+            long long o = __shfl_xor_sync(RTMPC_FULL_MASK, m, 1);
+            m = (o > m) ? o : m;
+            o = __shfl_xor_sync(RTMPC_FULL_MASK, m, 2);
+            m = (o > m) ? o : m;
+            const long long j = base + 8 * t + row;
+            if (j < M && m < 0) redo = true;
+            if (col == 0 && j < M) out[j] = __longlong_as_double(m);
+        }
+        if (!__any_sync(RTMPC_FULL_MASK, redo)) continue;
+        // (rare) some direction of this trip has a negative maximum: FP64 compares for the whole trip
+        double best0[RT], best1[RT];
+#pragma unroll
+        for (int t = 0; t < RT; ++t) { best0[t] = -RTMPC_INF; best1[t] = -RTMPC_INF; }
+#pragma unroll 1
         for (int vt = 0; vt < nv8; vt += 8) {
             double b[KC];
 #pragma unroll

@@ -72,3 +72,23 @@ def test_sweep_large_direction_count():
     dirs = rng.normal(size=(200000, 4))
     h = up.support_sweep(V, dirs)
     assert np.allclose(h, np.abs(dirs) @ np.array([1e-4, 2.7e-3, 3e-4, 4.3e-2]), rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("dim", [2, 4, 7, 13])
+def test_sweep_with_negative_maxima(dim):
+    """The sweep keeps its running maxima as signed integers on the bit patterns (right whenever the maximum is >= 0) and
+    redoes a trip with FP64 compares when a maximum comes out negative: vertex sets that do not contain the origin, so that
+    many directions have every <d, v> < 0; zeros and signed zeros among the products; every kernel instantiation (dim)."""
+    from rtmpc_b200 import sets as up
+    rng = np.random.default_rng(dim)
+    V = rng.uniform(2.0, 3.0, (37, dim))                     # a cloud far from the origin
+    V[5] = 0.0                                               # ... with the origin as one vertex in the second case
+    dirs = rng.standard_normal((5000, dim))
+    dirs[:50] = 0.0                                          # products are +0 / -0
+    dirs[50:100] = -np.abs(dirs[50:100])                     # every product negative (except with V[5])
+    for Vs in (np.delete(V, 5, axis=0), V):
+        h = up.support_sweep(Vs, dirs)
+        ref = (dirs @ Vs.T).max(axis=1)
+        assert (ref < 0).sum() > 40 or Vs.shape[0] == 37
+        assert np.abs(h - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+        assert np.array_equal(np.signbit(h[np.abs(ref) > 1e-9]), np.signbit(ref[np.abs(ref) > 1e-9]))
