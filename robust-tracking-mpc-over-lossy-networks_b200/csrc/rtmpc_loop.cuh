@@ -696,12 +696,15 @@ __device__ __forceinline__ void loop_step_body_warp_t(const LoopDev& L, const St
         out = (g == 1) ? acc + wi : acc;
         if (g == 0 && smart) out = S.x_nom(i);                // (no nominal model in Pezzutto's scheme)
     }
-    double xc[4] = {0.0, 0.0, 0.0, 0.0};
+    // (the array the plant routine works on lives in local memory: only inside the branch that needs it)
+    double xc0 = 0.0, xc1 = 0.0, xc2 = 0.0, xc3 = 0.0;
     const bool cart = L.plant == RTMPC_PLANT_CARTPOLE;
     if (NX == 4 && cart && lane == 0) {
+        double xc[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) xc[k] = x[k < NX ? k : 0];
         cartpole_substeps(xc, u[0], L.cart);
+        xc0 = xc[0]; xc1 = xc[1]; xc2 = xc[2]; xc3 = xc[3];
     }
     __syncwarp();
     // ---- write back -----------------------------------------------------------------------------------------
@@ -709,7 +712,7 @@ __device__ __forceinline__ void loop_step_body_warp_t(const LoopDev& L, const St
     else if (g == 1) { if (!cart) S.x(i) = out; }
     else if (g == 2) S.x_hat(i) = out;
     if (lane == 0) {
-        if (NX == 4 && cart) for (int k = 0; k < 4; ++k) S.x(k) = xc[k];
+        if (NX == 4 && cart) { S.x(0) = xc0; S.x(NX > 1 ? 1 : 0) = xc1; S.x(NX > 2 ? 2 : 0) = xc2; S.x(NX > 3 ? 3 : 0) = xc3; }
 #pragma unroll
         for (int j = 0; j < NU; ++j) S.u_last(j) = u[j];
         if (gamma == 1) S.q_t() = t;
