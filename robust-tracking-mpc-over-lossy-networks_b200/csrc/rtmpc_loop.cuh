@@ -82,6 +82,17 @@ struct LoopSmemState {
 // URDF_USE_INERTIA_FROM_FILE: m (0.05^2 + 1.0^2) / 12, cartpole.urdf:61-72) the model-error quantiles of
 // Results/estimate_W_for_Cartpole.py:79-127 land on the constants the reference hard-codes
 // (Results/results_linear_system.py:76-91) to within 0.5 % - see DESIGN.md section 7.
+static __device__ __noinline__ void cartpole_substeps(double* x, double F, const double* c);
+// The plant's parameters are read out of the kernel's parameter block element by element: taking the ADDRESS of a member of
+// a by-value kernel parameter (L.cart) makes the compiler keep a copy of the whole struct in local memory, and every later
+// L.field access of the kernel then reads that copy (12 local loads per control step of the rollout kernel).
+template <class LoopDevT>
+__device__ __forceinline__ void cartpole_substeps_of(const LoopDevT& L, double* x, double F) {
+    double cc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cc[k] = L.cart[k];
+    cartpole_substeps(x, F, cc);
+}
 static __device__ __noinline__ void cartpole_substeps(double* x, double F, const double* c) {
     const double M = c[0], m = c[1], I = c[2], g = c[3], l = c[4], dt = c[5], kd = c[7];
     const int nsub = (int)c[6];
@@ -325,7 +336,7 @@ static __device__ __noinline__ void loop_step_body_t(const LoopDev& L, const Sta
     double xnew[AX];
     if (L.plant == RTMPC_PLANT_CARTPOLE) {
         for (int k = 0; k < nx; ++k) xnew[k] = x[k];
-        cartpole_substeps(xnew, u[0], L.cart);
+        cartpole_substeps_of(L, xnew, u[0]);
     } else {
         for (int i = 0; i < nx; ++i) {
             double acc = 0.0;
@@ -550,7 +561,7 @@ __device__ __forceinline__ void loop_step_body_warp(const LoopDev& L, const Stat
     double xc[4] = {0.0, 0.0, 0.0, 0.0};
     if (L.plant == RTMPC_PLANT_CARTPOLE && lane == 0) {
         for (int k = 0; k < 4; ++k) xc[k] = S.x(k);
-        cartpole_substeps(xc, u[0], L.cart);
+        cartpole_substeps_of(L, xc, u[0]);
     }
     __syncwarp();
     // ---- write back -----------------------------------------------------------------------------------------
@@ -703,7 +714,7 @@ __device__ __forceinline__ void loop_step_body_warp_t(const LoopDev& L, const St
         double xc[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) xc[k] = x[k < NX ? k : 0];
-        cartpole_substeps(xc, u[0], L.cart);
+        cartpole_substeps_of(L, xc, u[0]);
         xc0 = xc[0]; xc1 = xc[1]; xc2 = xc[2]; xc3 = xc[3];
     }
     __syncwarp();
