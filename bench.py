@@ -452,10 +452,10 @@ def run_gpu_arm(args):
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
                          "limiter": "no single roof, and neither arithmetic nor DRAM: in the committed ncu --set full capture of this launch "
-                                    "(profiles/r2_rollout_ncu.md section 5) the GPC-level instruction cache serves requests at 83 % of its peak "
-                                    "rate (gcc__cache_requests_type_instruction; SM instruction cache hit rate 76 %), the L1 data pipe runs at "
-                                    "60 % of its wavefront rate (102 KB of shared-table reads per solve + step, L1 hit 97 %), issue slots are "
-                                    "40 % busy with four warps per scheduler (128 registers), the FP64 pipe is 15 % busy; the method needs "
+                                    "(profiles/r2_rollout_ncu.md section 5) the GPC-level instruction cache serves requests at 85 % of its peak "
+                                    "rate (gcc__cache_requests_type_instruction; SM instruction cache hit rate 74 %), the L1 data pipe runs at "
+                                    "62 % of its wavefront rate (102 KB of shared-table reads per solve + step, L1 hit 99 %), issue slots are "
+                                    "42 % busy with four warps per scheduler (128 registers), the FP64 pipe is 16 % busy; the method needs "
                                     "24 kflop per solve (round 1: 36), so frac moves less than the throughput",
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure; "
                                         f"its hbm_gbs={peaks.get('hbm_gbs')}, bf16_tflops={peaks.get('bf16_tflops')})",
