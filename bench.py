@@ -307,8 +307,6 @@ def run_gpu_arm(args):
     ref_d = torch.as_tensor(np.tile(REF, (B, 1)), device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)    # > 126 MB L2
     n, m = mpc._prob.n, mpc._prob.m
-    # the instantiation rtmpc_loop_rollout launches (from the library)
-    kernel_name = mpc._prob.rollout_kernel.replace("*", "true" if wl["extended"] else "false")
     f_it = ipm_flops_per_iteration(n, m)
     stream = torch.cuda.current_stream()
 
@@ -325,6 +323,9 @@ def run_gpu_arm(args):
     for wi in range(args.warmup):
         rollout(SEED + 1000 + wi)
     barrier()
+    # the instantiation rtmpc_loop_rollout launches (from the library; read after the first rollout: the extended controller's
+    # two problems are padded to a common row count when the loop first runs)
+    kernel_name = mpc._prob.rollout_kernel.replace("*", "true" if wl["extended"] else "false")
     fp64_peak = measure_fp64_peak(torch, dev) if rank == 0 else None
     # ---- timed region: K rollouts, device-timed, L2 flushed between them -------------------------
     launches_timed = 0          # our kernels launched between the timing events (the loop re-initialisation is outside them)
